@@ -1,0 +1,322 @@
+// api.cu -- context, workspace and the extern "C" entry points of libpicsong_b200.so.
+//
+// Replaces the orchestration the reference does in Engines/{Engine,CodingEngine,DecodingEngine}.cu:
+// LUT upload (Engine.cu:8-185), buffer allocation (CodingEngine.cu:119-199, DecodingEngine.cu:140-235)
+// and the per-frame stage order of runImage/runVideo (CodingEngine.cu:634-674,758-983;
+// DecodingEngine.cu:770-859,866-1043) -- minus its per-frame new/delete of stage objects, the
+// memsets, and the host synchronisation after every kernel.  A batch of frames goes through
+// DWT -> BPC -> bit-stream builder as 7 launches on one stream with no host round trip.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pcs_common.cuh"
+
+namespace pcs {
+
+unsigned long long g_launches = 0;
+
+size_t dwt_scratch_elems(int Wa, int Ha, int wl);
+int dwt_forward(const uint8_t*, void*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t);
+int dwt_inverse(const int32_t*, uint8_t*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t);
+int bpc_encode(const void*, bool, uint16_t*, int32_t*, const BpcArgs&, cudaStream_t);
+int bpc_decode(const uint16_t*, const int32_t*, int32_t*, const BpcArgs&, cudaStream_t);
+int export_ref_codestream(const uint16_t*, const int32_t*, int32_t*, long long, cudaStream_t);
+int bsb_pack(const uint16_t*, const int32_t*, uint16_t*, long long*, void*, const BsbArgs&, cudaStream_t);
+int bsb_unpack(const uint16_t*, const long long*, uint16_t*, int32_t*, void*, const BsbArgs&, cudaStream_t);
+size_t bsb_status_bytes(int ncb, int batch);
+
+}  // namespace pcs
+
+using namespace pcs;
+
+struct pcs_ctx {
+  pcs_params p;
+  int Wa, Ha, ncb;
+  size_t A, scratch_elems, max_words;
+  std::vector<int32_t> lut;
+  // device: probability tables
+  unsigned long long* d_sigp = nullptr; unsigned* d_sgnp = nullptr; unsigned char* d_refp = nullptr; int nrows = 0;
+  // device: workspace
+  void* d_scratch = nullptr;       // DWT LL ping-pong, [max_batch][scratch_elems] x 4 bytes
+  void* d_status = nullptr;        // look-back status words
+  uint8_t* d_px = nullptr;         // [max_batch][W*H]
+  int32_t* d_coeff = nullptr;      // [max_batch][A]
+  uint16_t* d_cw = nullptr;        // [max_batch][ncb][4096]
+  int32_t* d_sizes = nullptr;      // [max_batch][ncb]
+  uint16_t* d_stream = nullptr;    // [max_batch * max_words]
+  long long* d_off = nullptr;      // [max_batch + 1]
+  long long* h_off = nullptr;      // pinned
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool timing = false;
+  std::string err;
+};
+
+namespace {
+
+int fail(pcs_ctx* c, int code, const char* msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+BpcArgs bpc_args(const pcs_ctx* c, int batch) {
+  BpcArgs a{};
+  a.Wa = c->Wa; a.Ha = c->Ha; a.nbx = c->Wa / kCB; a.ncb = c->ncb; a.wl = c->p.wavelet_levels;
+  a.nBp = c->p.lut_header[0]; a.nSub = c->p.lut_header[1]; a.nrows = c->nrows; a.prec = c->p.lut_header[5];
+  a.total_cb = c->ncb * batch; a.A = (long long)c->A;
+  a.sigp = c->d_sigp; a.sgnp = c->d_sgnp; a.refp = c->d_refp;
+  return a;
+}
+
+BsbArgs bsb_args(const pcs_ctx* c, int batch, int first) {
+  BsbArgs a{};
+  a.ncb = c->ncb; a.batch = batch; a.first_frame_index = first;
+  uint16_t h[9];
+  pcs_header_pack(&c->p, h);
+  for (int i = 0; i < 9; ++i) a.hdr[i] = h[i];
+  return a;
+}
+
+// Packs the flat int32 table (ref | sig | sign sections, row = (lvl*nSub+sb)*nBp + bp) into per-row
+// registers-friendly words.  Rows past the table keep the reference's unguarded flat indexing
+// (BPCEngine.cu:329-350: MSB >= nBp walks into the next group / section); beyond the table -> 0.
+int build_prob_tables(pcs_ctx* c) {
+  const int32_t* h = c->p.lut_header;
+  const int nBp = h[0], nSub = h[1], cR = h[2], cG = h[3], cS = h[4], wl = c->p.wavelet_levels;
+  if (cR != 1 || cS < 1 || cS > 9 || cG < 1 || cG > 4 || nBp < 1 || nBp > 32 || nSub != 3 || h[5] < 1 || h[5] > 15)
+    return PCS_E_LUT_RANGE;
+  const int R = (nSub * wl + 1) * nBp * cR, S = (nSub * wl + 1) * nBp * cS;
+  const int n = (int)c->lut.size();
+  if (n < R + S + (nSub * wl + 1) * nBp * cG) return PCS_E_LUT;
+  const int nrows = (nSub * wl + 1) * nBp + 32;
+  std::vector<unsigned long long> sig(nrows, 0);
+  std::vector<unsigned> sgn(nrows, 0);
+  std::vector<unsigned char> ref(nrows, 0);
+  auto at = [&](long long i) -> int { return (i >= 0 && i < n) ? c->lut[(size_t)i] : 0; };
+  for (int r = 0; r < nrows; ++r) {
+    for (int k = 0; k < 9; ++k) {
+      const int v = k < cS ? at((long long)R + (long long)r * cS + k) : 0;
+      if (v < 0 || v > 127) return PCS_E_LUT_RANGE;
+      sig[r] |= (unsigned long long)v << (7 * k);
+    }
+    for (int k = 0; k < 4; ++k) {
+      const int v = k < cG ? at((long long)R + S + (long long)r * cG + k) : 0;
+      if (v < 0 || v > 127) return PCS_E_LUT_RANGE;
+      sgn[r] |= (unsigned)v << (7 * k);
+    }
+    const int v = at((long long)r * cR);
+    if (v < 0 || v > 127) return PCS_E_LUT_RANGE;
+    ref[r] = (unsigned char)v;
+  }
+  c->nrows = nrows;
+  PCS_CUDA_TRY(cudaMalloc(&c->d_sigp, nrows * sizeof(unsigned long long)));
+  PCS_CUDA_TRY(cudaMalloc(&c->d_sgnp, nrows * sizeof(unsigned)));
+  PCS_CUDA_TRY(cudaMalloc(&c->d_refp, nrows));
+  PCS_CUDA_TRY(cudaMemcpy(c->d_sigp, sig.data(), nrows * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  PCS_CUDA_TRY(cudaMemcpy(c->d_sgnp, sgn.data(), nrows * sizeof(unsigned), cudaMemcpyHostToDevice));
+  PCS_CUDA_TRY(cudaMemcpy(c->d_refp, ref.data(), nrows, cudaMemcpyHostToDevice));
+  return PCS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t pcs_create(const pcs_params* params, pcs_ctx** out) {
+  if (!params || !out) return PCS_E_ARG;
+  *out = nullptr;
+  const pcs_params& p = *params;
+  // Launcher.cu:132: "Incorrect parameters. Please choose valid values."
+  if (p.width <= 0 || p.height <= 0 || p.wavelet_levels < 1 || p.wavelet_levels > 10 || p.quant_size < 0 ||
+      p.quant_size > 1 || p.cb_width % 64 != 0 || p.cb_height < 18 || p.cb_height > 20 || p.coding_passes < 2 ||
+      p.coding_passes > 3 || p.k_factor < 0 || p.k_factor > 65.535f || p.max_batch < 1)
+    return PCS_E_ARG;
+  if (p.lossy && !(p.quant_size > 0)) return PCS_E_ARG;
+  if (p.coding_passes != 2 || p.k_factor != 0 || p.is_rgb || p.is_signed || p.components != 1 || p.bit_depth != 8)
+    return PCS_E_UNSUPPORTED;
+  if (!p.lut || p.lut_len <= 0) return PCS_E_LUT;
+  int Wa, Ha;
+  pcs_adapted_dims(p.width, p.height, &Wa, &Ha);
+  // every level input must have even size
+  if (((Wa >> (p.wavelet_levels - 1)) & 1) || ((Ha >> (p.wavelet_levels - 1)) & 1) || (Wa >> p.wavelet_levels) < 1 ||
+      (Ha >> p.wavelet_levels) < 1)
+    return PCS_E_ARG;
+  pcs_ctx* c = new (std::nothrow) pcs_ctx();
+  if (!c) return PCS_E_NOMEM;
+  c->p = p;
+  c->lut.assign(p.lut, p.lut + p.lut_len);
+  c->p.lut = c->lut.data();
+  c->Wa = Wa; c->Ha = Ha; c->A = (size_t)Wa * Ha; c->ncb = (Wa / kCB) * (Ha / kCB);
+  c->max_words = c->A + c->ncb + 10;
+  c->scratch_elems = dwt_scratch_elems(Wa, Ha, p.wavelet_levels);
+  const char* t = std::getenv("PCS_STAGE_TIMING");
+  c->timing = t && t[0] == '1';
+  int rc = build_prob_tables(c);
+  if (rc != PCS_OK) { pcs_destroy(c); return rc; }
+  const size_t B = (size_t)p.max_batch;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes ? bytes : 16); };
+  alloc(&c->d_scratch, B * (c->scratch_elems + 4) * 4);
+  alloc(&c->d_status, bsb_status_bytes(c->ncb, p.max_batch));
+  alloc((void**)&c->d_px, B * (size_t)p.width * p.height + 16);
+  alloc((void**)&c->d_coeff, B * c->A * 4);
+  alloc((void**)&c->d_cw, B * c->A * 2);
+  alloc((void**)&c->d_sizes, B * c->ncb * 4);
+  alloc((void**)&c->d_stream, B * c->max_words * 2);
+  alloc((void**)&c->d_off, (B + 1) * sizeof(long long));
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&c->h_off, (B + 1) * sizeof(long long), cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+  if (e != cudaSuccess) { pcs_destroy(c); return (int)e; }
+  *out = c;
+  return PCS_OK;
+}
+
+void pcs_destroy(pcs_ctx* c) {
+  if (!c) return;
+  cudaFree(c->d_sigp); cudaFree(c->d_sgnp); cudaFree(c->d_refp);
+  cudaFree(c->d_scratch); cudaFree(c->d_status); cudaFree(c->d_px); cudaFree(c->d_coeff); cudaFree(c->d_cw);
+  cudaFree(c->d_sizes); cudaFree(c->d_stream); cudaFree(c->d_off);
+  if (c->h_off) cudaFreeHost(c->h_off);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+  delete c;
+}
+
+const char* pcs_last_error(const pcs_ctx* c) { return c ? c->err.c_str() : "no context"; }
+size_t pcs_frame_pixels(const pcs_ctx* c) { return c->A; }
+int32_t pcs_frame_codeblocks(const pcs_ctx* c) { return c->ncb; }
+size_t pcs_frame_max_stream_words(const pcs_ctx* c) { return c->max_words; }
+uint64_t pcs_kernel_launch_count(void) { return g_launches; }
+
+#define CHECK_BATCH(c, batch) \
+  if (!(c)) return PCS_E_ARG; \
+  if ((batch) < 1 || (batch) > (c)->p.max_batch) return fail((c), PCS_E_BATCH, "batch exceeds max_batch")
+
+int32_t pcs_dwt_forward(pcs_ctx* c, const uint8_t* d_px, void* d_coeff, int32_t trunc, int32_t batch, void* st) {
+  CHECK_BATCH(c, batch);
+  return dwt_forward(d_px, d_coeff, c->d_scratch, c->p.width, c->p.height, c->Wa, c->Ha, c->p.wavelet_levels, c->p.lossy != 0,
+                     c->p.quant_size, trunc != 0, batch, (cudaStream_t)st);
+}
+
+int32_t pcs_dwt_inverse(pcs_ctx* c, const int32_t* d_q, uint8_t* d_px, int32_t batch, void* st) {
+  CHECK_BATCH(c, batch);
+  return dwt_inverse(d_q, d_px, c->d_scratch, c->p.width, c->p.height, c->Wa, c->Ha, c->p.wavelet_levels, c->p.lossy != 0,
+                     c->p.quant_size, (c->p.flags & PCS_F_REF_FLAT_CROP) != 0, batch, (cudaStream_t)st);
+}
+
+int32_t pcs_bpc_encode(pcs_ctx* c, const void* d_coeff, int32_t is_float, uint16_t* d_cw, int32_t* d_sizes, int32_t batch, void* st) {
+  CHECK_BATCH(c, batch);
+  return bpc_encode(d_coeff, is_float != 0, d_cw, d_sizes, bpc_args(c, batch), (cudaStream_t)st);
+}
+
+int32_t pcs_bpc_decode(pcs_ctx* c, const uint16_t* d_cw, const int32_t* d_sizes, int32_t* d_q, int32_t batch, void* st) {
+  CHECK_BATCH(c, batch);
+  return bpc_decode(d_cw, d_sizes, d_q, bpc_args(c, batch), (cudaStream_t)st);
+}
+
+int32_t pcs_bsb_pack(pcs_ctx* c, const uint16_t* d_cw, const int32_t* d_sizes, int32_t first, uint16_t* d_out, int64_t* d_off,
+                     int32_t batch, void* st) {
+  CHECK_BATCH(c, batch);
+  return bsb_pack(d_cw, d_sizes, d_out, reinterpret_cast<long long*>(d_off), c->d_status, bsb_args(c, batch, first), (cudaStream_t)st);
+}
+
+int32_t pcs_bsb_unpack(pcs_ctx* c, const uint16_t* d_in, const int64_t* d_off, uint16_t* d_cw, int32_t* d_sizes, int32_t batch, void* st) {
+  CHECK_BATCH(c, batch);
+  return bsb_unpack(d_in, reinterpret_cast<const long long*>(d_off), d_cw, d_sizes, c->d_status, bsb_args(c, batch, 1), (cudaStream_t)st);
+}
+
+int32_t pcs_export_ref_codestream(pcs_ctx* c, const uint16_t* d_cw, const int32_t* d_sizes, int32_t* d_ref, int32_t batch, void* st) {
+  CHECK_BATCH(c, batch);
+  return export_ref_codestream(d_cw, d_sizes, d_ref, (long long)c->A * batch, (cudaStream_t)st);
+}
+
+int32_t pcs_encode_device(pcs_ctx* c, const uint8_t* d_px, int32_t batch, int32_t first, uint16_t* d_stream, int64_t* d_off, void* stv) {
+  CHECK_BATCH(c, batch);
+  cudaStream_t st = (cudaStream_t)stv;
+  if (c->timing) cudaEventRecord(c->ev[0], st);
+  int rc = pcs_dwt_forward(c, d_px, c->d_coeff, 1, batch, st);  // 9/7: quantisation indices (int)c straight from the DWT
+  if (rc) return rc;
+  if (c->timing) cudaEventRecord(c->ev[1], st);
+  rc = pcs_bpc_encode(c, c->d_coeff, 0, c->d_cw, c->d_sizes, batch, st);
+  if (rc) return rc;
+  if (c->timing) cudaEventRecord(c->ev[2], st);
+  rc = pcs_bsb_pack(c, c->d_cw, c->d_sizes, first, d_stream, d_off, batch, st);
+  if (c->timing) cudaEventRecord(c->ev[3], st);
+  return rc;
+}
+
+int32_t pcs_decode_device(pcs_ctx* c, const uint16_t* d_stream, const int64_t* d_off, int32_t batch, uint8_t* d_px, void* stv) {
+  CHECK_BATCH(c, batch);
+  cudaStream_t st = (cudaStream_t)stv;
+  if (c->timing) cudaEventRecord(c->ev[0], st);
+  int rc = pcs_bsb_unpack(c, d_stream, d_off, c->d_cw, c->d_sizes, batch, st);
+  if (rc) return rc;
+  if (c->timing) cudaEventRecord(c->ev[1], st);
+  rc = pcs_bpc_decode(c, c->d_cw, c->d_sizes, c->d_coeff, batch, st);
+  if (rc) return rc;
+  if (c->timing) cudaEventRecord(c->ev[2], st);
+  rc = pcs_dwt_inverse(c, c->d_coeff, d_px, batch, st);
+  if (c->timing) cudaEventRecord(c->ev[3], st);
+  return rc;
+}
+
+int32_t pcs_last_stage_ms(pcs_ctx* c, float ms[3]) {
+  if (!c || !c->timing) return PCS_E_ARG;
+  PCS_CUDA_TRY(cudaEventSynchronize(c->ev[3]));
+  for (int i = 0; i < 3; ++i) PCS_CUDA_TRY(cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+  return PCS_OK;
+}
+
+int32_t pcs_encode_frames(pcs_ctx* c, const uint8_t* h_px, int32_t nframes, int32_t first, uint16_t* h_stream, size_t cap,
+                          int32_t* h_len, size_t* total_words) {
+  if (!c || !h_px || !h_stream || nframes < 1) return PCS_E_ARG;
+  const size_t fpx = (size_t)c->p.width * c->p.height;
+  size_t written = 0;
+  for (int f0 = 0; f0 < nframes; f0 += c->p.max_batch) {
+    const int b = std::min(c->p.max_batch, nframes - f0);
+    PCS_CUDA_TRY(cudaMemcpyAsync(c->d_px, h_px + (size_t)f0 * fpx, (size_t)b * fpx, cudaMemcpyHostToDevice, c->stream));
+    int rc = pcs_encode_device(c, c->d_px, b, first + f0, c->d_stream, reinterpret_cast<int64_t*>(c->d_off), c->stream);
+    if (rc) return rc;
+    PCS_CUDA_TRY(cudaMemcpyAsync(c->h_off, c->d_off, (size_t)(b + 1) * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    PCS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const size_t words = (size_t)c->h_off[b];
+    if (written + words > cap) return fail(c, PCS_E_NOMEM, "output capacity too small");
+    PCS_CUDA_TRY(cudaMemcpyAsync(h_stream + written, c->d_stream, words * 2, cudaMemcpyDeviceToHost, c->stream));
+    PCS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (h_len) for (int f = 0; f < b; ++f) h_len[f0 + f] = (int32_t)(c->h_off[f + 1] - c->h_off[f]);
+    written += words;
+  }
+  if (total_words) *total_words = written;
+  return PCS_OK;
+}
+
+int32_t pcs_decode_frames(pcs_ctx* c, const uint16_t* h_stream, const int32_t* h_len, int32_t nframes, uint8_t* h_px) {
+  if (!c || !h_stream || !h_len || !h_px || nframes < 1) return PCS_E_ARG;
+  const size_t fpx = (size_t)c->p.width * c->p.height;
+  size_t consumed = 0;
+  for (int f0 = 0; f0 < nframes; f0 += c->p.max_batch) {
+    const int b = std::min(c->p.max_batch, nframes - f0);
+    long long off = 0;
+    for (int f = 0; f < b; ++f) {
+      const int len = h_len[f0 + f];
+      if (len < 2 * c->ncb + 10 || (size_t)len > c->max_words) return fail(c, PCS_E_STREAM, "frame length out of range");
+      c->h_off[f] = off; off += len;
+    }
+    c->h_off[b] = off;
+    PCS_CUDA_TRY(cudaMemcpyAsync(c->d_stream, h_stream + consumed, (size_t)off * 2, cudaMemcpyHostToDevice, c->stream));
+    PCS_CUDA_TRY(cudaMemcpyAsync(c->d_off, c->h_off, (size_t)(b + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    int rc = pcs_decode_device(c, c->d_stream, reinterpret_cast<const int64_t*>(c->d_off), b, c->d_px, c->stream);
+    if (rc) return rc;
+    PCS_CUDA_TRY(cudaMemcpyAsync(h_px + (size_t)f0 * fpx, c->d_px, (size_t)b * fpx, cudaMemcpyDeviceToHost, c->stream));
+    PCS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    consumed += (size_t)off;
+  }
+  return PCS_OK;
+}
+
+}  // extern "C"

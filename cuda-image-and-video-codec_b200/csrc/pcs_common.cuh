@@ -1,0 +1,52 @@
+// pcs_common.cuh -- shared device/host helpers of libpicsong_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/picsong_b200.h"
+
+namespace pcs {
+
+constexpr int kCB = 64;          // codeblock edge (BPC/BPCEngine.cuh:29-36 of the reference)
+constexpr int kCBWords = 4096;   // words reserved per codeblock
+constexpr int kMaxLevels = 10;   // Launcher.cu:132 accepts wl in [1,10]
+
+// Whole-sample symmetric extension: fold an index into [0, n), period 2(n-1).
+// (x[-i] = x[i], x[n-1+i] = x[n-1-i]; DWT/DWTGenerator.cu:148-150,285,290 mirror rule.)
+__host__ __device__ __forceinline__ int fold_ws(int i, int n) {
+  if (n == 1) return 0;
+  const int m = 2 * (n - 1);
+  i %= m;
+  if (i < 0) i += m;
+  return i < n ? i : m - i;
+}
+
+// Edge-inclusive mirror padding of the ORIGINAL frame to the adapted (x64) size
+// (IO/IOManager.ipp:99-110: column W+j <- W-1-j, row H+r <- H-1-r).
+__host__ __device__ __forceinline__ int pad_src(int i, int n) { return i < n ? i : 2 * n - 1 - i; }
+
+extern unsigned long long g_launches;  // host-side counter of kernel launches (pcs_kernel_launch_count)
+
+// Arguments of the bit-plane coder kernels (bpc.cu)
+struct BpcArgs {
+  int Wa, Ha, nbx, ncb, wl, nBp, nSub, nrows, prec, total_cb;
+  long long A;
+  const unsigned long long* sigp;  // [nrows] 9 x 7-bit P(0) per significance context
+  const unsigned* sgnp;            // [nrows] 4 x 7-bit per sign context
+  const unsigned char* refp;       // [nrows] refinement probability
+};
+// Arguments of the bit-stream builder kernels (bsb.cu)
+struct BsbArgs {
+  int ncb;                // codeblocks per frame
+  int batch;              // frames
+  int first_frame_index;  // global index of frame 0 of this batch (only global frame 0 carries the header)
+  unsigned short hdr[9];
+};
+
+}  // namespace pcs
+
+#define PCS_CUDA_TRY(expr)                     \
+  do {                                         \
+    cudaError_t e__ = (expr);                  \
+    if (e__ != cudaSuccess) return (int)e__;   \
+  } while (0)

@@ -39,6 +39,12 @@ for tu in "${TUS[@]}"; do
 done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
 "$NVCC" "-gencode=arch=compute_100,code=[sm_100,compute_100]" -rdc=true "${objs[@]}" -o "$OUT/PICSONG_ref${REF_SUFFIX:-}"
+# Stage-level driver (oracle/ref_harness.cu: our code, includes the reference's headers in place,
+# links the reference's own objects minus Launcher.cu's main).
+"$NVCC" "${FLAGS[@]}" -I "$SRC" -x cu -dc "$HERE/ref_harness.cu" -o "$OUT/obj/ref_harness.o"
+hobjs=()
+for o in "${objs[@]}"; do case "$o" in *Launcher_cu.o) ;; *) hobjs+=("$o");; esac; done
+"$NVCC" "-gencode=arch=compute_100,code=[sm_100,compute_100]" -rdc=true "$OUT/obj/ref_harness.o" "${hobjs[@]}" -o "$OUT/ref_harness${REF_SUFFIX:-}"
 # The reference binary needs its probability tables at run time (-LUTFolder); stage the k=0
 # tables beside it (data, git-ignored, travels with oracle/_ref like the binary).
 for d in n1_lossless n1_lossy video_lossless video_lossy; do

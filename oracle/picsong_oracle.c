@@ -87,17 +87,60 @@ static const float A97 = -1.586134342059924f, B97 = -0.052980118572961f, G97 = 0
 /* The reference is built with -use_fast_math => flush-to-zero on every fp32 result. */
 static inline float ftz(float v) { return (fabsf(v) < 1.17549435e-38f) ? copysignf(0.0f, v) : v; }
 
-/* DWT/DWTGenerator.cu:91-104, :184-227, :311-323.  `*b += (a+c)*k` is one add then one FMA under
- * nvcc's default -fmad=true; step four is FMA then multiply; odd samples are then scaled by K. */
-static void fwd97_1d(float* x, int n, int st) {
+/* Forward 9/7 lifting, DWT/DWTGenerator.cu:91-104, :184-227, :311-323.  `*b += (a+c)*k` is one add
+ * then one FMA under nvcc's default -fmad=true; step four is FMA then multiply by 1/K; odd samples
+ * are then scaled by K.
+ *
+ * Bit-exactness note (pinned against the reference binary's SASS and its B200 output): the
+ * compiler contracts ACROSS the vertical->horizontal boundary.  The last operation of the vertical
+ * pass on every sample is a bare multiply by S (S = 1/K on even rows, K on odd rows).  For ODD
+ * columns that product has a single use -- the `*b + ...` of horizontal step one -- so it is fused
+ * there: o = fma(v, S, (eL+eR)*alpha) with the product (eL+eR)*alpha rounded separately
+ * (SASS: FADD, FMUL 1.586..., FFMA v,S,-t).  Even columns are materialised as v*S because
+ * they have several uses.  fwd97_vert therefore leaves samples UNSCALED and fwd97_horz applies
+ * the row scale S. */
 #define XL(k) x[((k) > 0 ? (k) - 1 : 1) * st]
 #define XR(k) x[((k) + 1 < n ? (k) + 1 : (k) - 1) * st]
+static void fwd97_vert(float* x, int n, int st) { /* columns: steps 1-4, final scaling deferred */
   for (int k = 1; k < n; k += 2) x[k * st] = ftz(fmaf(ftz(XL(k) + XR(k)), A97, x[k * st]));
   for (int k = 0; k < n; k += 2) x[k * st] = ftz(fmaf(ftz(XL(k) + XR(k)), B97, x[k * st]));
   for (int k = 1; k < n; k += 2) x[k * st] = ftz(fmaf(ftz(XL(k) + XR(k)), G97, x[k * st]));
-  for (int k = 0; k < n; k += 2)
-    x[k * st] = ftz(ftz(fmaf(ftz(XL(k) + XR(k)), D97, x[k * st])) * IK97);
-  for (int k = 1; k < n; k += 2) x[k * st] = ftz(x[k * st] * K97);
+  for (int k = 0; k < n; k += 2) x[k * st] = ftz(fmaf(ftz(XL(k) + XR(k)), D97, x[k * st]));
+}
+static void fwd97_horz(float* x, int n, float S, int fused_sum) { /* one row; S = deferred vertical scale */
+  const int st = 1;
+  /* step one needs the UNSCALED even samples when the compiler also fused the own-sample scaling into
+   * the neighbour sum (fused_sum, see fwd97_row_variant): sum = fma(v, S, right) instead of v*S + right */
+  for (int k = 1; k < n; k += 2) {
+    float right = ftz(XR(k) * S), sum;
+    if (fused_sum) sum = ftz(fmaf(XL(k), S, right));
+    else sum = ftz(ftz(XL(k) * S) + right);
+    x[k] = ftz(fmaf(x[k], S, ftz(sum * A97)));
+  }
+  for (int k = 0; k < n; k += 2) x[k] = ftz(x[k] * S);
+  for (int k = 0; k < n; k += 2) x[k] = ftz(fmaf(ftz(XL(k) + XR(k)), B97, x[k]));
+  for (int k = 1; k < n; k += 2) x[k] = ftz(fmaf(ftz(XL(k) + XR(k)), G97, x[k]));
+  for (int k = 0; k < n; k += 2) x[k] = ftz(ftz(fmaf(ftz(XL(k) + XR(k)), D97, x[k])) * IK97);
+  for (int k = 1; k < n; k += 2) x[k] = ftz(x[k] * K97);
+}
+
+/* Which rows use the fused neighbour sum.  The reference kernel is fully unrolled over its 64x18
+ * register tile and the compiler (nvcc 12.9, sm_100) made that extra contraction only for tile rows
+ * 12..17 (recovered by symbolic execution of the binary's SASS).  A row's tile-local
+ * index follows the reference's vertical tiling (DWTGenerator.cu:699-744,1281-1285): tiles every 10
+ * rows, tile t writes local rows 4..13 (the top tile 0..13, the bottom tile 4..17, aligned to the
+ * image bottom).  Rows that both a middle tile and the shifted bottom tile write (when (Hc-8) % 10 != 0)
+ * are a WRITE RACE in the reference between two warps whose values can differ in the last bit; the
+ * bottom tile lives in the last blocks of the grid and wins whenever the grid spans more than one wave
+ * (observed: 512x512 level 1), while on tiny grids the middle tile has been seen to win (256x256 level
+ * 1).  The bottom tile is modelled.  This only ever affects 2 image rows per level by <= 1 ulp. */
+static int fwd97_row_variant(int y, int Hc) {
+  int nWy = (Hc - 8 + 9) / 10;
+  if (nWy <= 1) return y >= 12;
+  int last_start = (nWy - 1) * 10 - ((10 - ((Hc - 8) % 10)) % 10);
+  if (y >= last_start + 4) return (y - last_start) >= 12; /* bottom tile (last blocks of the grid) */
+  if (y < 14) return y >= 12;                              /* top tile */
+  return (y - 4) % 10 >= 8;                                /* middle tile t = (y-4)/10, local row y-10t */
 }
 
 /* DWT/DWTGenerator.cu:110-122, :230-272, :326-339.  The reference's two divisions per sample are
@@ -182,8 +225,8 @@ int pcso_dwt97_forward(const uint8_t* px, int Wa, int Ha, int wl, float qs, floa
   for (size_t i = 0; i < A; i++) out[i] = (float)((int)px[i] - 128);
   int Wc = Wa, Hc = Ha;
   for (int l = 1; l <= wl; l++) {
-    for (int x = 0; x < Wc; x++) fwd97_1d(out + x, Hc, Wa);
-    for (int y = 0; y < Hc; y++) fwd97_1d(out + (size_t)y * Wa, Wc, 1);
+    for (int x = 0; x < Wc; x++) fwd97_vert(out + x, Hc, Wa);
+    for (int y = 0; y < Hc; y++) fwd97_horz(out + (size_t)y * Wa, Wc, (y & 1) ? K97 : IK97, fwd97_row_variant(y, Hc));
     for (int y = 0; y < Hc; y++)
       for (int x = 0; x < Wc; x++) {
         int sb = (x & 1) + 2 * (y & 1); /* 0 LL, 1 HL, 2 LH, 3 HH */
