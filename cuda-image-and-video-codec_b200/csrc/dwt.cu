@@ -109,7 +109,11 @@ __device__ __forceinline__ void hfwd53(int x[4]) {
 // still pending: even columns are scaled first, odd columns get S fused into step one.  `fused_sum`
 // selects the second contraction the reference binary contains for its tile rows 12..17
 // (sum = fma(v, S, right) instead of v*S + right; see fwd97_row_variant).
-__device__ __forceinline__ void hfwd97(float x[4], float S, bool fused_sum) {
+// `left_edge`: the lane holding image column 0 takes o[-1] := o[0] (the reference's clamped shuffle,
+// DWTGenerator.cu:317,319) instead of the halo lane's recomputation, which is not bitwise symmetric
+// when the sum is fused.  Likewise at the right edge e[Wc] := e[Wc-2]: `right1` = the lane's second
+// pair is the image's last column pair, `right0` = its first pair is (then the second pair is mirror data).
+__device__ __forceinline__ void hfwd97(float x[4], float S, bool fused_sum, bool left_edge, bool right0, bool right1) {
   float e0 = __fmul_rn(x[0], S), e1 = __fmul_rn(x[2], S);
   float n0 = __shfl_down_sync(0xffffffffu, e0, 1);
   const float s0 = fused_sum ? __fmaf_rn(x[0], S, e1) : __fadd_rn(e0, e1);
@@ -117,12 +121,16 @@ __device__ __forceinline__ void hfwd97(float x[4], float S, bool fused_sum) {
   float o0 = __fmaf_rn(x[1], S, __fmul_rn(s0, kA));
   float o1 = __fmaf_rn(x[3], S, __fmul_rn(s1, kA));
   float p1 = __shfl_up_sync(0xffffffffu, o1, 1);
+  if (left_edge) p1 = o0;
   e0 = __fmaf_rn(__fadd_rn(p1, o0), kB, e0);
   e1 = __fmaf_rn(__fadd_rn(o0, o1), kB, e1);
   n0 = __shfl_down_sync(0xffffffffu, e0, 1);
+  if (right0) e1 = e0;
+  if (right1) n0 = e1;
   o0 = __fmaf_rn(__fadd_rn(e0, e1), kG, o0);
   o1 = __fmaf_rn(__fadd_rn(e1, n0), kG, o1);
   p1 = __shfl_up_sync(0xffffffffu, o1, 1);
+  if (left_edge) p1 = o0;
   e0 = __fmul_rn(__fmaf_rn(__fadd_rn(p1, o0), kD, e0), kIK);
   e1 = __fmul_rn(__fmaf_rn(__fadd_rn(o0, o1), kD, e1), kIK);
   x[0] = e0; x[2] = e1;
@@ -279,8 +287,9 @@ __global__ void __launch_bounds__(128) dwt_forward_level(const FwdArgs a) {
         xe[j] = x2[j]; o1p[j] = o1; e1p[j] = e1; o2pp[j] = o2;
       }
       if (m - 1 >= n0) {  // warp-uniform
-        hfwd97(lo, kIK, fwd97_row_variant(2 * (m - 1), Hc));
-        hfwd97(hi, kK, fwd97_row_variant(2 * (m - 1) + 1, Hc));
+        const bool r0 = ld.c0 + 1 == Wc - 1, r1 = ld.c0 + 3 == Wc - 1;
+        hfwd97(lo, kIK, fwd97_row_variant(2 * (m - 1), Hc), ld.c0 == 0, r0, r1);
+        hfwd97(hi, kK, fwd97_row_variant(2 * (m - 1) + 1, Hc), ld.c0 == 0, r0, r1);
         emit(m - 1, reinterpret_cast<T*>(lo), reinterpret_cast<T*>(hi));
       }
 #pragma unroll
