@@ -1,0 +1,72 @@
+"""CPU tests of the C ABI boundary: the shared library loads, exports every symbol
+include/picsong_b200.h declares, its host utilities agree with the oracle, and it fails loudly (no CPU
+fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from picsong_b200 import _lib, codec
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "picsong_b200.h")).read()
+    declared = set(re.findall(r"\b(pcs_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"pcs_ctx", "pcs_params"}
+    lib = _lib.load()
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in picsong_b200.h but not exported"
+    assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
+
+
+def test_host_utilities_match_oracle(lut_root):
+    assert codec.adapted_dims(200, 150) == O.adapted_dims(200, 150) == (256, 192)
+    assert codec.adapted_dims(7680, 4320) == (7680, 4352)
+    for folder in ("n1_lossless", "n1_lossy", "video_lossless", "video_lossy"):
+        for wl in (1, 2, 4, 5, 6):
+            a = codec.load_lut(f"{lut_root}/{folder}/", wl)
+            b = O.lut_load(f"{lut_root}/{folder}/", wl)
+            assert np.array_equal(a.table, b.table) and np.array_equal(a.header, b.hdr)
+    lut = codec.load_lut(f"{lut_root}/n1_lossy/", 5)
+    for (W, H, wl, lossy, qs, frames) in ((512, 512, 5, 0, 1.0, 0), (4096, 4096, 5, 1, 0.5, 0), (3840, 2160, 5, 1, 1.0, 600),
+                                          (7680, 4320, 6, 0, 1.0, 0), (200, 150, 2, 1, 0.1234, 3)):
+        p = codec.Params(W, H, wl, bool(lossy), qs, frames=frames)
+        h = codec.header_pack(p, lut)
+        assert np.array_equal(h, O.header_pack(W, H, wl, lossy, qs, frames))
+        u = codec.header_unpack(h)
+        assert (u["width"], u["height"], u["wavelet_levels"], u["lossy"], u["frames"]) == (W, H, wl, lossy, frames)
+        assert abs(u["quant_size"] - int(np.float32(qs) * 10000) / 10000.0) < 1e-7
+
+
+def test_lut_errors(tmp_path):
+    with pytest.raises(codec.PcsError):
+        codec.load_lut(str(tmp_path) + "/nope/", 5)
+
+
+def test_parameter_validation_and_no_cpu_fallback(lut_root):
+    """pcs_create mirrors Launcher.cu:132 ("Incorrect parameters") and never falls back to the CPU."""
+    lut = codec.load_lut(f"{lut_root}/n1_lossless/", 5)
+    lib = _lib.load()
+
+    def create(**kw):
+        p = codec.Params(512, 512, 5)
+        for k, v in kw.items():
+            setattr(p, k, v)
+        cp = p.to_c(lut)
+        ctx = C.c_void_p()
+        return lib.pcs_create(C.byref(cp), C.byref(ctx)), ctx
+
+    assert create(wl=0)[0] == -1 and create(wl=11)[0] == -1        # PCS_E_ARG
+    assert create(cb_height=17)[0] == -1 and create(cb_width=65)[0] == -1
+    assert create(qs=1.5)[0] == -1 and create(width=0)[0] == -1
+    assert create(cp=3)[0] == -4 and create(k=1.0)[0] == -4        # PCS_E_UNSUPPORTED (out of scope)
+    import torch
+    if not torch.cuda.is_available():
+        rc, ctx = create()
+        assert rc > 0 and not ctx.value, "without a CUDA device pcs_create must fail with the CUDA error"
