@@ -1,0 +1,53 @@
+"""GPU test of the PICSONG-compatible command line (C++ host code over the C ABI): same flags and file
+formats as the reference's Launcher; outputs compared with the reference binary's (tests/golden)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "cuda-image-and-video-codec_b200", "PICSONG_b200")
+
+
+def run(args):
+    p = subprocess.run([CLI] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    return p.returncode, p.stdout
+
+
+def test_cli_still_and_video(tmp_path, golden, lut_root):
+    from picsong_b200 import synth
+    assert os.path.exists(CLI), "build the CLI with make -C cuda-image-and-video-codec_b200"
+    # ---- still, lossless: byte-identical to the reference's file; decode gives the reference's PGM ----
+    e = golden.manifest["s256x192_wl3_ll"]
+    raw, enc, dec = tmp_path / "a.raw", tmp_path / "a.pcs", tmp_path / "a.pgm"
+    golden.input("s256x192_wl3_ll").tofile(raw)
+    rc, out = run(["-cd", 0, "-wl", 3, "-cp", 2, "-type", 0, "-qs", 1, "-i", raw, "-o", enc, "-cbWidth", 64, "-cbLength", 18,
+                   "-xSize", 256, "-ySize", 192, "-video", 0, "-LUTFolder", f"{lut_root}/n1_lossless/", "-k", 0])
+    assert rc == 0, out
+    assert "User entered -wl command 3" in out and "The time spent with the app is:" in out
+    assert np.array_equal(np.fromfile(enc, dtype=np.uint16), golden.stream("s256x192_wl3_ll"))
+    assert not os.path.exists(str(enc) + "_SIZE")
+    rc, out = run(["-cd", 1, "-i", enc, "-o", dec, "-LUTFolder", f"{lut_root}/n1_lossless/", "-video", 0])
+    assert rc == 0, out
+    blob = open(dec, "rb").read()
+    assert blob.startswith(b"P5\n256 192\n255\n")
+    assert np.array_equal(np.frombuffer(blob[len(b"P5\n256 192\n255\n"):], dtype=np.uint8), golden.input("s256x192_wl3_ll").reshape(-1))
+    # ---- video, lossy: stream + _SIZE sidecar identical to the reference's ----
+    e = golden.manifest["v256_f3_wl3_q1"]
+    raw, enc, dec = tmp_path / "v.raw", tmp_path / "v.pcs", tmp_path / "v.out"
+    synth.synth_video(256, 256, 3).tofile(raw)
+    rc, out = run(["-cd", 0, "-wl", 3, "-cp", 2, "-type", 1, "-qs", 1.0, "-i", raw, "-o", enc, "-cbWidth", 64, "-cbHeight", 18,
+                   "-xSize", 256, "-ySize", 256, "-video", 1, "-frames", 3, "-numberOfStreams", 2, "-LUTFolder", f"{lut_root}/video_lossy/"])
+    assert rc == 0, out
+    assert np.array_equal(np.fromfile(enc, dtype=np.uint16), golden.stream("v256_f3_wl3_q1"))
+    assert open(str(enc) + "_SIZE").read() == e["size_text"]
+    rc, out = run(["-cd", 1, "-i", enc, "-o", dec, "-LUTFolder", f"{lut_root}/video_lossy/", "-video", 1])
+    assert rc == 0, out
+    d = np.abs(np.fromfile(dec, dtype=np.uint8).astype(int) - golden.decoded("v256_f3_wl3_q1").astype(int))
+    assert d.max() <= 1 and (d != 0).mean() <= 1e-4
+    # ---- invalid parameters: the reference's message and exit(-1) ----
+    rc, out = run(["-cd", 0, "-wl", 11, "-i", raw, "-o", enc, "-xSize", 256, "-ySize", 256])
+    assert rc == 255 and "Incorrect parameters. Please choose valid values." in out
