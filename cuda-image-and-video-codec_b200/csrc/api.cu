@@ -39,7 +39,7 @@ struct pcs_ctx {
   size_t A, scratch_elems, max_words;
   std::vector<int32_t> lut;
   // device: probability tables
-  unsigned long long* d_sigp = nullptr; unsigned* d_sgnp = nullptr; unsigned char* d_refp = nullptr; int nrows = 0;
+  unsigned long long* d_sigp = nullptr; unsigned* d_sgnp = nullptr; unsigned char* d_refp = nullptr; uint4* d_tab4 = nullptr; int nrows = 0;
   // device: workspace
   void* d_scratch = nullptr;       // DWT LL ping-pong, [max_batch][scratch_elems] x 4 bytes
   void* d_status = nullptr;        // look-back status words
@@ -68,7 +68,7 @@ BpcArgs bpc_args(const pcs_ctx* c, int batch) {
   a.Wa = c->Wa; a.Ha = c->Ha; a.nbx = c->Wa / kCB; a.ncb = c->ncb; a.wl = c->p.wavelet_levels;
   a.nBp = c->p.lut_header[0]; a.nSub = c->p.lut_header[1]; a.nrows = c->nrows; a.prec = c->p.lut_header[5];
   a.total_cb = c->ncb * batch; a.A = (long long)c->A;
-  a.sigp = c->d_sigp; a.sgnp = c->d_sgnp; a.refp = c->d_refp;
+  a.sigp = c->d_sigp; a.sgnp = c->d_sgnp; a.refp = c->d_refp; a.tab4 = c->d_tab4;
   return a;
 }
 
@@ -96,26 +96,34 @@ int build_prob_tables(pcs_ctx* c) {
   std::vector<unsigned long long> sig(nrows, 0);
   std::vector<unsigned> sgn(nrows, 0);
   std::vector<unsigned char> ref(nrows, 0);
+  std::vector<uint4> tab4(nrows, make_uint4(0, 0, 0, 0));
   auto at = [&](long long i) -> int { return (i >= 0 && i < n) ? c->lut[(size_t)i] : 0; };
   for (int r = 0; r < nrows; ++r) {
     for (int k = 0; k < 9; ++k) {
       const int v = k < cS ? at((long long)R + (long long)r * cS + k) : 0;
       if (v < 0 || v > 127) return PCS_E_LUT_RANGE;
       sig[r] |= (unsigned long long)v << (7 * k);
+      if (k < 4) tab4[r].x |= (unsigned)v << (8 * k);
+      else if (k < 8) tab4[r].y |= (unsigned)v << (8 * (k - 4));
+      else tab4[r].w |= (unsigned)v;
     }
     for (int k = 0; k < 4; ++k) {
       const int v = k < cG ? at((long long)R + S + (long long)r * cG + k) : 0;
       if (v < 0 || v > 127) return PCS_E_LUT_RANGE;
       sgn[r] |= (unsigned)v << (7 * k);
+      tab4[r].z |= (unsigned)v << (8 * k);
     }
     const int v = at((long long)r * cR);
     if (v < 0 || v > 127) return PCS_E_LUT_RANGE;
     ref[r] = (unsigned char)v;
+    tab4[r].w |= (unsigned)v << 8;
   }
   c->nrows = nrows;
   PCS_CUDA_TRY(cudaMalloc(&c->d_sigp, nrows * sizeof(unsigned long long)));
   PCS_CUDA_TRY(cudaMalloc(&c->d_sgnp, nrows * sizeof(unsigned)));
   PCS_CUDA_TRY(cudaMalloc(&c->d_refp, nrows));
+  PCS_CUDA_TRY(cudaMalloc(&c->d_tab4, nrows * sizeof(uint4)));
+  PCS_CUDA_TRY(cudaMemcpy(c->d_tab4, tab4.data(), nrows * sizeof(uint4), cudaMemcpyHostToDevice));
   PCS_CUDA_TRY(cudaMemcpy(c->d_sigp, sig.data(), nrows * sizeof(unsigned long long), cudaMemcpyHostToDevice));
   PCS_CUDA_TRY(cudaMemcpy(c->d_sgnp, sgn.data(), nrows * sizeof(unsigned), cudaMemcpyHostToDevice));
   PCS_CUDA_TRY(cudaMemcpy(c->d_refp, ref.data(), nrows, cudaMemcpyHostToDevice));
@@ -178,7 +186,7 @@ int32_t pcs_create(const pcs_params* params, pcs_ctx** out) {
 
 void pcs_destroy(pcs_ctx* c) {
   if (!c) return;
-  cudaFree(c->d_sigp); cudaFree(c->d_sgnp); cudaFree(c->d_refp);
+  cudaFree(c->d_sigp); cudaFree(c->d_sgnp); cudaFree(c->d_refp); cudaFree(c->d_tab4);
   cudaFree(c->d_scratch); cudaFree(c->d_status); cudaFree(c->d_px); cudaFree(c->d_coeff); cudaFree(c->d_cw);
   cudaFree(c->d_sizes); cudaFree(c->d_stream); cudaFree(c->d_off);
   if (c->h_off) cudaFreeHost(c->h_off);

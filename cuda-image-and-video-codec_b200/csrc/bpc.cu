@@ -126,25 +126,156 @@ __device__ __forceinline__ unsigned prob_sgn(unsigned pack, unsigned idx) { retu
 // ---------------------------------------------------------------------------------------------
 // encoder
 // ---------------------------------------------------------------------------------------------
+
+// In-register 32x32 bit-matrix transpose: on return w[k] bit i == (old w[i]) bit k.  5 stages of masked
+// swaps, fully unrolled (all indices compile-time).
+__device__ __forceinline__ void transpose32(unsigned (&w)[32]) {
+  unsigned m = 0x0000FFFFu;
+#pragma unroll
+  for (int j = 16; j != 0; j >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      if (k & j) continue;
+      const unsigned t = ((w[k] >> j) ^ w[k + j]) & m;
+      w[k] ^= t << j;
+      w[k + j] ^= t;
+    }
+    m ^= m << (j >> 1);
+  }
+}
+
+// 4 bit planes (32 rows each) -> 4 words of 8 nibbles: afterwards nibble j of n[q] holds, for row 4j+q,
+// the value plane0 | plane1<<1 | plane2<<2 | plane3<<3.
+__device__ __forceinline__ void nibble_net(unsigned (&n)[4]) {
+  unsigned t;
+  t = ((n[0] >> 1) ^ n[1]) & 0x55555555u; n[1] ^= t; n[0] ^= t << 1;
+  t = ((n[2] >> 1) ^ n[3]) & 0x55555555u; n[3] ^= t; n[2] ^= t << 1;
+  t = ((n[0] >> 2) ^ n[2]) & 0x33333333u; n[2] ^= t; n[0] ^= t << 2;
+  t = ((n[1] >> 2) ^ n[3]) & 0x33333333u; n[3] ^= t; n[1] ^= t << 2;
+}
+// same for 2 planes (value 0..3 per nibble)
+__device__ __forceinline__ void nibble_net2(unsigned p0, unsigned p1, unsigned (&n)[4]) {
+  const unsigned t = ((p0 >> 1) ^ p1) & 0x55555555u;
+  const unsigned e = p0 ^ (t << 1), o = p1 ^ t;  // bit pairs of even / odd rows
+  n[0] = e & 0x33333333u; n[2] = (e >> 2) & 0x33333333u;
+  n[1] = o & 0x33333333u; n[3] = (o >> 2) & 0x33333333u;
+}
+
+// Four table look-ups at once: byte i of the result = table entry selected by nibble i of `sel`
+// (entries 0..7 = bytes of lo|hi; bit 3 of a nibble is PRMT's sign-replication flag and is masked off, so
+// context 8 reads entry 0 and is patched by fix8).
+__device__ __forceinline__ unsigned lut4(unsigned lo, unsigned hi, unsigned sel) { return __byte_perm(lo, hi, sel & 0x7777u); }
+// rows whose context is 8 looked up entry 0 above; replace it: delta = entry 8 - entry 0 (no inter-byte carry)
+__device__ __forceinline__ unsigned fix8(unsigned probs, unsigned sel, unsigned delta) {
+  const unsigned m = (sel >> 3) & 0x1111u;
+  const unsigned spread = (m & 1u) | ((m & 0x10u) << 4) | ((m & 0x100u) << 8) | ((m & 0x1000u) << 12);
+  return probs + spread * delta;
+}
+
+__device__ __forceinline__ unsigned byte_of(unsigned x, int k) { return __byte_perm(x, 0u, 0x4440u + (unsigned)k); }
+
+// Per-lane interval coder, branch-free step (BPCEngine.cu:371-399).  `slot` is relative to out+1.
+struct EncState { unsigned lower, size, slot, count, lt; };
+// One call site of the interval coder for the whole warp.  `abw` / `anbw`: words whose bit `bitm` says
+// "this lane codes a 1 here" / "codes a 0 here" (neither: the lane is idle at this call site).
+// Hand-scheduled as predicated PTX: nvcc's lowering of the equivalent C++ (kept below) costs ~50 % more
+// instructions on the ALU pipe, which is what bounds this kernel.
+#ifndef PCS_ENC_PTX
+#define PCS_ENC_PTX 1
+#endif
+__device__ __forceinline__ void enc_step(unsigned abw, unsigned anbw, unsigned bitm, unsigned p, EncState& c,
+                                         unsigned short* out1, unsigned prec) {
+#if PCS_ENC_PTX
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pab, panb, pact, pneed, pst;\n\t"
+      ".reg .b32 t, m, x, pre, pm, r, q, sl;\n\t"
+      ".reg .b64 ad;\n\t"
+      "and.b32 t, %4, %6;\n\t"
+      "setp.ne.u32 pab, t, 0;\n\t"
+      "and.b32 t, %5, %6;\n\t"
+      "setp.ne.u32 panb, t, 0;\n\t"
+      "or.pred pact, pab, panb;\n\t"
+      "setp.eq.and.u32 pneed, %1, 0, pact;\n\t"       // lanes that start a codeword at this call site,
+      "vote.sync.ballot.b32 m, pneed, 0xffffffff;\n\t"  // served in lane order (BPCEngine.cu:376-384)
+      "and.b32 x, m, %7;\n\t"
+      "popc.b32 pre, x;\n\t"
+      "popc.b32 pm, m;\n\t"
+      "@pneed add.u32 %2, %3, pre;\n\t"
+      "add.u32 %3, %3, pm;\n\t"
+      "@pneed mov.u32 %1, 0xFFFF;\n\t"
+      "@pneed mov.u32 %0, 0;\n\t"
+      "mul.lo.u32 r, %1, %8;\n\t"
+      "shr.u32 q, r, %9;\n\t"
+      "add.u32 r, q, 1;\n\t"
+      "@pab sub.u32 %1, %1, r;\n\t"
+      "@pab add.u32 %0, %0, r;\n\t"
+      "@panb mov.u32 %1, q;\n\t"
+      "setp.eq.and.u32 pst, %1, 0, pact;\n\t"
+      "min.u32 sl, %2, 4094;\n\t"
+      "mad.wide.u32 ad, sl, 2, %10;\n\t"
+      "@pst st.global.u16 [ad], %0;\n\t"
+      "}"
+      : "+r"(c.lower), "+r"(c.size), "+r"(c.slot), "+r"(c.count)
+      : "r"(abw), "r"(anbw), "r"(bitm), "r"(c.lt), "r"(p), "r"(prec), "l"(out1)
+      : "memory");
+#else
+  const bool ab = (abw & bitm) != 0, anb = (anbw & bitm) != 0;
+  const bool act = ab || anb;
+  const bool need = act && (c.size == 0);
+  const unsigned m = __ballot_sync(kFull, need);
+  const unsigned pre = __popc(m & c.lt);
+  if (need) { c.slot = c.count + pre; c.size = 0xFFFFu; c.lower = 0u; }
+  c.count += __popc(m);
+  const unsigned q = (c.size * p) >> prec;
+  if (ab) { c.size = c.size - q - 1u; c.lower = c.lower + q + 1u; }
+  if (anb) c.size = q;
+  if (act && c.size == 0) out1[min(c.slot, 4094u)] = (unsigned short)c.lower;
+#endif
+}
+
+#ifndef PCS_SPP_UNROLL
+#define PCS_SPP_UNROLL 1
+#endif
+constexpr int kSppUnroll = PCS_SPP_UNROLL;
+
+#ifndef PCS_ENC_MINB
+#define PCS_ENC_MINB 4
+#endif
 template <typename T>
-__global__ void __launch_bounds__(128) bpc_encode_kernel(const T* __restrict__ coeff, unsigned short* __restrict__ cw,
+__global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* __restrict__ coeff, unsigned short* __restrict__ cw,
                                                         int* __restrict__ sizes, const BpcArgs p) {
-  const int lane = threadIdx.x & 31;
-  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // transposed magnitude bits of the warp's codeblock: word [32*half + k][lane], k < 16: plane k of the
+  // lane's column 0, k >= 16: plane k-16 of column 1; bit i = row 32*half + i
+  __shared__ unsigned s_pl[4][64][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int w = blockIdx.x * (blockDim.x >> 5) + wib;
   if (w >= p.total_cb) return;
   const int frame = w / p.ncb, cb = w - frame * p.ncb;
   const int bx = cb % p.nbx, by = cb / p.nbx;
   const T* src = coeff + (size_t)frame * p.A + (size_t)(by * kCB) * p.Wa + bx * kCB + 2 * lane;
   unsigned short* out = cw + (size_t)w * kCBWords;
+  unsigned (*pl)[32] = s_pl[wib];
 
-  // pass 0: MSB of the block and the sign masks (BPCEngine.cu:41-63,176-192)
+  // pass 0: MSB of the block, sign masks (BPCEngine.cu:41-63,176-192), bit-plane transposition
   u64 g0 = 0, g1 = 0;
   unsigned ormag = 0;
-#pragma unroll 8
-  for (int i = 0; i < kCB; ++i) {
-    int a, b; load2<T>(src + (size_t)i * p.Wa, a, b);
-    ormag |= umag(a) | umag(b);
-    g0 |= (u64)(a < 0) << i; g1 |= (u64)(b < 0) << i;
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    unsigned wv[32], sg0 = 0, sg1 = 0;
+#pragma unroll
+    for (int i = 31; i >= 0; --i) {
+      int a, b; load2<T>(src + (size_t)(32 * h + i) * p.Wa, a, b);
+      const unsigned ma = umag(a), mb = umag(b);
+      ormag |= ma | mb;
+      sg0 = __funnelshift_l((unsigned)a, sg0, 1);  // (sg0 << 1) | sign(a): row i ends up at bit i
+      sg1 = __funnelshift_l((unsigned)b, sg1, 1);
+      wv[i] = (ma & 0xFFFFu) | (mb << 16);
+    }
+    transpose32(wv);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) pl[32 * h + k][lane] = wv[k];
+    g0 |= (u64)sg0 << (32 * h); g1 |= (u64)sg1 << (32 * h);
   }
   ormag = __reduce_or_sync(kFull, ormag);
   const int MSB = ormag ? 31 - __clz(ormag) : 32;
@@ -152,19 +283,29 @@ __global__ void __launch_bounds__(128) bpc_encode_kernel(const T* __restrict__ c
     if (lane == 0) { out[0] = 32; sizes[w] = 1; }
     return;
   }
+  __syncwarp();
   int row = lane_group(bx * kCB + 2 * lane, by * kCB, p) * p.nBp + MSB;  // initializeLUTPointers :329-350
   const u64 Lg = shfl_up64(g1, lane), Rg = shfl_down64(g0, lane);       // neighbour lanes' signs
+  unsigned short* const out1 = out + 1;
+  const unsigned prec = (unsigned)p.prec;
 
-  Coder ac; ac.init(lane, p.prec);
+  EncState ac; ac.lower = 0; ac.size = 0; ac.slot = 0; ac.count = 0; ac.lt = (1u << lane) - 1u;
   u64 s0 = 0, s1 = 0;  // significant BEFORE the current plane
   for (int bp = MSB; bp >= 0; --bp, --row) {
-    u64 B0 = 0, B1 = 0;
-#pragma unroll 8
-    for (int i = 0; i < kCB; ++i) {
-      int a, b; load2<T>(src + (size_t)i * p.Wa, a, b);
-      B0 |= (u64)((umag(a) >> bp) & 1u) << i; B1 |= (u64)((umag(b) >> bp) & 1u) << i;
+    u64 B0, B1;
+    if (bp < 16) {
+      B0 = (u64)pl[bp][lane] | ((u64)pl[32 + bp][lane] << 32);
+      B1 = (u64)pl[16 + bp][lane] | ((u64)pl[48 + bp][lane] << 32);
+    } else {  // |q| >= 2^16: not reachable from 8-bit images with the shipped quantiser; generic slow path
+      B0 = 0; B1 = 0;
+#pragma unroll 4
+      for (int i = 0; i < kCB; ++i) {
+        int a, b; load2<T>(src + (size_t)i * p.Wa, a, b);
+        B0 |= (u64)((umag(a) >> bp) & 1u) << i; B1 |= (u64)((umag(b) >> bp) & 1u) << i;
+      }
     }
-    const Probs pr = load_probs(p, row);
+    const uint4 tab = (row >= 0 && row < p.nrows) ? __ldg(p.tab4 + row) : make_uint4(0, 0, 0, 0);
+    const unsigned d8 = (tab.w & 0xFFu) - (tab.x & 0xFFu), pref = (tab.w >> 8) & 0xFFu;
     const u64 a0 = s0 | B0, a1 = s1 | B1;  // significant AFTER this plane's SPP visit
     const u64 Lb = shfl_up64(s1, lane), La = shfl_up64(a1, lane);
     const u64 Rb = shfl_down64(s0, lane), Ra = shfl_down64(a0, lane);
@@ -202,52 +343,73 @@ __global__ void __launch_bounds__(128) bpc_encode_kernel(const T* __restrict__ c
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
       const int sh = 32 * h;
-      unsigned A0 = ~(unsigned)(s0 >> sh), A1 = ~(unsigned)(s1 >> sh), b0 = (unsigned)(B0 >> sh), b1 = (unsigned)(B1 >> sh);
-      unsigned k00 = (unsigned)(K0[0] >> sh), k01 = (unsigned)(K0[1] >> sh), k02 = (unsigned)(K0[2] >> sh), k03 = (unsigned)(K0[3] >> sh);
-      unsigned k10 = (unsigned)(K1[0] >> sh), k11 = (unsigned)(K1[1] >> sh), k12 = (unsigned)(K1[2] >> sh), k13 = (unsigned)(K1[3] >> sh);
-      unsigned y0 = (unsigned)(SY0 >> sh), i00 = (unsigned)(I00 >> sh), i01 = (unsigned)(I01 >> sh);
-      unsigned y1 = (unsigned)(SY1 >> sh), i10 = (unsigned)(I10 >> sh), i11 = (unsigned)(I11 >> sh);
-#pragma unroll 2
-      for (int j = 0; j < 32; ++j) {
-        {
-          const bool act = A0 & 1u;
-          const unsigned b = b0 & 1u;
-          const unsigned ctx = (k00 & 1u) | ((k01 & 1u) << 1) | ((k02 & 1u) << 2) | ((k03 & 1u) << 3);
-          ac.encode(act, b, prob_sig(pr.sig, ctx), out);
-          const bool sg = act && b;
-          if (__any_sync(kFull, sg)) ac.encode(sg, y0 & 1u, prob_sgn(pr.sgn, (i00 & 1u) | ((i01 & 1u) << 1)), out);
+      const unsigned A0 = ~(unsigned)(s0 >> sh), A1 = ~(unsigned)(s1 >> sh);
+      const unsigned anyact = __reduce_or_sync(kFull, A0 | A1);  // rows of this half in which some lane codes a symbol
+      if (anyact == 0) continue;
+      const unsigned b0 = (unsigned)(B0 >> sh), b1 = (unsigned)(B1 >> sh), y0 = (unsigned)(SY0 >> sh), y1 = (unsigned)(SY1 >> sh);
+      unsigned n0[4] = {(unsigned)(K0[0] >> sh), (unsigned)(K0[1] >> sh), (unsigned)(K0[2] >> sh), (unsigned)(K0[3] >> sh)};
+      unsigned n1[4] = {(unsigned)(K1[0] >> sh), (unsigned)(K1[1] >> sh), (unsigned)(K1[2] >> sh), (unsigned)(K1[3] >> sh)};
+      const bool has8 = (n0[3] | n1[3]) != 0;  // some row of this lane has all 8 neighbours significant
+      nibble_net(n0); nibble_net(n1);
+      unsigned i0[4], i1[4];
+      nibble_net2((unsigned)(I00 >> sh), (unsigned)(I01 >> sh), i0);
+      nibble_net2((unsigned)(I10 >> sh), (unsigned)(I11 >> sh), i1);
+#pragma unroll 1
+      for (int jj = 0; jj < 2; ++jj) {
+        // probabilities of rows 16*jj + 4*t + q: byte t of P?[q] (significance) and S?[q] (sign)
+        unsigned P0[4], P1[4], S0[4], S1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const unsigned e0 = n0[q] >> (16 * jj), e1 = n1[q] >> (16 * jj);
+          P0[q] = lut4(tab.x, tab.y, e0); P1[q] = lut4(tab.x, tab.y, e1);
+          S0[q] = lut4(tab.z, 0u, i0[q] >> (16 * jj)); S1[q] = lut4(tab.z, 0u, i1[q] >> (16 * jj));
         }
-        {
-          const bool act = A1 & 1u;
-          const unsigned b = b1 & 1u;
-          const unsigned ctx = (k10 & 1u) | ((k11 & 1u) << 1) | ((k12 & 1u) << 2) | ((k13 & 1u) << 3);
-          ac.encode(act, b, prob_sig(pr.sig, ctx), out);
-          const bool sg = act && b;
-          if (__any_sync(kFull, sg)) ac.encode(sg, y1 & 1u, prob_sgn(pr.sgn, (i10 & 1u) | ((i11 & 1u) << 1)), out);
+        if (has8) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            P0[q] = fix8(P0[q], n0[q] >> (16 * jj), d8); P1[q] = fix8(P1[q], n1[q] >> (16 * jj), d8);
+          }
         }
-        A0 >>= 1; A1 >>= 1; b0 >>= 1; b1 >>= 1;
-        k00 >>= 1; k01 >>= 1; k02 >>= 1; k03 >>= 1; k10 >>= 1; k11 >>= 1; k12 >>= 1; k13 >>= 1;
-        y0 >>= 1; i00 >>= 1; i01 >>= 1; y1 >>= 1; i10 >>= 1; i11 >>= 1;
+        // this 16-row slab's symbol masks: lane codes a 1 / a 0; sign symbol 1 / 0 of samples that become significant
+        const unsigned sl = 16 * jj;
+        const unsigned ab0 = (A0 & b0) >> sl, an0 = (A0 & ~b0) >> sl, ab1 = (A1 & b1) >> sl, an1 = (A1 & ~b1) >> sl;
+        const unsigned gp0 = ab0 & (y0 >> sl), gn0 = ab0 & ~(y0 >> sl), gp1 = ab1 & (y1 >> sl), gn1 = ab1 & ~(y1 >> sl);
+        const unsigned anyj = anyact >> sl;
+        const unsigned new0 = __reduce_or_sync(kFull, ab0), new1 = __reduce_or_sync(kFull, ab1);  // warp-uniform
+#pragma unroll(kSppUnroll)
+        for (int t = 0; t < 4; ++t) {
+          if (((anyj >> (4 * t)) & 15u) == 0) continue;  // warp-uniform
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const unsigned bitm = 1u << (4 * t + q);
+            enc_step(ab0, an0, bitm, byte_of(P0[q], t), ac, out1, prec);
+            if (new0 & bitm) enc_step(gp0, gn0, bitm, byte_of(S0[q], t), ac, out1, prec);
+            enc_step(ab1, an1, bitm, byte_of(P1[q], t), ac, out1, prec);
+            if (new1 & bitm) enc_step(gp1, gn1, bitm, byte_of(S1[q], t), ac, out1, prec);
+          }
+        }
       }
     }
-    // ---- magnitude refinement pass: samples significant before this plane (BPCEngine.cu:726-736,1249-1261) ----
-    if (__any_sync(kFull, (s0 | s1) != 0)) {
+    // ---- magnitude refinement pass: samples significant before this plane (BPCEngine.cu:726-736,1249-1261);
+    //      only rows in which some lane refines are visited ----
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const int sh = 32 * h;
-        unsigned r0 = (unsigned)(s0 >> sh), r1 = (unsigned)(s1 >> sh), b0 = (unsigned)(B0 >> sh), b1 = (unsigned)(B1 >> sh);
-#pragma unroll 2
-        for (int j = 0; j < 32; ++j) {
-          ac.encode(r0 & 1u, b0 & 1u, pr.ref, out);
-          ac.encode(r1 & 1u, b1 & 1u, pr.ref, out);
-          r0 >>= 1; r1 >>= 1; b0 >>= 1; b1 >>= 1;
-        }
+    for (int h = 0; h < 2; ++h) {
+      const int sh = 32 * h;
+      const unsigned r0m = (unsigned)(s0 >> sh), r1m = (unsigned)(s1 >> sh), b0 = (unsigned)(B0 >> sh), b1 = (unsigned)(B1 >> sh);
+      const unsigned r0b = r0m & b0, r0n = r0m & ~b0, r1b = r1m & b1, r1n = r1m & ~b1;
+      unsigned U = __reduce_or_sync(kFull, r0m | r1m);
+      while (U) {
+        const int r = __ffs(U) - 1;
+        U &= U - 1;
+        const unsigned bitm = 1u << r;
+        enc_step(r0b, r0n, bitm, pref, ac, out1, prec);
+        enc_step(r1b, r1n, bitm, pref, ac, out1, prec);
       }
     }
     s0 = a0; s1 = a1;
   }
-  out[ac.slot] = (unsigned short)ac.lower;  // flush (BPCEngine.cu:1719)
-  const int size = (int)ac.count + 1;       // :2010
+  out1[min(ac.slot, 4094u)] = (unsigned short)ac.lower;  // flush (BPCEngine.cu:1719)
+  const int size = (int)min(ac.count, 4095u) + 1;         // :2010
   __syncwarp();
   if (size == kCBWords) {
     // expansion fallback (BPCEngine.cu:2015-2024,1904-1912): raw low 16 bits of (|q|<<1 | sign), lane-major
@@ -266,18 +428,81 @@ __global__ void __launch_bounds__(128) bpc_encode_kernel(const T* __restrict__ c
 // ---------------------------------------------------------------------------------------------
 // decoder
 // ---------------------------------------------------------------------------------------------
-constexpr int kSmemPlanes = 16;
-// sign context table (BPCEngine.cu:252-293) indexed by (sgn(h)+1)*3 + (sgn(v)+1), 3 bits each
+// sign context table (BPCEngine.cu:252-293) indexed by (sgn(h)+1)*3 + (sgn(v)+1), 3 bits each:
+// bit 0 = "flip the decoded symbol", bits 2:1 = probability index
 constexpr unsigned kSignTab = 7u | (5u << 3) | (1u << 6) | (3u << 9) | (0u << 12) | (2u << 15) | (0u << 18) | (4u << 21) | (6u << 24);
 __device__ __forceinline__ unsigned sign_ctx(int h, int v) {
   const int sh = (h > 0) - (h < 0), sv = (v > 0) - (v < 0);
   return (kSignTab >> (3 * ((sh + 1) * 3 + (sv + 1)))) & 7u;
 }
 __device__ __forceinline__ int contrib(unsigned sig, unsigned neg) { return sig ? (neg ? -1 : 1) : 0; }
+// Entry of the decoder's sign-context byte table.  Index bits: [1:0] left (significant, negative),
+// [3:2] right, [5:4] up, [7:6] down.
+__device__ __forceinline__ unsigned sign_entry(unsigned i) {
+  const int h = contrib(i & 1u, (i >> 1) & 1u) + contrib((i >> 2) & 1u, (i >> 3) & 1u);
+  const int v = contrib((i >> 4) & 1u, (i >> 5) & 1u) + contrib((i >> 6) & 1u, (i >> 7) & 1u);
+  return sign_ctx(h, v);
+}
 
-__global__ void __launch_bounds__(128) bpc_decode_kernel(const unsigned short* __restrict__ cw, const int* __restrict__ sizes,
-                                                        int* __restrict__ q, const BpcArgs p) {
-  __shared__ uint4 planes[4][kSmemPlanes][32];
+struct DecState { unsigned lower, size, slot, count, code, lt; };
+// One call site of the interval decoder for the whole warp (BPCEngine.cu:405-442); returns the decoded
+// bit (0 for idle lanes).  `actw` bit `bitm`: this lane decodes a symbol here.  Predicated PTX, see enc_step.
+__device__ __forceinline__ unsigned dec_step(unsigned actw, unsigned bitm, unsigned p, DecState& c,
+                                             const unsigned short* in1, unsigned prec) {
+  unsigned b;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pact, pneed, pb, pnb;\n\t"
+      ".reg .b32 t, m, x, pre, pm, r, q, sl, lim;\n\t"
+      ".reg .b64 ad;\n\t"
+      "and.b32 t, %6, %7;\n\t"
+      "setp.ne.u32 pact, t, 0;\n\t"
+      "setp.eq.and.u32 pneed, %1, 0, pact;\n\t"
+      "vote.sync.ballot.b32 m, pneed, 0xffffffff;\n\t"
+      "and.b32 x, m, %8;\n\t"
+      "popc.b32 pre, x;\n\t"
+      "popc.b32 pm, m;\n\t"
+      "@pneed add.u32 %2, %3, pre;\n\t"
+      "add.u32 %3, %3, pm;\n\t"
+      "min.u32 sl, %2, 4094;\n\t"
+      "mad.wide.u32 ad, sl, 2, %11;\n\t"
+      "@pneed ld.global.nc.u16 %4, [ad];\n\t"
+      "@pneed mov.u32 %1, 0xFFFF;\n\t"
+      "@pneed mov.u32 %0, 0;\n\t"
+      "mul.lo.u32 r, %1, %9;\n\t"
+      "shr.u32 q, r, %10;\n\t"
+      "add.u32 t, q, 1;\n\t"
+      "add.u32 lim, %0, t;\n\t"
+      "setp.ge.and.u32 pb, %4, lim, pact;\n\t"
+      "setp.lt.and.u32 pnb, %4, lim, pact;\n\t"
+      "@pb sub.u32 %1, %1, t;\n\t"
+      "@pb mov.u32 %0, lim;\n\t"
+      "@pnb mov.u32 %1, q;\n\t"
+      "selp.u32 %5, 1, 0, pb;\n\t"
+      "}"
+      : "+r"(c.lower), "+r"(c.size), "+r"(c.slot), "+r"(c.count), "+r"(c.code), "=r"(b)
+      : "r"(actw), "r"(bitm), "r"(c.lt), "r"(p), "r"(prec), "l"(in1)
+      : "memory");
+  return b;
+}
+
+// probability of significance context 0..8 from the byte table
+__device__ __forceinline__ unsigned sig_prob(const uint4& tab, unsigned ctx) {
+  const unsigned pr = __byte_perm(tab.x, tab.y, ctx & 7u);
+  return (ctx & 8u) ? (tab.w & 0xFFu) : (pr & 0xFFu);
+}
+
+#ifndef PCS_DEC_MINB
+#define PCS_DEC_MINB 4
+#endif
+__global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const unsigned short* __restrict__ cw, const int* __restrict__ sizes,
+                                                                      int* __restrict__ q, const BpcArgs p) {
+  // decoded magnitude bit planes, same layout as the encoder's: word [32*half + k][lane], k < 16: plane k of
+  // column 0, k >= 16: plane k-16 of column 1
+  __shared__ unsigned s_pl[4][64][32];
+  __shared__ unsigned char s_sign[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_sign[i] = (unsigned char)sign_entry((unsigned)i);
+  __syncthreads();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int w = blockIdx.x * (blockDim.x >> 5) + wib;
   if (w >= p.total_cb) return;
@@ -287,6 +512,7 @@ __global__ void __launch_bounds__(128) bpc_decode_kernel(const unsigned short* _
   const unsigned short* in = cw + (size_t)w * kCBWords;
   const int size = sizes[w];
   const int MSB = in[0];
+  unsigned (*pl)[32] = s_pl[wib];
 
   if (size == kCBWords) {  // raw block (BPCEngine.cu:2197-2200,1914-1922,94-111)
     for (int i = 0; i < kCB; ++i) {
@@ -300,108 +526,129 @@ __global__ void __launch_bounds__(128) bpc_decode_kernel(const unsigned short* _
     for (int i = 0; i < kCB; ++i) *reinterpret_cast<int2*>(dst + (size_t)i * p.Wa) = make_int2(0, 0);
     return;
   }
-  const bool hi_planes = MSB >= kSmemPlanes;  // rare: planes >= 16 are accumulated in the output directly
+  const bool hi_planes = MSB >= 16;  // rare: planes >= 16 are accumulated in the output directly
   if (hi_planes)
     for (int i = 0; i < kCB; ++i) *reinterpret_cast<int2*>(dst + (size_t)i * p.Wa) = make_int2(0, 0);
+#pragma unroll
+  for (int k = 0; k < 64; ++k) pl[k][lane] = 0u;
 
   int row = lane_group(bx * kCB + 2 * lane, by * kCB, p) * p.nBp + MSB;
-  Coder ac; ac.init(lane, p.prec);
-  unsigned code = 0;
+  const unsigned short* const in1 = in + 1;
+  const unsigned prec = (unsigned)p.prec;
+  DecState ac; ac.lower = 0; ac.size = 0; ac.slot = 0; ac.count = 0; ac.code = 0; ac.lt = (1u << lane) - 1u;
   u64 s0 = 0, s1 = 0, g0 = 0, g1 = 0;  // significant before this plane; sign (1 = negative) of significant samples
   for (int bp = MSB; bp >= 0; --bp, --row) {
-    const Probs pr = load_probs(p, row);
+    const uint4 tab = (row >= 0 && row < p.nrows) ? __ldg(p.tab4 + row) : make_uint4(0, 0, 0, 0);
+    const unsigned pref = (tab.w >> 8) & 0xFFu;
     const u64 Lb = shfl_up64(s1, lane), Lg = shfl_up64(g1, lane), Rb = shfl_down64(s0, lane);
     // static part of the contexts: state BEFORE this pass of all eight neighbours
     u64 K0[4], K1[4];
     count8(Lb << 1, s0 << 1, s1 << 1, Lb, s1, Lb >> 1, s0 >> 1, s1 >> 1, K0);
     count8(s0 << 1, s1 << 1, Rb << 1, s0, Rb, s0 >> 1, s1 >> 1, Rb >> 1, K1);
-    // static sign-context inputs: column 0's horizontal pair (left lane col 1, own col 1) is not visited
-    // before it, the sample below is never visited before
+    // static sign-context inputs.  Column 0: its horizontal pair (left lane's column 1, own column 1) is not
+    // visited before it -> the sign of their sum, presented as a fake "left" neighbour; the sample below is
+    // never visited before.
     const u64 Lp = Lb & ~Lg, Ln = Lb & Lg, Rp = s1 & ~g1, Rn = s1 & g1;
     const u64 Hp0 = (Lp & ~Rn) | (Rp & ~Ln), Hn0 = (Ln & ~Rp) | (Rn & ~Lp);
-    const u64 Dp0 = (s0 & ~g0) >> 1, Dn0 = (s0 & g0) >> 1, Dp1 = (s1 & ~g1) >> 1, Dn1 = (s1 & g1) >> 1;
+    const u64 Hs0 = Hp0 | Hn0;                                   // |h| != 0
+    const u64 Ds0 = s0 >> 1, Dn0 = (s0 & g0) >> 1, Ds1 = s1 >> 1, Dn1 = (s1 & g1) >> 1;
 
     u64 B0 = 0, B1 = 0;  // decoded 1-bits of this plane
     u64 N0 = 0, N1 = 0;  // newly significant in this pass
-    // carried from the previous row: "became significant in this pass" flags and current state of (i-1)
-    unsigned pn0 = 0, pn1 = 0, pnl = 0, pnr = 0, u0s = 0, u0n = 0, u1s = 0, u1n = 0;
+    // carried from the previous row: "became significant in this pass" flags and (significant | negative << 1) of row i-1
+    unsigned pns = 0, pnl = 0, pnr = 0, u0 = 0, u1 = 0;
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
       const int sh = 32 * h;
-      unsigned S0 = (unsigned)(s0 >> sh), S1 = (unsigned)(s1 >> sh), G0 = (unsigned)(g0 >> sh), G1 = (unsigned)(g1 >> sh);
-      unsigned k00 = (unsigned)(K0[0] >> sh), k01 = (unsigned)(K0[1] >> sh), k02 = (unsigned)(K0[2] >> sh), k03 = (unsigned)(K0[3] >> sh);
-      unsigned k10 = (unsigned)(K1[0] >> sh), k11 = (unsigned)(K1[1] >> sh), k12 = (unsigned)(K1[2] >> sh), k13 = (unsigned)(K1[3] >> sh);
-      unsigned hp0 = (unsigned)(Hp0 >> sh), hn0 = (unsigned)(Hn0 >> sh);
-      unsigned dp0 = (unsigned)(Dp0 >> sh), dn0 = (unsigned)(Dn0 >> sh), dp1 = (unsigned)(Dp1 >> sh), dn1 = (unsigned)(Dn1 >> sh);
-      unsigned nb0 = 0, nb1 = 0, nn0 = 0, nn1 = 0, ng0 = 0, ng1 = 0;  // this half's decoded bits / new flags / new signs
+      const unsigned S0 = (unsigned)(s0 >> sh), S1 = (unsigned)(s1 >> sh), G0 = (unsigned)(g0 >> sh), G1 = (unsigned)(g1 >> sh);
+      const unsigned A0 = ~S0, A1 = ~S1;
+      const unsigned anyact = __reduce_or_sync(kFull, A0 | A1);
+      unsigned nb0 = 0, nb1 = 0, ng0 = 0, ng1 = 0;  // this half's decoded bits (= new flags) and new signs, row i at bit i
+      if (anyact != 0) {
+        unsigned n0[4] = {(unsigned)(K0[0] >> sh), (unsigned)(K0[1] >> sh), (unsigned)(K0[2] >> sh), (unsigned)(K0[3] >> sh)};
+        unsigned n1[4] = {(unsigned)(K1[0] >> sh), (unsigned)(K1[1] >> sh), (unsigned)(K1[2] >> sh), (unsigned)(K1[3] >> sh)};
+        unsigned c0[4] = {(unsigned)(Hs0 >> sh), (unsigned)(Hn0 >> sh), (unsigned)(Ds0 >> sh), (unsigned)(Dn0 >> sh)};
+        unsigned c1[4];
+        nibble_net(n0); nibble_net(n1); nibble_net(c0);
+        nibble_net2((unsigned)(Ds1 >> sh), (unsigned)(Dn1 >> sh), c1);
 #pragma unroll 1
-      for (int j = 0; j < 32; ++j) {
-        // ---- column 0 ----
-        unsigned cn0 = 0, neg0 = G0 & 1u;
-        {
-          const bool act = !(S0 & 1u);
-          const unsigned ctx = ((k00 & 1u) | ((k01 & 1u) << 1) | ((k02 & 1u) << 2) | ((k03 & 1u) << 3)) + pnl + pn0 + pn1;
-          const unsigned b = ac.decode(act, prob_sig(pr.sig, ctx), code, in);
-          if (__any_sync(kFull, b)) {
-            const int hh = (int)(hp0 & 1u) - (int)(hn0 & 1u);
-            const int vv = contrib(u0s, u0n) + (int)(dp0 & 1u) - (int)(dn0 & 1u);
-            const unsigned sc = sign_ctx(hh, vv);
-            const unsigned sym = ac.decode(b != 0, prob_sgn(pr.sgn, sc >> 1), code, in);
-            if (b) { cn0 = 1; neg0 = sym ^ (sc & 1u); }  // BPCEngine.cu:583-589
+        for (int g = 0; g < 8; ++g) {  // rows 4g .. 4g+3
+          const int r0 = 4 * g;
+          if (((anyact >> r0) & 15u) == 0) {
+            // nobody decodes in these rows: nothing becomes significant; carry the state of row 4g+3
+            pns = 0; pnl = 0; pnr = 0;
+            u0 = ((S0 >> (r0 + 3)) & 1u) | (((G0 >> (r0 + 3)) & 1u) << 1);
+            u1 = ((S1 >> (r0 + 3)) & 1u) | (((G1 >> (r0 + 3)) & 1u) << 1);
+            continue;
           }
-          nb0 |= cn0 << j; nn0 |= cn0 << j; ng0 |= (cn0 & neg0) << j;
-        }
-        const unsigned cur0 = (S0 & 1u) | cn0;
-        // right neighbour's (i, col 0): current significance, sign, new flag
-        unsigned rv = __shfl_down_sync(kFull, cur0 | (neg0 << 1) | (cn0 << 2), 1);
-        if (lane == 31) rv = 0;
-        const unsigned cnr = (rv >> 2) & 1u;
-        // ---- column 1 ----
-        unsigned cn1 = 0, neg1 = G1 & 1u;
-        {
-          const bool act = !(S1 & 1u);
-          const unsigned ctx = ((k10 & 1u) | ((k11 & 1u) << 1) | ((k12 & 1u) << 2) | ((k13 & 1u) << 3)) + pn0 + pn1 + pnr + cn0 + cnr;
-          const unsigned b = ac.decode(act, prob_sig(pr.sig, ctx), code, in);
-          if (__any_sync(kFull, b)) {
-            const int hh = contrib(cur0, neg0) + contrib(rv & 1u, (rv >> 1) & 1u);
-            const int vv = contrib(u1s, u1n) + (int)(dp1 & 1u) - (int)(dn1 & 1u);
-            const unsigned sc = sign_ctx(hh, vv);
-            const unsigned sym = ac.decode(b != 0, prob_sgn(pr.sgn, sc >> 1), code, in);
-            if (b) { cn1 = 1; neg1 = sym ^ (sc & 1u); }
+          const unsigned a40 = A0 >> r0, a41 = A1 >> r0, s40 = S0 >> r0, s41 = S1 >> r0, g40 = G0 >> r0, g41 = G1 >> r0;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const unsigned bitm = 1u << qq;
+            // ---- column 0 ----
+            unsigned ctx = ((n0[qq] >> r0) & 15u) + pnl + pns;
+            unsigned cn0 = dec_step(a40, bitm, sig_prob(tab, ctx), ac, in1, prec);
+            unsigned neg0 = (g40 >> qq) & 1u;
+            if (__any_sync(kFull, cn0)) {
+              // left/right: static (fake left = sign of the static horizontal sum), up: row i-1 now, down: static
+              const unsigned st = (c0[qq] >> r0) & 15u;
+              const unsigned sc = s_sign[(st & 3u) | (u0 << 4) | ((st & 12u) << 4)];
+              const unsigned sym = dec_step(cn0, 1u, __byte_perm(tab.z, 0u, sc >> 1) & 0xFFu, ac, in1, prec);
+              if (cn0) neg0 = sym ^ (sc & 1u);  // BPCEngine.cu:583-589
+            }
+            nb0 |= cn0 << (r0 + qq); ng0 |= (cn0 & neg0) << (r0 + qq);
+            const unsigned cur0 = ((s40 >> qq) & 1u) | cn0;
+            // right neighbour's (i, column 0): current significance, sign, new flag
+            unsigned rv = __shfl_down_sync(kFull, cur0 | (neg0 << 1) | (cn0 << 2), 1);
+            if (lane == 31) rv = 0;
+            const unsigned cnr = rv >> 2;
+            // ---- column 1 ----
+            ctx = ((n1[qq] >> r0) & 15u) + pns + pnr + cn0 + cnr;
+            unsigned cn1 = dec_step(a41, bitm, sig_prob(tab, ctx), ac, in1, prec);
+            unsigned neg1 = (g41 >> qq) & 1u;
+            if (__any_sync(kFull, cn1)) {
+              const unsigned st = (c1[qq] >> r0) & 3u;
+              const unsigned sc = s_sign[cur0 | (neg0 << 1) | ((rv & 3u) << 2) | (u1 << 4) | (st << 6)];
+              const unsigned sym = dec_step(cn1, 1u, __byte_perm(tab.z, 0u, sc >> 1) & 0xFFu, ac, in1, prec);
+              if (cn1) neg1 = sym ^ (sc & 1u);
+            }
+            nb1 |= cn1 << (r0 + qq); ng1 |= (cn1 & neg1) << (r0 + qq);
+            const unsigned cur1 = ((s41 >> qq) & 1u) | cn1;
+            unsigned lv = __shfl_up_sync(kFull, cn1, 1);
+            if (lane == 0) lv = 0;
+            pns = cn0 + cn1; pnl = lv; pnr = cnr;
+            u0 = cur0 | (neg0 << 1); u1 = cur1 | (neg1 << 1);
           }
-          nb1 |= cn1 << j; nn1 |= cn1 << j; ng1 |= (cn1 & neg1) << j;
         }
-        const unsigned cur1 = (S1 & 1u) | cn1;
-        unsigned lv = __shfl_up_sync(kFull, cn1, 1);
-        if (lane == 0) lv = 0;
-        pn0 = cn0; pn1 = cn1; pnl = lv; pnr = cnr;
-        u0s = cur0; u0n = neg0; u1s = cur1; u1n = neg1;
-        S0 >>= 1; S1 >>= 1; G0 >>= 1; G1 >>= 1;
-        k00 >>= 1; k01 >>= 1; k02 >>= 1; k03 >>= 1; k10 >>= 1; k11 >>= 1; k12 >>= 1; k13 >>= 1;
-        hp0 >>= 1; hn0 >>= 1; dp0 >>= 1; dn0 >>= 1; dp1 >>= 1; dn1 >>= 1;
+      } else {
+        pns = 0; pnl = 0; pnr = 0;
+        u0 = (S0 >> 31) | ((G0 >> 31) << 1);
+        u1 = (S1 >> 31) | ((G1 >> 31) << 1);
       }
       B0 |= (u64)nb0 << sh; B1 |= (u64)nb1 << sh;
-      N0 |= (u64)nn0 << sh; N1 |= (u64)nn1 << sh;
+      N0 |= (u64)nb0 << sh; N1 |= (u64)nb1 << sh;
       g0 |= (u64)ng0 << sh; g1 |= (u64)ng1 << sh;
     }
-    // ---- magnitude refinement pass (BPCEngine.cu:742-762,1267-1279) ----
-    if (__any_sync(kFull, (s0 | s1) != 0)) {
+    // ---- magnitude refinement pass (BPCEngine.cu:742-762,1267-1279): only rows in which some lane refines ----
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const int sh = 32 * h;
-        unsigned r0 = (unsigned)(s0 >> sh), r1 = (unsigned)(s1 >> sh), nb0 = 0, nb1 = 0;
-#pragma unroll 2
-        for (int j = 0; j < 32; ++j) {
-          nb0 |= ac.decode(r0 & 1u, pr.ref, code, in) << j;
-          nb1 |= ac.decode(r1 & 1u, pr.ref, code, in) << j;
-          r0 >>= 1; r1 >>= 1;
-        }
-        B0 |= (u64)nb0 << sh; B1 |= (u64)nb1 << sh;
+    for (int h = 0; h < 2; ++h) {
+      const int sh = 32 * h;
+      const unsigned r0m = (unsigned)(s0 >> sh), r1m = (unsigned)(s1 >> sh);
+      unsigned nb0 = 0, nb1 = 0;
+      unsigned U = __reduce_or_sync(kFull, r0m | r1m);
+      while (U) {
+        const int r = __ffs(U) - 1;
+        U &= U - 1;
+        const unsigned bitm = 1u << r;
+        nb0 |= dec_step(r0m, bitm, pref, ac, in1, prec) << r;
+        nb1 |= dec_step(r1m, bitm, pref, ac, in1, prec) << r;
       }
+      B0 |= (u64)nb0 << sh; B1 |= (u64)nb1 << sh;
     }
     s0 |= N0; s1 |= N1;
-    if (bp < kSmemPlanes) {
-      planes[wib][bp][lane] = make_uint4((unsigned)B0, (unsigned)(B0 >> 32), (unsigned)B1, (unsigned)(B1 >> 32));
+    if (bp < 16) {
+      pl[bp][lane] = (unsigned)B0; pl[32 + bp][lane] = (unsigned)(B0 >> 32);
+      pl[16 + bp][lane] = (unsigned)B1; pl[48 + bp][lane] = (unsigned)(B1 >> 32);
     } else {
       for (int i = 0; i < kCB; ++i) {
         int2* d = reinterpret_cast<int2*>(dst + (size_t)i * p.Wa);
@@ -412,21 +659,21 @@ __global__ void __launch_bounds__(128) bpc_decode_kernel(const unsigned short* _
     }
   }
   __syncwarp();
-  // assemble magnitudes from the bit planes and write (BPCEngine.cu:94-111)
-  const int top = min(MSB, kSmemPlanes - 1);
+  // assemble magnitudes from the bit planes (transpose back), apply signs and write (BPCEngine.cu:94-111)
+#pragma unroll 1
   for (int h = 0; h < 2; ++h) {
-    for (int j = 0; j < 32; ++j) {
-      unsigned a = 0, b = 0;
-      for (int bp = 0; bp <= top; ++bp) {
-        const uint4 v = planes[wib][bp][lane];
-        a |= (((h ? v.y : v.x) >> j) & 1u) << bp;
-        b |= (((h ? v.w : v.z) >> j) & 1u) << bp;
-      }
-      const int i = 32 * h + j;
-      int2* d = reinterpret_cast<int2*>(dst + (size_t)i * p.Wa);
+    unsigned wv[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) wv[k] = pl[32 * h + k][lane];
+    transpose32(wv);
+    const unsigned sg0 = (unsigned)(g0 >> (32 * h)), sg1 = (unsigned)(g1 >> (32 * h));
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      int2* d = reinterpret_cast<int2*>(dst + (size_t)(32 * h + i) * p.Wa);
+      unsigned a = wv[i] & 0xFFFFu, b = wv[i] >> 16;
       if (hi_planes) { const int2 o = *d; a |= (unsigned)o.x; b |= (unsigned)o.y; }
       const int va = (int)a, vb = (int)b;
-      *d = make_int2(((g0 >> i) & 1ull) ? -va : va, ((g1 >> i) & 1ull) ? -vb : vb);
+      *d = make_int2(((sg0 >> i) & 1u) ? -va : va, ((sg1 >> i) & 1u) ? -vb : vb);
     }
   }
 }

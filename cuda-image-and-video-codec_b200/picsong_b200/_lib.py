@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libpicsong_b200.so")
+# PCS_LIB_PATH: developer override to A/B-test an alternative build of the same library (scripts/stage_time.py)
+LIB_PATH = os.environ.get("PCS_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "libpicsong_b200.so")
 
 
 class PcsParams(C.Structure):
