@@ -105,18 +105,18 @@ int build_prob_tables(pcs_ctx* c) {
       sig[r] |= (unsigned long long)v << (7 * k);
       if (k < 4) tab4[r].x |= (unsigned)v << (8 * k);
       else if (k < 8) tab4[r].y |= (unsigned)v << (8 * (k - 4));
-      else tab4[r].w |= (unsigned)v;
+      else tab4[r].z |= (unsigned)v;
     }
     for (int k = 0; k < 4; ++k) {
       const int v = k < cG ? at((long long)R + S + (long long)r * cG + k) : 0;
       if (v < 0 || v > 127) return PCS_E_LUT_RANGE;
       sgn[r] |= (unsigned)v << (7 * k);
-      tab4[r].z |= (unsigned)v << (8 * k);
+      tab4[r].w |= (unsigned)v << (8 * k);
     }
     const int v = at((long long)r * cR);
     if (v < 0 || v > 127) return PCS_E_LUT_RANGE;
     ref[r] = (unsigned char)v;
-    tab4[r].w |= (unsigned)v << 8;
+    tab4[r].z |= (unsigned)v << 8;
   }
   c->nrows = nrows;
   PCS_CUDA_TRY(cudaMalloc(&c->d_sigp, nrows * sizeof(unsigned long long)));

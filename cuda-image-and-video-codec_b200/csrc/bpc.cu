@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* 
       }
     }
     const uint4 tab = (row >= 0 && row < p.nrows) ? __ldg(p.tab4 + row) : make_uint4(0, 0, 0, 0);
-    const unsigned d8 = (tab.w & 0xFFu) - (tab.x & 0xFFu), pref = (tab.w >> 8) & 0xFFu;
+    const unsigned d8 = (tab.z & 0xFFu) - (tab.x & 0xFFu), pref = (tab.z >> 8) & 0xFFu;
     const u64 a0 = s0 | B0, a1 = s1 | B1;  // significant AFTER this plane's SPP visit
     const u64 Lb = shfl_up64(s1, lane), La = shfl_up64(a1, lane);
     const u64 Rb = shfl_down64(s0, lane), Ra = shfl_down64(a0, lane);
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* 
         for (int q = 0; q < 4; ++q) {
           const unsigned e0 = n0[q] >> (16 * jj), e1 = n1[q] >> (16 * jj);
           P0[q] = lut4(tab.x, tab.y, e0); P1[q] = lut4(tab.x, tab.y, e1);
-          S0[q] = lut4(tab.z, 0u, i0[q] >> (16 * jj)); S1[q] = lut4(tab.z, 0u, i1[q] >> (16 * jj));
+          S0[q] = lut4(tab.w, 0u, i0[q] >> (16 * jj)); S1[q] = lut4(tab.w, 0u, i1[q] >> (16 * jj));
         }
         if (has8) {
 #pragma unroll
@@ -436,11 +436,17 @@ __device__ __forceinline__ unsigned sign_ctx(int h, int v) {
   return (kSignTab >> (3 * ((sh + 1) * 3 + (sv + 1)))) & 7u;
 }
 __device__ __forceinline__ int contrib(unsigned sig, unsigned neg) { return sig ? (neg ? -1 : 1) : 0; }
-// Entry of the decoder's sign-context byte table.  Index bits: [1:0] left (significant, negative),
-// [3:2] right, [5:4] up, [7:6] down.
-__device__ __forceinline__ unsigned sign_entry(unsigned i) {
-  const int h = contrib(i & 1u, (i >> 1) & 1u) + contrib((i >> 2) & 1u, (i >> 3) & 1u);
-  const int v = contrib((i >> 4) & 1u, (i >> 5) & 1u) + contrib((i >> 6) & 1u, (i >> 7) & 1u);
+// Entries of the decoder's sign-context byte tables (value: bit 0 = flip, bits 2:1 = probability index).
+// Column 0, index bits: [1:0] static horizontal sum as (non-zero, negative), [3:2] down, [5:4] up.
+__device__ __forceinline__ unsigned sign_entry0(unsigned i) {
+  const int h = contrib(i & 1u, (i >> 1) & 1u);
+  const int v = contrib((i >> 4) & 1u, (i >> 5) & 1u) + contrib((i >> 2) & 1u, (i >> 3) & 1u);
+  return sign_ctx(h, v);
+}
+// Column 1, index bits: [1:0] down, [3:2] left, [5:4] right, [7:6] up (each: significant, negative).
+__device__ __forceinline__ unsigned sign_entry1(unsigned i) {
+  const int h = contrib((i >> 2) & 1u, (i >> 3) & 1u) + contrib((i >> 4) & 1u, (i >> 5) & 1u);
+  const int v = contrib((i >> 6) & 1u, (i >> 7) & 1u) + contrib(i & 1u, (i >> 1) & 1u);
   return sign_ctx(h, v);
 }
 
@@ -473,8 +479,7 @@ __device__ __forceinline__ unsigned dec_step(unsigned actw, unsigned bitm, unsig
       "shr.u32 q, r, %10;\n\t"
       "add.u32 t, q, 1;\n\t"
       "add.u32 lim, %0, t;\n\t"
-      "setp.ge.and.u32 pb, %4, lim, pact;\n\t"
-      "setp.lt.and.u32 pnb, %4, lim, pact;\n\t"
+      "setp.ge.and.u32 pb|pnb, %4, lim, pact;\n\t"
       "@pb sub.u32 %1, %1, t;\n\t"
       "@pb mov.u32 %0, lim;\n\t"
       "@pnb mov.u32 %1, q;\n\t"
@@ -486,11 +491,7 @@ __device__ __forceinline__ unsigned dec_step(unsigned actw, unsigned bitm, unsig
   return b;
 }
 
-// probability of significance context 0..8 from the byte table
-__device__ __forceinline__ unsigned sig_prob(const uint4& tab, unsigned ctx) {
-  const unsigned pr = __byte_perm(tab.x, tab.y, ctx & 7u);
-  return (ctx & 8u) ? (tab.w & 0xFFu) : (pr & 0xFFu);
-}
+constexpr int kMaxProbRows = (3 * kMaxLevels + 1) * 15 + 32;  // shipped tables: nSub = 3, nBp = 15
 
 #ifndef PCS_DEC_MINB
 #define PCS_DEC_MINB 4
@@ -500,9 +501,17 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
   // decoded magnitude bit planes, same layout as the encoder's: word [32*half + k][lane], k < 16: plane k of
   // column 0, k >= 16: plane k-16 of column 1
   __shared__ unsigned s_pl[4][64][32];
-  __shared__ unsigned char s_sign[256];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_sign[i] = (unsigned char)sign_entry((unsigned)i);
+  __shared__ unsigned char s_sign0[64], s_sign1[256];
+  // probability bytes per table row: [0..8] significance contexts, [9] refinement, [12..15] sign contexts
+  __shared__ uint4 s_tab[kMaxProbRows + 1];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    s_sign1[i] = (unsigned char)sign_entry1((unsigned)i);
+    if (i < 64) s_sign0[i] = (unsigned char)sign_entry0((unsigned)i);
+  }
+  const int zero_row = min(p.nrows, kMaxProbRows);  // rows outside the table read as zero probabilities
+  for (int i = threadIdx.x; i <= zero_row; i += blockDim.x) s_tab[i] = i < zero_row ? __ldg(p.tab4 + i) : make_uint4(0, 0, 0, 0);
   __syncthreads();
+  const unsigned char* const s_prob = reinterpret_cast<const unsigned char*>(s_tab);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int w = blockIdx.x * (blockDim.x >> 5) + wib;
   if (w >= p.total_cb) return;
@@ -538,8 +547,8 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
   DecState ac; ac.lower = 0; ac.size = 0; ac.slot = 0; ac.count = 0; ac.code = 0; ac.lt = (1u << lane) - 1u;
   u64 s0 = 0, s1 = 0, g0 = 0, g1 = 0;  // significant before this plane; sign (1 = negative) of significant samples
   for (int bp = MSB; bp >= 0; --bp, --row) {
-    const uint4 tab = (row >= 0 && row < p.nrows) ? __ldg(p.tab4 + row) : make_uint4(0, 0, 0, 0);
-    const unsigned pref = (tab.w >> 8) & 0xFFu;
+    const unsigned char* const prob = s_prob + 16 * ((row >= 0 && row < zero_row) ? row : zero_row);
+    const unsigned pref = prob[9];
     const u64 Lb = shfl_up64(s1, lane), Lg = shfl_up64(g1, lane), Rb = shfl_down64(s0, lane);
     // static part of the contexts: state BEFORE this pass of all eight neighbours
     u64 K0[4], K1[4];
@@ -555,7 +564,8 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
 
     u64 B0 = 0, B1 = 0;  // decoded 1-bits of this plane
     u64 N0 = 0, N1 = 0;  // newly significant in this pass
-    // carried from the previous row: "became significant in this pass" flags and (significant | negative << 1) of row i-1
+    // carried from the previous row: "became significant in this pass" flags; u0 / u1 = (significant | negative << 1)
+    // of row i-1, kept pre-shifted to their position in the sign-table index (<< 4 / << 6)
     unsigned pns = 0, pnl = 0, pnr = 0, u0 = 0, u1 = 0;
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
@@ -563,7 +573,8 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
       const unsigned S0 = (unsigned)(s0 >> sh), S1 = (unsigned)(s1 >> sh), G0 = (unsigned)(g0 >> sh), G1 = (unsigned)(g1 >> sh);
       const unsigned A0 = ~S0, A1 = ~S1;
       const unsigned anyact = __reduce_or_sync(kFull, A0 | A1);
-      unsigned nb0 = 0, nb1 = 0, ng0 = 0, ng1 = 0;  // this half's decoded bits (= new flags) and new signs, row i at bit i
+      // this half's decoded bits (= new flags) and new signs; rows are shifted in from the top, so row i ends at bit i
+      unsigned nb0 = 0, nb1 = 0, ng0 = 0, ng1 = 0;
       if (anyact != 0) {
         unsigned n0[4] = {(unsigned)(K0[0] >> sh), (unsigned)(K0[1] >> sh), (unsigned)(K0[2] >> sh), (unsigned)(K0[3] >> sh)};
         unsigned n1[4] = {(unsigned)(K1[0] >> sh), (unsigned)(K1[1] >> sh), (unsigned)(K1[2] >> sh), (unsigned)(K1[3] >> sh)};
@@ -577,8 +588,9 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
           if (((anyact >> r0) & 15u) == 0) {
             // nobody decodes in these rows: nothing becomes significant; carry the state of row 4g+3
             pns = 0; pnl = 0; pnr = 0;
-            u0 = ((S0 >> (r0 + 3)) & 1u) | (((G0 >> (r0 + 3)) & 1u) << 1);
-            u1 = ((S1 >> (r0 + 3)) & 1u) | (((G1 >> (r0 + 3)) & 1u) << 1);
+            u0 = (((S0 >> (r0 + 3)) & 1u) | (((G0 >> (r0 + 3)) & 1u) << 1)) << 4;
+            u1 = (((S1 >> (r0 + 3)) & 1u) | (((G1 >> (r0 + 3)) & 1u) << 1)) << 6;
+            nb0 >>= 4; nb1 >>= 4; ng0 >>= 4; ng1 >>= 4;
             continue;
           }
           const unsigned a40 = A0 >> r0, a41 = A1 >> r0, s40 = S0 >> r0, s41 = S1 >> r0, g40 = G0 >> r0, g41 = G1 >> r0;
@@ -586,44 +598,42 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
           for (int qq = 0; qq < 4; ++qq) {
             const unsigned bitm = 1u << qq;
             // ---- column 0 ----
-            unsigned ctx = ((n0[qq] >> r0) & 15u) + pnl + pns;
-            unsigned cn0 = dec_step(a40, bitm, sig_prob(tab, ctx), ac, in1, prec);
+            unsigned ctx = (n0[qq] >> r0) + pnl + pns;  // bits above the nibble are masked at the look-up
+            const unsigned cn0 = dec_step(a40, bitm, prob[ctx & 15u], ac, in1, prec);
             unsigned neg0 = (g40 >> qq) & 1u;
             if (__any_sync(kFull, cn0)) {
-              // left/right: static (fake left = sign of the static horizontal sum), up: row i-1 now, down: static
-              const unsigned st = (c0[qq] >> r0) & 15u;
-              const unsigned sc = s_sign[(st & 3u) | (u0 << 4) | ((st & 12u) << 4)];
-              const unsigned sym = dec_step(cn0, 1u, __byte_perm(tab.z, 0u, sc >> 1) & 0xFFu, ac, in1, prec);
-              if (cn0) neg0 = sym ^ (sc & 1u);  // BPCEngine.cu:583-589
+              // horizontal: static (sign of the static sum), up: row i-1 now, down: static
+              const unsigned sc = s_sign0[((c0[qq] >> r0) & 15u) | u0];
+              const unsigned sym = dec_step(cn0, 1u, prob[12u + (sc >> 1)], ac, in1, prec);
+              if (cn0) neg0 = (sym ^ sc) & 1u;  // BPCEngine.cu:583-589
             }
-            nb0 |= cn0 << (r0 + qq); ng0 |= (cn0 & neg0) << (r0 + qq);
-            const unsigned cur0 = ((s40 >> qq) & 1u) | cn0;
-            // right neighbour's (i, column 0): current significance, sign, new flag
-            unsigned rv = __shfl_down_sync(kFull, cur0 | (neg0 << 1) | (cn0 << 2), 1);
+            nb0 = __funnelshift_r(nb0, cn0, 1); ng0 = __funnelshift_r(ng0, cn0 & neg0, 1);
+            const unsigned cur0 = (((s40 >> qq) & 1u) | cn0) | (neg0 << 1);  // significant | negative << 1
+            // right neighbour's (i, column 0): state and new flag
+            unsigned rv = __shfl_down_sync(kFull, cur0 | (cn0 << 2), 1);
             if (lane == 31) rv = 0;
             const unsigned cnr = rv >> 2;
             // ---- column 1 ----
-            ctx = ((n1[qq] >> r0) & 15u) + pns + pnr + cn0 + cnr;
-            unsigned cn1 = dec_step(a41, bitm, sig_prob(tab, ctx), ac, in1, prec);
+            ctx = (n1[qq] >> r0) + pns + pnr + cn0 + cnr;
+            const unsigned cn1 = dec_step(a41, bitm, prob[ctx & 15u], ac, in1, prec);
             unsigned neg1 = (g41 >> qq) & 1u;
             if (__any_sync(kFull, cn1)) {
-              const unsigned st = (c1[qq] >> r0) & 3u;
-              const unsigned sc = s_sign[cur0 | (neg0 << 1) | ((rv & 3u) << 2) | (u1 << 4) | (st << 6)];
-              const unsigned sym = dec_step(cn1, 1u, __byte_perm(tab.z, 0u, sc >> 1) & 0xFFu, ac, in1, prec);
-              if (cn1) neg1 = sym ^ (sc & 1u);
+              const unsigned sc = s_sign1[((c1[qq] >> r0) & 3u) | (cur0 << 2) | ((rv & 3u) << 4) | u1];
+              const unsigned sym = dec_step(cn1, 1u, prob[12u + (sc >> 1)], ac, in1, prec);
+              if (cn1) neg1 = (sym ^ sc) & 1u;
             }
-            nb1 |= cn1 << (r0 + qq); ng1 |= (cn1 & neg1) << (r0 + qq);
-            const unsigned cur1 = ((s41 >> qq) & 1u) | cn1;
+            nb1 = __funnelshift_r(nb1, cn1, 1); ng1 = __funnelshift_r(ng1, cn1 & neg1, 1);
+            const unsigned cur1 = (((s41 >> qq) & 1u) | cn1) | (neg1 << 1);
             unsigned lv = __shfl_up_sync(kFull, cn1, 1);
             if (lane == 0) lv = 0;
             pns = cn0 + cn1; pnl = lv; pnr = cnr;
-            u0 = cur0 | (neg0 << 1); u1 = cur1 | (neg1 << 1);
+            u0 = cur0 << 4; u1 = cur1 << 6;
           }
         }
       } else {
         pns = 0; pnl = 0; pnr = 0;
-        u0 = (S0 >> 31) | ((G0 >> 31) << 1);
-        u1 = (S1 >> 31) | ((G1 >> 31) << 1);
+        u0 = ((S0 >> 31) | ((G0 >> 31) << 1)) << 4;
+        u1 = ((S1 >> 31) | ((G1 >> 31) << 1)) << 6;
       }
       B0 |= (u64)nb0 << sh; B1 |= (u64)nb1 << sh;
       N0 |= (u64)nb0 << sh; N1 |= (u64)nb1 << sh;

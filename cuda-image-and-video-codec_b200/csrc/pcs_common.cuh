@@ -34,7 +34,7 @@ struct BpcArgs {
   const unsigned long long* sigp;  // [nrows] 9 x 7-bit P(0) per significance context
   const unsigned* sgnp;            // [nrows] 4 x 7-bit per sign context
   const unsigned char* refp;       // [nrows] refinement probability
-  const uint4* tab4;               // [nrows] the same as bytes: x = sig ctx 0..3, y = sig ctx 4..7, z = sign 0..3, w = sig ctx 8 | ref << 8
+  const uint4* tab4;               // [nrows] the same as bytes: x = sig ctx 0..3, y = sig ctx 4..7, z = sig ctx 8 | ref << 8, w = sign ctx 0..3
 };
 // Arguments of the bit-stream builder kernels (bsb.cu)
 struct BsbArgs {
