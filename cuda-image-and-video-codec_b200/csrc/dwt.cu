@@ -20,6 +20,8 @@
 // 9/7 arithmetic uses explicit __fmaf_rn/__fadd_rn/__fmul_rn so that the operation shapes are
 // exactly those of the reference binary, including its one cross-statement FMA contraction
 // (vertical scale fused into horizontal step one on odd columns; see oracle/picsong_oracle.c).
+#include <cstdlib>
+
 #include "pcs_common.cuh"
 
 namespace pcs {
@@ -523,12 +525,34 @@ static size_t ll_offset(int Wa, int Ha, int l) {
   return n;
 }
 
+bool dwt_forward_fused_ok(const void*, const void*, const void*, int, int, int, int, int);
+int dwt_forward_fused(const uint8_t*, void*, void*, long long, int, int, int, int, int, int, bool, float, bool, int, int, cudaStream_t);
+
+// PCS_DWT_FUSE = 0 | 1 | 2: how many leading levels the fused streaming kernel (dwt_fast.cu) may take (default 2)
+static int fuse_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("PCS_DWT_FUSE");
+    mode = e ? atoi(e) : 2;
+    if (mode < 0 || mode > 2) mode = 2;
+  }
+  return mode;
+}
+
 // Host loop over levels (replaces DWTEngine::DWTForward, DWT/DWTGenerator.cu:1268-1342; no host
 // synchronisation between levels).  out_int: 9/7 only, write (int)c instead of c.
 int dwt_forward(const uint8_t* d_px, void* d_coeff, void* d_scratch, int W, int H, int Wa, int Ha, int wl,
                 bool lossy, float qs, bool out_int, int frames, cudaStream_t st) {
   const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl);
-  for (int l = 1; l <= wl; ++l) {
+  int first = 1;
+  if (fuse_mode() > 0 && S % 4 == 0 && dwt_forward_fused_ok(d_px, d_coeff, d_scratch, W, H, Wa, Ha, wl)) {
+    const int lv = wl >= 2 ? fuse_mode() : 1;
+    int rc = dwt_forward_fused(d_px, d_coeff, static_cast<char*>(d_scratch) + ll_offset(Wa, Ha, lv) * 4, (long long)S, Wa >> lv, W, H, Wa, Ha,
+                               wl, lossy, qs, out_int, frames, lv, st);
+    if (rc) return rc;
+    first = lv + 1;
+  }
+  for (int l = first; l <= wl; ++l) {
     FwdArgs a{};
     a.Wc = Wa >> (l - 1); a.Hc = Ha >> (l - 1);
     a.W = W; a.H = H; a.Wa = Wa;

@@ -1,0 +1,393 @@
+// dwt_fast.cu -- fused two-level forward lifting DWT for sm_100a (the bandwidth-critical front of the
+// forward transform): u8 pixels -> level-1 HL/LH/HH and level-2 HL/LH/HH (+ LL2) in ONE pass.
+//
+// Replaces, for frames whose width needs no padding (W == W_a), the first two iterations of the
+// reference's host loop DWTEngine::DWTForward (DWT/DWTGenerator.cu:1268-1342: one kernel + one
+// cudaStreamSynchronize per level, int32/f32 LL ping-pong through global memory) together with
+// offsetImage (Engines/CodingEngine.cu:581-588).  Arithmetic, boundary rules and the quantiser are the
+// ones of dwt.cu / oracle/picsong_oracle.c, bit for bit.
+//
+// Design: a warp owns a 256-pixel-wide strip (8 pixels per lane, 16-byte subband stores) and streams
+// down a chunk of rows.  Level 1 runs as a register pipeline (vertical lifting state per column,
+// horizontal lifting with 4 shuffles per row); the LL samples it produces -- 4 per lane, exactly the
+// operand layout of a 4-sample-per-lane transform -- feed a second register pipeline for level 2 in
+// the same warp, so LL1 never exists in memory.  HBM traffic per frame: 1 B/px read, 4 B/px
+// written, + LL2 (A/16 samples) for the remaining levels.  Lanes 0,1,30,31 are halo (level 1 needs
+// one neighbour lane, level 2 one more); image borders are handled by explicit mirror rules in the
+// lifting steps, so halo lanes outside the image never influence a result.
+#include "pcs_common.cuh"
+
+namespace pcs {
+
+namespace {
+
+constexpr float kA = -1.586134342059924f, kB = -0.052980118572961f, kG = 0.882911075530934f,
+                kD = 0.443506852043971f, kK = 1.230174104914001f, kIK = 0.812893066f;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+struct FastFwdArgs {
+  const unsigned char* px; long long px_fstride; int W, H;  // W == Wa
+  void* out; long long out_fstride; int Wa, Ha;             // Mallat plane
+  void* ll; long long ll_fstride; int ll_pitch;             // LL destination of the LAST fused level (scratch), unless `last`
+  int last;                                                 // the last fused level is the last level: LL goes to `out`, quantised
+  float q1[4], q2[4], qs;                                   // quantiser steps of levels 1, 2: LL, HL, LH, HH
+  int nW1, ls1, nW2, ls2;                                   // row-variant tiling of the reference, per level (9/7 only)
+  int nstrips, nchunks, rp;                                 // rp: level-1 row pairs per chunk (multiple of 4)
+};
+
+// Which row PAIR the reference computes with the fused neighbour sum (dwt.cu fwd97_row_variant restated
+// per pair: both rows of a pair always agree because tile seams are even).
+__device__ __forceinline__ bool pair_variant(int n, int nW, int ls) {
+  if (nW <= 1) return n >= 6;
+  if (2 * n >= ls + 4) return 2 * n - ls >= 12;
+  if (n < 7) return n >= 6;
+  return (n - 2) % 5 == 4;
+}
+
+template <typename OT> __device__ __forceinline__ OT cvt(float v);
+template <> __device__ __forceinline__ float cvt<float>(float v) { return v; }
+template <> __device__ __forceinline__ int cvt<int>(float v) { return __float2int_rz(v); }  // BPCEngine.cu:49
+template <typename OT> __device__ __forceinline__ OT quant(float v, float q, float qs) { return cvt<OT>(__fmul_rn(__fmul_rn(v, q), qs)); }
+
+// ---- horizontal analysis, N samples per lane (N = 8: level 1, N = 4: level 2) ----------------------
+// 5/3 (DWTGenerator.cu:72-76,279-292).  left: the lane holds image column 0 (d[-1] := d[0]);
+// right: the lane's last pair is the image's last pair (x[Wc] := x[Wc-2]).
+template <int N>
+__device__ __forceinline__ void hfwd53(int (&x)[N], bool left, bool right) {
+  constexpr int P = N / 2;
+  int nx = __shfl_down_sync(kFullMask, x[0], 1);
+  if (right) nx = x[N - 2];
+  int d[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) d[k] = x[2 * k + 1] - ((x[2 * k] + (k + 1 < P ? x[2 * k + 2] : nx)) >> 1);
+  int pd = __shfl_up_sync(kFullMask, d[P - 1], 1);
+  if (left) pd = d[0];
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    x[2 * k] = x[2 * k] + (((k ? d[k - 1] : pd) + d[k] + 2) >> 2);
+    x[2 * k + 1] = d[k];
+  }
+}
+
+// 9/7 (DWTGenerator.cu:91-104,311-323) of a row whose vertical-pass scale S is still pending; see
+// dwt.cu hfwd97 for the operation shapes (they are the reference binary's, FMA contractions included).
+template <int N>
+__device__ __forceinline__ void hfwd97(float (&x)[N], float S, bool fused_sum, bool left, bool right) {
+  constexpr int P = N / 2;
+  float e[P], o[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) e[k] = __fmul_rn(x[2 * k], S);
+  float n0 = __shfl_down_sync(kFullMask, e[0], 1);
+  if (right) n0 = e[P - 1];
+  if (fused_sum) {
+#pragma unroll
+    for (int k = 0; k < P; ++k) o[k] = __fmaf_rn(x[2 * k], S, k + 1 < P ? e[k + 1] : n0);
+  } else {
+#pragma unroll
+    for (int k = 0; k < P; ++k) o[k] = __fadd_rn(e[k], k + 1 < P ? e[k + 1] : n0);
+  }
+#pragma unroll
+  for (int k = 0; k < P; ++k) o[k] = __fmaf_rn(x[2 * k + 1], S, __fmul_rn(o[k], kA));
+  float p1 = __shfl_up_sync(kFullMask, o[P - 1], 1);
+  if (left) p1 = o[0];
+#pragma unroll
+  for (int k = P - 1; k >= 0; --k) e[k] = __fmaf_rn(__fadd_rn(k ? o[k - 1] : p1, o[k]), kB, e[k]);
+  n0 = __shfl_down_sync(kFullMask, e[0], 1);
+  if (right) n0 = e[P - 1];
+#pragma unroll
+  for (int k = 0; k < P; ++k) o[k] = __fmaf_rn(__fadd_rn(e[k], k + 1 < P ? e[k + 1] : n0), kG, o[k]);
+  p1 = __shfl_up_sync(kFullMask, o[P - 1], 1);
+  if (left) p1 = o[0];
+#pragma unroll
+  for (int k = P - 1; k >= 0; --k) e[k] = __fmul_rn(__fmaf_rn(__fadd_rn(k ? o[k - 1] : p1, o[k]), kD, e[k]), kIK);
+#pragma unroll
+  for (int k = 0; k < P; ++k) { x[2 * k] = e[k]; x[2 * k + 1] = __fmul_rn(o[k], kK); }
+}
+
+// ---- vertical analysis pipelines (state per column) ------------------------------------------------
+// 5/3: step m consumes rows 2m+1, 2m+2 and produces row pair m.  d[n] = x[2n+1] - ((x[2n]+x[2n+2])>>1),
+// s[n] = x[2n] + ((d[n-1]+d[n]+2)>>2)  (DWTGenerator.cu:72-76,137-157).
+template <int N>
+struct V53 {
+  int xe[N], dp[N];
+  static constexpr int kDelay = 0, kWarm = 1;
+  __device__ __forceinline__ void init(const int (&r)[N]) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) { xe[j] = r[j]; dp[j] = 0; }
+  }
+  // top: first pair of the image (d[-1] := d[0]); the bottom rule (x[N] := x[N-2]) is applied by the caller to x2
+  __device__ __forceinline__ void step(const int (&xo)[N], const int (&x2)[N], bool top, int (&lo)[N], int (&hi)[N]) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const int d = xo[j] - ((xe[j] + x2[j]) >> 1);
+      const int p = top ? d : dp[j];
+      lo[j] = xe[j] + ((p + d + 2) >> 2);
+      hi[j] = d; dp[j] = d; xe[j] = x2[j];
+    }
+  }
+};
+// 9/7: step m consumes rows 2m+1, 2m+2 and produces row pair m-1 (scales 1/K, K still pending)
+// (DWTGenerator.cu:91-104,184-227).
+template <int N>
+struct V97 {
+  float xe[N], o1p[N], e1p[N], o2pp[N];
+  static constexpr int kDelay = 1, kWarm = 2;
+  __device__ __forceinline__ void init(const float (&r)[N]) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) { xe[j] = r[j]; o1p[j] = 0.f; e1p[j] = 0.f; o2pp[j] = 0.f; }
+  }
+  // m0: this is step 0 of the image (o1[-1] := o1[0]); m1: step 1 (o2[-1] := o2[0]);
+  // flush: one step past the last pair (e1[n/2] := e1[n/2-1]); xo/x2 are ignored then
+  __device__ __forceinline__ void step(const float (&xo)[N], const float (&x2)[N], bool m0, bool m1, bool flush,
+                                       float (&lo)[N], float (&hi)[N]) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const float o1 = __fmaf_rn(__fadd_rn(xe[j], x2[j]), kA, xo[j]);
+      const float op = m0 ? o1 : o1p[j];
+      float e1 = __fmaf_rn(__fadd_rn(op, o1), kB, xe[j]);
+      if (flush) e1 = e1p[j];
+      const float o2 = __fmaf_rn(__fadd_rn(e1p[j], e1), kG, op);       // o2[m-1]
+      const float opp = m1 ? o2 : o2pp[j];
+      lo[j] = __fmaf_rn(__fadd_rn(opp, o2), kD, e1p[j]);               // e2[m-1]
+      hi[j] = o2;
+      xe[j] = x2[j]; o1p[j] = o1; e1p[j] = e1; o2pp[j] = o2;
+    }
+  }
+};
+
+template <bool LOSSY, int N> struct VSel { using type = V53<N>; using T = int; };
+template <int N> struct VSel<true, N> { using type = V97<N>; using T = float; };
+
+// 8 pixels of a u8 row -> T (px - 128; for 5/3 the shift is applied to the LL output instead, which is
+// exact because every high-pass step is shift-invariant and the low-pass steps carry the offset through)
+__device__ __forceinline__ void unpack8(uint2 p, float (&v)[8]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[j] = __fadd_rn(__uint_as_float(__byte_perm(p.x, 0x4B000000u, 0x7540u + j)), -8388736.0f);      // 2^23 + b - (2^23 + 128)
+    v[4 + j] = __fadd_rn(__uint_as_float(__byte_perm(p.y, 0x4B000000u, 0x7540u + j)), -8388736.0f);
+  }
+}
+__device__ __forceinline__ void unpack8(uint2 p, int (&v)[8]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[j] = (int)__byte_perm(p.x, 0u, 0x4440u + j) - 128;
+    v[4 + j] = (int)__byte_perm(p.y, 0u, 0x4440u + j) - 128;
+  }
+}
+
+template <typename OT> struct V4;
+template <> struct V4<int> { using type = int4; };
+template <> struct V4<float> { using type = float4; };
+template <typename OT> struct V2;
+template <> struct V2<int> { using type = int2; };
+template <> struct V2<float> { using type = float2; };
+
+template <typename OT>
+__device__ __forceinline__ void st4(OT* p, OT a, OT b, OT c, OT d) {
+  typename V4<OT>::type t; t.x = a; t.y = b; t.z = c; t.w = d;
+  *reinterpret_cast<typename V4<OT>::type*>(p) = t;
+}
+template <typename OT>
+__device__ __forceinline__ void st2(OT* p, OT a, OT b) {
+  typename V2<OT>::type t; t.x = a; t.y = b;
+  *reinterpret_cast<typename V2<OT>::type*>(p) = t;
+}
+
+// Stores the three (or four) subband rows of one row pair.  NS = samples per lane per row (8 or 4).
+template <bool LOSSY, typename OT, typename T, int NS>
+__device__ __forceinline__ void emit_pair(const T (&lo)[NS], const T (&hi)[NS], OT* row_lo, OT* row_hi, int hw, const float (&q)[4], float qs,
+                                          bool ll_to_out, T* ll_dst) {
+  constexpr int P = NS / 2;
+  OT v[4][P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    if constexpr (LOSSY) {
+      v[0][k] = quant<OT>(lo[2 * k], q[0], qs); v[1][k] = quant<OT>(lo[2 * k + 1], q[1], qs);
+      v[2][k] = quant<OT>(hi[2 * k], q[2], qs); v[3][k] = quant<OT>(hi[2 * k + 1], q[3], qs);
+    } else {
+      v[0][k] = lo[2 * k]; v[1][k] = lo[2 * k + 1]; v[2][k] = hi[2 * k]; v[3][k] = hi[2 * k + 1];
+    }
+  }
+  if constexpr (P == 4) {
+    st4<OT>(row_lo + hw, v[1][0], v[1][1], v[1][2], v[1][3]);
+    st4<OT>(row_hi, v[2][0], v[2][1], v[2][2], v[2][3]);
+    st4<OT>(row_hi + hw, v[3][0], v[3][1], v[3][2], v[3][3]);
+    if (ll_to_out) st4<OT>(row_lo, v[0][0], v[0][1], v[0][2], v[0][3]);
+    else if (ll_dst) st4<T>(ll_dst, lo[0], lo[2], lo[4], lo[6]);
+  } else {
+    st2<OT>(row_lo + hw, v[1][0], v[1][1]);
+    st2<OT>(row_hi, v[2][0], v[2][1]);
+    st2<OT>(row_hi + hw, v[3][0], v[3][1]);
+    if (ll_to_out) st2<OT>(row_lo, v[0][0], v[0][1]);
+    else if (ll_dst) st2<T>(ll_dst, lo[0], lo[2]);
+  }
+}
+
+// LEVELS = 1: level 1 only (LL1 -> scratch or, if last, -> out); LEVELS = 2: levels 1 and 2 fused.
+template <bool LOSSY, typename OT, int LEVELS>
+__global__ void __launch_bounds__(128, 3) dwt_forward_fused(const FastFwdArgs a) {
+  using T = typename VSel<LOSSY, 8>::T;
+  using VP1 = typename VSel<LOSSY, 8>::type;
+  using VP2 = typename VSel<LOSSY, 4>::type;
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= a.nstrips * a.nchunks) return;
+  const int frame = blockIdx.y;
+  const int strip = item % a.nstrips, chunk = item / a.nstrips;
+  constexpr int kHalo = LEVELS;                        // halo lanes per side
+  constexpr int kEff = (32 - 2 * kHalo) * 8;           // effective columns per strip
+  const int Wa = a.Wa, Ha = a.Ha, hw1 = Wa >> 1, hh1 = Ha >> 1, hw2 = Wa >> 2, hh2 = Ha >> 2;
+  const int c0 = strip * kEff - 8 * kHalo + 8 * lane;  // first of the lane's 8 columns
+  const bool inimg = c0 >= 0 && c0 < Wa;
+  const bool wlane = lane >= kHalo && lane < 32 - kHalo && inimg;
+  const bool left = c0 == 0, right = c0 + 8 == Wa;
+  // lanes outside the image read inside it; their values are never used (explicit border rules)
+  const unsigned char* const px = a.px + (size_t)frame * a.px_fstride + min(max(c0, 0), Wa - 8);
+  OT* const out = static_cast<OT*>(a.out) + (size_t)frame * a.out_fstride;
+  T* const llbase = a.last ? nullptr : static_cast<T*>(a.ll) + (size_t)frame * a.ll_fstride;
+
+  // level-1 row pairs [n0, n1) and level-2 row pairs [m2_0, m2_1) are written by this chunk
+  const int n0 = chunk * a.rp, n1 = min(n0 + a.rp, hh1);
+  const int m2_0 = n0 >> 1, m2_1 = n1 >> 1;
+  const int M0 = max(m2_0 - VP2::kWarm, 0);  // first level-2 step; it starts from LL1 row 2*M0
+  // first / last level-1 pair whose output is needed (by level 1 itself and by level 2)
+  const int P0 = LEVELS == 2 ? min(n0, 2 * M0) : n0;
+  const int Plast = LEVELS == 2 ? min(max(n1 - 1, 2 * (m2_1 - 1 + VP2::kDelay) + 2), hh1 - 1) : n1 - 1;
+
+  auto load_row = [&](int y) -> uint2 {  // whole-sample fold at the adapted borders, then the pad mapping
+    int ys = y < 0 ? -y : (y >= Ha ? 2 * (Ha - 1) - y : y);
+    ys = ys < a.H ? ys : 2 * a.H - 1 - ys;
+    return __ldg(reinterpret_cast<const uint2*>(px + (size_t)ys * a.W));
+  };
+
+  VP1 v1;
+  VP2 v2;
+  T ll_odd[4] = {};  // buffered odd LL1 row for level 2
+  const int ms = P0 - VP1::kWarm;          // first level-1 step: pair P0 is the first valid one
+  const int mend = Plast + VP1::kDelay;    // last level-1 step
+  {
+    T r[8];
+    unpack8(load_row(2 * ms), r);
+    v1.init(r);
+  }
+  uint2 pa = load_row(2 * ms + 1), pb = load_row(2 * ms + 2);  // rows of the current step
+  uint2 qa = load_row(2 * ms + 3), qb = load_row(2 * ms + 4);  // rows of the next step (prefetch)
+
+  for (int m = ms; m <= mend; ++m) {
+    T xo[8], x2[8], lo[8], hi[8];
+    unpack8(pa, xo); unpack8(pb, x2);
+    pa = qa; pb = qb;
+    if (m + 2 <= mend) { qa = load_row(2 * m + 5); qb = load_row(2 * m + 6); }
+    // level-1 borders come from the folded loads, so no explicit rule here
+    if constexpr (LOSSY) v1.step(xo, x2, false, false, false, lo, hi);
+    else v1.step(xo, x2, false, lo, hi);
+    const int pr = m - VP1::kDelay;  // row pair leaving the vertical pipeline
+    if (pr < P0) continue;           // warm-up (warp-uniform)
+    if constexpr (LOSSY) {
+      const bool var = pair_variant(pr, a.nW1, a.ls1);
+      hfwd97<8>(lo, kIK, var, left, right);
+      hfwd97<8>(hi, kK, var, left, right);
+    } else {
+      hfwd53<8>(lo, left, right);
+      hfwd53<8>(hi, left, right);
+    }
+    if (wlane && pr >= n0 && pr < n1) {
+      const int oc1 = c0 >> 1;
+      emit_pair<LOSSY, OT, T, 8>(lo, hi, out + (size_t)pr * Wa + oc1, out + (size_t)(pr + hh1) * Wa + oc1, hw1, a.q1, a.qs,
+                                 LEVELS == 1 && a.last, (LEVELS == 1 && !a.last) ? llbase + (size_t)pr * a.ll_pitch + oc1 : nullptr);
+    }
+    if constexpr (LEVELS == 2) {
+      // ---- level 2 in the same warp: LL1 row R arrives, 4 samples per lane (LL1 columns c0/2 .. c0/2+3) ----
+      const int R = pr;
+      if (R < 2 * M0) continue;
+      T row[4] = {lo[0], lo[2], lo[4], lo[6]};
+      if (R == 2 * M0) { v2.init(row); continue; }
+      const bool lastrow = R == hh1 - 1;  // bottom of the image: LL1 row hh1 does not exist
+      if (R & 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ll_odd[j] = row[j];
+        if (!lastrow) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) row[j] = v2.xe[j];  // x[n] := x[n-2]
+      }
+      // normally one step (M = R/2 - 1); at the bottom row the last step and, for 9/7, the flush step
+      const int Mfirst = lastrow ? (R - 1) >> 1 : (R >> 1) - 1;
+      const int Mlast = lastrow ? Mfirst + VP2::kDelay : Mfirst;
+      for (int M = Mfirst; M <= Mlast; ++M) {
+        T lo2[4], hi2[4];
+        if constexpr (LOSSY) v2.step(ll_odd, row, M == 0, M == 1, M == hh2, lo2, hi2);
+        else v2.step(ll_odd, row, M == 0, lo2, hi2);
+        const int p2 = M - VP2::kDelay;
+        if (p2 < m2_0 || p2 >= m2_1) continue;
+        if constexpr (LOSSY) {
+          const bool var = pair_variant(p2, a.nW2, a.ls2);
+          hfwd97<4>(lo2, kIK, var, left, right);  // the same lanes hold the level-2 borders
+          hfwd97<4>(hi2, kK, var, left, right);
+        } else {
+          hfwd53<4>(lo2, left, right);
+          hfwd53<4>(hi2, left, right);
+        }
+        if (!wlane) continue;
+        const int oc2 = c0 >> 2;
+        emit_pair<LOSSY, OT, T, 4>(lo2, hi2, out + (size_t)p2 * Wa + oc2, out + (size_t)(p2 + hh2) * Wa + oc2, hw2, a.q2, a.qs, a.last != 0,
+                                   a.last ? nullptr : llbase + (size_t)p2 * a.ll_pitch + oc2);
+      }
+    }
+  }
+}
+
+// quantiser steps, [level-1][LL,HL,LH,HH] (DWT/DWTGenerator.cuh:168-179)
+const float kQ[2][4] = {{1.965908f, 1.0112865f, 1.0112865f, 0.52021784f}, {4.1224113f, 1.9968134f, 1.9968134f, 0.96721643f}};
+
+void variant_params(int Hc, int* nW, int* ls) {
+  *nW = (Hc - 8 + 9) / 10;
+  *ls = (*nW - 1) * 10 - ((10 - ((Hc - 8) % 10)) % 10);
+}
+
+}  // namespace
+
+// Can the fused kernel take this geometry?  (Everything else goes through the per-level kernels of dwt.cu.)
+bool dwt_forward_fused_ok(const void* d_px, const void* d_coeff, const void* d_scratch, int W, int H, int Wa, int Ha, int wl) {
+  if (W != Wa) return false;                                                  // rows are padded: generic path
+  if ((reinterpret_cast<uintptr_t>(d_px) & 7) || (reinterpret_cast<uintptr_t>(d_coeff) & 15) || (reinterpret_cast<uintptr_t>(d_scratch) & 15)) return false;
+  if (((long long)W * H) % 8) return false;
+  if (wl >= 2 && (Ha % 16 || Wa % 32)) return false;
+  return Ha >= 32 && Wa >= 64;
+}
+
+// Levels 1..min(wl,2) of the forward transform in one launch.  Returns the number of levels done (1 or 2)
+// through *levels_done; the caller continues with the per-level kernels from LL_{levels_done}.
+int dwt_forward_fused(const uint8_t* d_px, void* d_coeff, void* d_ll, long long ll_fstride, int ll_pitch, int W, int H, int Wa,
+                      int Ha, int wl, bool lossy, float qs, bool out_int, int frames, int levels, cudaStream_t st) {
+  FastFwdArgs a{};
+  a.px = d_px; a.px_fstride = (long long)W * H; a.W = W; a.H = H;
+  a.out = d_coeff; a.out_fstride = (long long)Wa * Ha; a.Wa = Wa; a.Ha = Ha;
+  a.ll = d_ll; a.ll_fstride = ll_fstride; a.ll_pitch = ll_pitch;
+  a.last = (levels == wl);
+  for (int i = 0; i < 4; ++i) { a.q1[i] = kQ[0][i]; a.q2[i] = kQ[1][i]; }
+  a.qs = qs;
+  variant_params(Ha, &a.nW1, &a.ls1);
+  variant_params(Ha >> 1, &a.nW2, &a.ls2);
+  const int eff = (32 - 2 * levels) * 8;
+  a.nstrips = (Wa + eff - 1) / eff;
+  const int hh1 = Ha >> 1;
+  // chunk length: long enough to amortise the warm-up rows, short enough to fill 148 SMs a few times
+  int rp = 128;
+  while (rp > 32 && (long long)a.nstrips * ((hh1 + rp - 1) / rp) * frames < 148LL * 12) rp >>= 1;
+  a.rp = rp;
+  a.nchunks = (hh1 + rp - 1) / rp;
+  dim3 grid((a.nstrips * a.nchunks + 3) / 4, frames), block(128);
+  if (levels == 2) {
+    if (!lossy) dwt_forward_fused<false, int, 2><<<grid, block, 0, st>>>(a);
+    else if (out_int) dwt_forward_fused<true, int, 2><<<grid, block, 0, st>>>(a);
+    else dwt_forward_fused<true, float, 2><<<grid, block, 0, st>>>(a);
+  } else {
+    if (!lossy) dwt_forward_fused<false, int, 1><<<grid, block, 0, st>>>(a);
+    else if (out_int) dwt_forward_fused<true, int, 1><<<grid, block, 0, st>>>(a);
+    else dwt_forward_fused<true, float, 1><<<grid, block, 0, st>>>(a);
+  }
+  ++g_launches;
+  return (int)cudaGetLastError();
+}
+
+}  // namespace pcs
