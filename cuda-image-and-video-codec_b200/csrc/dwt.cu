@@ -525,16 +525,18 @@ static size_t ll_offset(int Wa, int Ha, int l) {
   return n;
 }
 
-bool dwt_forward_fused_ok(const void*, const void*, const void*, int, int, int, int, int);
-int dwt_forward_fused(const uint8_t*, void*, void*, long long, int, int, int, int, int, int, bool, float, bool, int, int, cudaStream_t);
+bool dwt_forward_fast_ok(const void*, const void*, const void*, bool, int, long long, int, int, int, int);
+int dwt_forward_fast(const void*, bool, long long, int, int, int, int, void*, long long, int, void*, long long, int, int, int, int, bool, float,
+                     bool, int, cudaStream_t);
 
-// PCS_DWT_FUSE = 0 | 1 | 2: how many leading levels the fused streaming kernel (dwt_fast.cu) may take (default 2)
+// PCS_DWT_FUSE = 0: per-level kernels of this file only; 1: streaming kernel of dwt_fast.cu, one level per launch
+// (default); 2: the same with levels 1+2 fused in one launch
 static int fuse_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("PCS_DWT_FUSE");
-    mode = e ? atoi(e) : 2;
-    if (mode < 0 || mode > 2) mode = 2;
+    mode = e ? atoi(e) : 1;
+    if (mode < 0 || mode > 2) mode = 1;
   }
   return mode;
 }
@@ -545,12 +547,24 @@ int dwt_forward(const uint8_t* d_px, void* d_coeff, void* d_scratch, int W, int 
                 bool lossy, float qs, bool out_int, int frames, cudaStream_t st) {
   const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl);
   int first = 1;
-  if (fuse_mode() > 0 && S % 4 == 0 && dwt_forward_fused_ok(d_px, d_coeff, d_scratch, W, H, Wa, Ha, wl)) {
-    const int lv = wl >= 2 ? fuse_mode() : 1;
-    int rc = dwt_forward_fused(d_px, d_coeff, static_cast<char*>(d_scratch) + ll_offset(Wa, Ha, lv) * 4, (long long)S, Wa >> lv, W, H, Wa, Ha,
-                               wl, lossy, qs, out_int, frames, lv, st);
+  // leading levels through the streaming kernel of dwt_fast.cu while the geometry allows it
+  while (fuse_mode() > 0 && first <= wl) {
+    const int l = first, Wc = Wa >> (l - 1), Hc = Ha >> (l - 1);
+    const bool u8 = l == 1;
+    const void* src = u8 ? static_cast<const void*>(d_px) : static_cast<const char*>(d_scratch) + ll_offset(Wa, Ha, l - 1) * 4;
+    const long long sfs = u8 ? (long long)W * H : (long long)S;
+    const int sp = u8 ? W : Wc;
+    int lv = (u8 && fuse_mode() == 2 && wl >= 2) ? 2 : 1;
+    void* ll = (l + lv - 1 == wl) ? nullptr : static_cast<char*>(d_scratch) + ll_offset(Wa, Ha, l + lv - 1) * 4;
+    if (!dwt_forward_fast_ok(src, d_coeff, ll, u8, sp, sfs, H, Wc, Hc, lv)) {
+      if (lv == 2) { lv = 1; ll = (l == wl) ? nullptr : static_cast<char*>(d_scratch) + ll_offset(Wa, Ha, l) * 4; }
+      if (!dwt_forward_fast_ok(src, d_coeff, ll, u8, sp, sfs, H, Wc, Hc, lv)) break;
+    }
+    if (S % 4) break;
+    int rc = dwt_forward_fast(src, u8, sfs, sp, H, Wc, Hc, d_coeff, (long long)A, Wa, ll, (long long)S, Wa >> (l + lv - 1), l, lv, wl, lossy,
+                              qs, out_int, frames, st);
     if (rc) return rc;
-    first = lv + 1;
+    first = l + lv;
   }
   for (int l = first; l <= wl; ++l) {
     FwdArgs a{};

@@ -15,6 +15,8 @@
 // written, + LL2 (A/16 samples) for the remaining levels.  Lanes 0,1,30,31 are halo (level 1 needs
 // one neighbour lane, level 2 one more); image borders are handled by explicit mirror rules in the
 // lifting steps, so halo lanes outside the image never influence a result.
+#include <type_traits>
+
 #include "pcs_common.cuh"
 
 namespace pcs {
@@ -26,13 +28,15 @@ constexpr float kA = -1.586134342059924f, kB = -0.052980118572961f, kG = 0.88291
 constexpr unsigned kFullMask = 0xffffffffu;
 
 struct FastFwdArgs {
-  const unsigned char* px; long long px_fstride; int W, H;  // W == Wa
-  void* out; long long out_fstride; int Wa, Ha;             // Mallat plane
-  void* ll; long long ll_fstride; int ll_pitch;             // LL destination of the LAST fused level (scratch), unless `last`
-  int last;                                                 // the last fused level is the last level: LL goes to `out`, quantised
-  float q1[4], q2[4], qs;                                   // quantiser steps of levels 1, 2: LL, HL, LH, HH
+  const void* src; long long src_fstride; int src_pitch;    // level input: u8 pixels (level 1) or the 32-bit LL plane of the level above
+  int H;                                                    // u8 input: original height (rows >= H are mirror padding); else == Hc
+  int Wc, Hc;                                               // level input size (multiples of 8 / 2)
+  void* out; long long out_fstride; int pitch;              // Mallat plane and its row pitch (the adapted frame width)
+  void* ll; long long ll_fstride; int ll_pitch;             // LL destination of the LAST level of this launch (scratch), unless `last`
+  int last;                                                 // that level is the last level: LL goes to `out`, quantised
+  float q1[4], q2[4], qs;                                   // quantiser steps of the first / second level of this launch: LL, HL, LH, HH
   int nW1, ls1, nW2, ls2;                                   // row-variant tiling of the reference, per level (9/7 only)
-  int nstrips, nchunks, rp;                                 // rp: level-1 row pairs per chunk (multiple of 4)
+  int nstrips, nchunks, rp;                                 // rp: row pairs per chunk (multiple of 4)
 };
 
 // Which row PAIR the reference computes with the fused neighbour sum (dwt.cu fwd97_row_variant restated
@@ -175,6 +179,14 @@ __device__ __forceinline__ void unpack8(uint2 p, int (&v)[8]) {
   }
 }
 
+template <typename T> struct Row8 { typename std::conditional<std::is_same<T, float>::value, float4, int4>::type a, b; };
+__device__ __forceinline__ void unpack8(const Row8<float>& r, float (&v)[8]) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+__device__ __forceinline__ void unpack8(const Row8<int>& r, int (&v)[8]) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+
 template <typename OT> struct V4;
 template <> struct V4<int> { using type = int4; };
 template <> struct V4<float> { using type = float4; };
@@ -223,12 +235,14 @@ __device__ __forceinline__ void emit_pair(const T (&lo)[NS], const T (&hi)[NS], 
   }
 }
 
-// LEVELS = 1: level 1 only (LL1 -> scratch or, if last, -> out); LEVELS = 2: levels 1 and 2 fused.
-template <bool LOSSY, typename OT, int LEVELS>
+// One launch = one level (LEVELS = 1; LL -> scratch or, if last, -> out) or two fused levels (LEVELS = 2,
+// u8 input only).  SRC_U8: the input is the u8 frame (level 1), else the 32-bit LL plane of the level above.
+template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS, bool QS1>
 __global__ void __launch_bounds__(128, 3) dwt_forward_fused(const FastFwdArgs a) {
   using T = typename VSel<LOSSY, 8>::T;
   using VP1 = typename VSel<LOSSY, 8>::type;
   using VP2 = typename VSel<LOSSY, 4>::type;
+  using RowT = typename std::conditional<SRC_U8, uint2, Row8<T>>::type;
   const int lane = threadIdx.x & 31;
   const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (item >= a.nstrips * a.nchunks) return;
@@ -236,49 +250,60 @@ __global__ void __launch_bounds__(128, 3) dwt_forward_fused(const FastFwdArgs a)
   const int strip = item % a.nstrips, chunk = item / a.nstrips;
   constexpr int kHalo = LEVELS;                        // halo lanes per side
   constexpr int kEff = (32 - 2 * kHalo) * 8;           // effective columns per strip
-  const int Wa = a.Wa, Ha = a.Ha, hw1 = Wa >> 1, hh1 = Ha >> 1, hw2 = Wa >> 2, hh2 = Ha >> 2;
+  const int Wc = a.Wc, Hc = a.Hc, hw1 = Wc >> 1, hh1 = Hc >> 1, hw2 = Wc >> 2, hh2 = Hc >> 2;
   const int c0 = strip * kEff - 8 * kHalo + 8 * lane;  // first of the lane's 8 columns
-  const bool inimg = c0 >= 0 && c0 < Wa;
+  const bool inimg = c0 >= 0 && c0 < Wc;
   const bool wlane = lane >= kHalo && lane < 32 - kHalo && inimg;
-  const bool left = c0 == 0, right = c0 + 8 == Wa;
+  const bool left = c0 == 0, right = c0 + 8 == Wc;
   // lanes outside the image read inside it; their values are never used (explicit border rules)
-  const unsigned char* const px = a.px + (size_t)frame * a.px_fstride + min(max(c0, 0), Wa - 8);
+  const int cl = min(max(c0, 0), Wc - 8);
+  const unsigned char* const src8 = static_cast<const unsigned char*>(a.src) + (size_t)frame * a.src_fstride + cl;
+  const T* const srcT = static_cast<const T*>(a.src) + (size_t)frame * a.src_fstride + cl;
   OT* const out = static_cast<OT*>(a.out) + (size_t)frame * a.out_fstride;
   T* const llbase = a.last ? nullptr : static_cast<T*>(a.ll) + (size_t)frame * a.ll_fstride;
+  const float qs = QS1 ? 1.0f : a.qs;  // x * 1.0f == x: the second quantiser multiply folds away
 
-  // level-1 row pairs [n0, n1) and level-2 row pairs [m2_0, m2_1) are written by this chunk
+  // first-level row pairs [n0, n1) and second-level row pairs [m2_0, m2_1) are written by this chunk
   const int n0 = chunk * a.rp, n1 = min(n0 + a.rp, hh1);
   const int m2_0 = n0 >> 1, m2_1 = n1 >> 1;
-  const int M0 = max(m2_0 - VP2::kWarm, 0);  // first level-2 step; it starts from LL1 row 2*M0
-  // first / last level-1 pair whose output is needed (by level 1 itself and by level 2)
+  const int M0 = max(m2_0 - VP2::kWarm, 0);  // first second-level step; it starts from LL row 2*M0
+  // first / last first-level pair whose output is needed (by that level itself and by the second one)
   const int P0 = LEVELS == 2 ? min(n0, 2 * M0) : n0;
   const int Plast = LEVELS == 2 ? min(max(n1 - 1, 2 * (m2_1 - 1 + VP2::kDelay) + 2), hh1 - 1) : n1 - 1;
 
-  auto load_row = [&](int y) -> uint2 {  // whole-sample fold at the adapted borders, then the pad mapping
-    int ys = y < 0 ? -y : (y >= Ha ? 2 * (Ha - 1) - y : y);
-    ys = ys < a.H ? ys : 2 * a.H - 1 - ys;
-    return __ldg(reinterpret_cast<const uint2*>(px + (size_t)ys * a.W));
+  auto load_row = [&](int y) -> RowT {  // whole-sample fold at the borders of the level input, then the pad mapping
+    int ys = y < 0 ? -y : (y >= Hc ? 2 * (Hc - 1) - y : y);
+    if constexpr (SRC_U8) {
+      ys = ys < a.H ? ys : 2 * a.H - 1 - ys;
+      return __ldg(reinterpret_cast<const uint2*>(src8 + (size_t)ys * a.src_pitch));
+    } else {
+      RowT r;
+      const auto* p4 = reinterpret_cast<const decltype(r.a)*>(srcT + (size_t)ys * a.src_pitch);
+      r.a = __ldg(p4); r.b = __ldg(p4 + 1);
+      return r;
+    }
   };
 
   VP1 v1;
   VP2 v2;
-  T ll_odd[4] = {};  // buffered odd LL1 row for level 2
-  const int ms = P0 - VP1::kWarm;          // first level-1 step: pair P0 is the first valid one
-  const int mend = Plast + VP1::kDelay;    // last level-1 step
+  T ll_odd[4] = {};  // buffered odd LL row for the second level
+  const int ms = P0 - VP1::kWarm;          // first step: pair P0 is the first valid one
+  const int mend = Plast + VP1::kDelay;    // last step
   {
     T r[8];
     unpack8(load_row(2 * ms), r);
     v1.init(r);
   }
-  uint2 pa = load_row(2 * ms + 1), pb = load_row(2 * ms + 2);  // rows of the current step
-  uint2 qa = load_row(2 * ms + 3), qb = load_row(2 * ms + 4);  // rows of the next step (prefetch)
+  RowT pa = load_row(2 * ms + 1), pb = load_row(2 * ms + 2);  // rows of the current step
+  RowT qa = load_row(2 * ms + 3), qb = load_row(2 * ms + 4);  // rows of the next step (prefetch)
 
+#pragma unroll 2
   for (int m = ms; m <= mend; ++m) {
     T xo[8], x2[8], lo[8], hi[8];
     unpack8(pa, xo); unpack8(pb, x2);
     pa = qa; pb = qb;
     if (m + 2 <= mend) { qa = load_row(2 * m + 5); qb = load_row(2 * m + 6); }
-    // level-1 borders come from the folded loads, so no explicit rule here
+    // borders of this level come from the folded loads, so no explicit rule here
     if constexpr (LOSSY) v1.step(xo, x2, false, false, false, lo, hi);
     else v1.step(xo, x2, false, lo, hi);
     const int pr = m - VP1::kDelay;  // row pair leaving the vertical pipeline
@@ -293,16 +318,16 @@ __global__ void __launch_bounds__(128, 3) dwt_forward_fused(const FastFwdArgs a)
     }
     if (wlane && pr >= n0 && pr < n1) {
       const int oc1 = c0 >> 1;
-      emit_pair<LOSSY, OT, T, 8>(lo, hi, out + (size_t)pr * Wa + oc1, out + (size_t)(pr + hh1) * Wa + oc1, hw1, a.q1, a.qs,
+      emit_pair<LOSSY, OT, T, 8>(lo, hi, out + (size_t)pr * a.pitch + oc1, out + (size_t)(pr + hh1) * a.pitch + oc1, hw1, a.q1, qs,
                                  LEVELS == 1 && a.last, (LEVELS == 1 && !a.last) ? llbase + (size_t)pr * a.ll_pitch + oc1 : nullptr);
     }
     if constexpr (LEVELS == 2) {
-      // ---- level 2 in the same warp: LL1 row R arrives, 4 samples per lane (LL1 columns c0/2 .. c0/2+3) ----
+      // ---- second level in the same warp: LL row R arrives, 4 samples per lane (LL columns c0/2 .. c0/2+3) ----
       const int R = pr;
       if (R < 2 * M0) continue;
       T row[4] = {lo[0], lo[2], lo[4], lo[6]};
       if (R == 2 * M0) { v2.init(row); continue; }
-      const bool lastrow = R == hh1 - 1;  // bottom of the image: LL1 row hh1 does not exist
+      const bool lastrow = R == hh1 - 1;  // bottom of the image: LL row hh1 does not exist
       if (R & 1) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) ll_odd[j] = row[j];
@@ -321,7 +346,7 @@ __global__ void __launch_bounds__(128, 3) dwt_forward_fused(const FastFwdArgs a)
         if (p2 < m2_0 || p2 >= m2_1) continue;
         if constexpr (LOSSY) {
           const bool var = pair_variant(p2, a.nW2, a.ls2);
-          hfwd97<4>(lo2, kIK, var, left, right);  // the same lanes hold the level-2 borders
+          hfwd97<4>(lo2, kIK, var, left, right);  // the same lanes hold the second level's borders
           hfwd97<4>(hi2, kK, var, left, right);
         } else {
           hfwd53<4>(lo2, left, right);
@@ -329,62 +354,85 @@ __global__ void __launch_bounds__(128, 3) dwt_forward_fused(const FastFwdArgs a)
         }
         if (!wlane) continue;
         const int oc2 = c0 >> 2;
-        emit_pair<LOSSY, OT, T, 4>(lo2, hi2, out + (size_t)p2 * Wa + oc2, out + (size_t)(p2 + hh2) * Wa + oc2, hw2, a.q2, a.qs, a.last != 0,
-                                   a.last ? nullptr : llbase + (size_t)p2 * a.ll_pitch + oc2);
+        emit_pair<LOSSY, OT, T, 4>(lo2, hi2, out + (size_t)p2 * a.pitch + oc2, out + (size_t)(p2 + hh2) * a.pitch + oc2, hw2, a.q2, qs,
+                                   a.last != 0, a.last ? nullptr : llbase + (size_t)p2 * a.ll_pitch + oc2);
       }
     }
   }
 }
 
 // quantiser steps, [level-1][LL,HL,LH,HH] (DWT/DWTGenerator.cuh:168-179)
-const float kQ[2][4] = {{1.965908f, 1.0112865f, 1.0112865f, 0.52021784f}, {4.1224113f, 1.9968134f, 1.9968134f, 0.96721643f}};
+const float kQ[10][4] = {
+    {1.965908f, 1.0112865f, 1.0112865f, 0.52021784f}, {4.1224113f, 1.9968134f, 1.9968134f, 0.96721643f},
+    {8.416739f, 4.1833673f, 4.1833673f, 2.0792568f},  {16.935543f, 8.534108f, 8.534108f, 4.3004827f},
+    {33.924816f, 17.166693f, 17.166693f, 8.686718f},  {67.87687f, 34.385098f, 34.385098f, 17.41882f},
+    {135.76744f, 68.7964f, 68.7964f, 34.860676f},     {271.5416f, 137.60588f, 137.60588f, 69.73287f},
+    {543.0866f, 275.21814f, 275.21814f, 139.47136f},  {1086.1624f, 550.43286f, 550.43286f, 278.94202f}};
 
 void variant_params(int Hc, int* nW, int* ls) {
   *nW = (Hc - 8 + 9) / 10;
   *ls = (*nW - 1) * 10 - ((10 - ((Hc - 8) % 10)) % 10);
 }
 
-}  // namespace
-
-// Can the fused kernel take this geometry?  (Everything else goes through the per-level kernels of dwt.cu.)
-bool dwt_forward_fused_ok(const void* d_px, const void* d_coeff, const void* d_scratch, int W, int H, int Wa, int Ha, int wl) {
-  if (W != Wa) return false;                                                  // rows are padded: generic path
-  if ((reinterpret_cast<uintptr_t>(d_px) & 7) || (reinterpret_cast<uintptr_t>(d_coeff) & 15) || (reinterpret_cast<uintptr_t>(d_scratch) & 15)) return false;
-  if (((long long)W * H) % 8) return false;
-  if (wl >= 2 && (Ha % 16 || Wa % 32)) return false;
-  return Ha >= 32 && Wa >= 64;
+template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS>
+void launch(const FastFwdArgs& a, dim3 grid, cudaStream_t st) {
+  if (a.qs == 1.0f) dwt_forward_fused<LOSSY, OT, SRC_U8, LEVELS, true><<<grid, 128, 0, st>>>(a);
+  else dwt_forward_fused<LOSSY, OT, SRC_U8, LEVELS, false><<<grid, 128, 0, st>>>(a);
 }
 
-// Levels 1..min(wl,2) of the forward transform in one launch.  Returns the number of levels done (1 or 2)
-// through *levels_done; the caller continues with the per-level kernels from LL_{levels_done}.
-int dwt_forward_fused(const uint8_t* d_px, void* d_coeff, void* d_ll, long long ll_fstride, int ll_pitch, int W, int H, int Wa,
-                      int Ha, int wl, bool lossy, float qs, bool out_int, int frames, int levels, cudaStream_t st) {
+}  // namespace
+
+// Can the streaming kernel take level `level` (1-based) of this geometry?  src = its input.
+bool dwt_forward_fast_ok(const void* src, const void* d_coeff, const void* ll, bool src_u8, int src_pitch, long long src_fstride, int H,
+                         int Wc, int Hc, int levels) {
+  if (Wc % 8 || Hc % 2 || Wc < 64 || Hc < 16) return false;
+  if (levels == 2 && (Wc % 32 || Hc % 16 || Hc < 64)) return false;
+  if (reinterpret_cast<uintptr_t>(d_coeff) & 15) return false;
+  if (ll && (reinterpret_cast<uintptr_t>(ll) & 15)) return false;
+  if (src_u8) {
+    if ((reinterpret_cast<uintptr_t>(src) & 7) || src_pitch % 8 || src_fstride % 8 || src_pitch != Wc || H > Hc) return false;
+  } else {
+    if ((reinterpret_cast<uintptr_t>(src) & 15) || src_pitch % 4 || src_fstride % 4) return false;
+  }
+  return true;
+}
+
+// `levels` (1 or 2) levels of the forward transform, starting at 1-based level `level`, in one launch.
+int dwt_forward_fast(const void* src, bool src_u8, long long src_fstride, int src_pitch, int H, int Wc, int Hc, void* d_coeff,
+                     long long out_fstride, int pitch, void* d_ll, long long ll_fstride, int ll_pitch, int level, int levels, int wl,
+                     bool lossy, float qs, bool out_int, int frames, cudaStream_t st) {
   FastFwdArgs a{};
-  a.px = d_px; a.px_fstride = (long long)W * H; a.W = W; a.H = H;
-  a.out = d_coeff; a.out_fstride = (long long)Wa * Ha; a.Wa = Wa; a.Ha = Ha;
+  a.src = src; a.src_fstride = src_fstride; a.src_pitch = src_pitch; a.H = src_u8 ? H : Hc; a.Wc = Wc; a.Hc = Hc;
+  a.out = d_coeff; a.out_fstride = out_fstride; a.pitch = pitch;
   a.ll = d_ll; a.ll_fstride = ll_fstride; a.ll_pitch = ll_pitch;
-  a.last = (levels == wl);
-  for (int i = 0; i < 4; ++i) { a.q1[i] = kQ[0][i]; a.q2[i] = kQ[1][i]; }
+  a.last = (level + levels - 1 == wl);
+  for (int i = 0; i < 4; ++i) { a.q1[i] = kQ[level - 1][i]; a.q2[i] = kQ[level < 10 ? level : 9][i]; }
   a.qs = qs;
-  variant_params(Ha, &a.nW1, &a.ls1);
-  variant_params(Ha >> 1, &a.nW2, &a.ls2);
+  variant_params(Hc, &a.nW1, &a.ls1);
+  variant_params(Hc >> 1, &a.nW2, &a.ls2);
   const int eff = (32 - 2 * levels) * 8;
-  a.nstrips = (Wa + eff - 1) / eff;
-  const int hh1 = Ha >> 1;
-  // chunk length: long enough to amortise the warm-up rows, short enough to fill 148 SMs a few times
+  a.nstrips = (Wc + eff - 1) / eff;
+  const int hh1 = Hc >> 1;
+  // chunk length: long enough to amortise the warm-up rows, short enough to fill 148 SMs with >= 12 warps each
   int rp = 128;
-  while (rp > 32 && (long long)a.nstrips * ((hh1 + rp - 1) / rp) * frames < 148LL * 12) rp >>= 1;
+  while (rp > 4 && (long long)a.nstrips * ((hh1 + rp - 1) / rp) * frames < 148LL * 12) rp >>= 1;
   a.rp = rp;
   a.nchunks = (hh1 + rp - 1) / rp;
-  dim3 grid((a.nstrips * a.nchunks + 3) / 4, frames), block(128);
-  if (levels == 2) {
-    if (!lossy) dwt_forward_fused<false, int, 2><<<grid, block, 0, st>>>(a);
-    else if (out_int) dwt_forward_fused<true, int, 2><<<grid, block, 0, st>>>(a);
-    else dwt_forward_fused<true, float, 2><<<grid, block, 0, st>>>(a);
+  dim3 grid((a.nstrips * a.nchunks + 3) / 4, frames);
+  if (src_u8) {
+    if (levels == 2) {
+      if (!lossy) launch<false, int, true, 2>(a, grid, st);
+      else if (out_int) launch<true, int, true, 2>(a, grid, st);
+      else launch<true, float, true, 2>(a, grid, st);
+    } else {
+      if (!lossy) launch<false, int, true, 1>(a, grid, st);
+      else if (out_int) launch<true, int, true, 1>(a, grid, st);
+      else launch<true, float, true, 1>(a, grid, st);
+    }
   } else {
-    if (!lossy) dwt_forward_fused<false, int, 1><<<grid, block, 0, st>>>(a);
-    else if (out_int) dwt_forward_fused<true, int, 1><<<grid, block, 0, st>>>(a);
-    else dwt_forward_fused<true, float, 1><<<grid, block, 0, st>>>(a);
+    if (!lossy) launch<false, int, false, 1>(a, grid, st);
+    else if (out_int) launch<true, int, false, 1>(a, grid, st);
+    else launch<true, float, false, 1>(a, grid, st);
   }
   ++g_launches;
   return (int)cudaGetLastError();
