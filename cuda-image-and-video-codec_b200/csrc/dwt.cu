@@ -529,6 +529,10 @@ bool dwt_forward_fast_ok(const void*, const void*, const void*, bool, int, long 
 int dwt_forward_fast(const void*, bool, long long, int, int, int, int, void*, long long, int, void*, long long, int, int, int, int, bool, float,
                      bool, int, cudaStream_t);
 
+bool dwt_inverse_fast_ok(const void*, const void*, const void*, bool, int, long long, int, long long, int, int);
+int dwt_inverse_fast(const int32_t*, long long, int, const void*, long long, int, bool, int, int, void*, bool, long long, int, int, int, bool,
+                     float, int, cudaStream_t);
+
 // PCS_DWT_FUSE = 0: per-level kernels of this file only; 1: streaming kernel of dwt_fast.cu, one level per launch
 // (default); 2: the same with levels 1+2 fused in one launch
 static int fuse_mode() {
@@ -627,6 +631,13 @@ int dwt_inverse(const int32_t* d_q, uint8_t* d_px, void* d_scratch, int W, int H
     a.r_ll = 1.0f / kQStep[l - 1][0]; a.r_hl = 1.0f / kQStep[l - 1][1];
     a.r_lh = 1.0f / kQStep[l - 1][2]; a.r_hh = 1.0f / kQStep[l - 1][3];
     a.rqs = 1.0f / qs;
+    if (fuse_mode() > 0 && S % 4 == 0 && !(l == 1 && flat_crop && W != Wa) &&
+        dwt_inverse_fast_ok(d_q, a.first ? nullptr : a.ll, a.dst, l == 1, a.dst_pitch, a.dst_fstride, a.ll_pitch, a.ll_fstride, a.Wc, a.Hc)) {
+      int rc = dwt_inverse_fast(d_q, (long long)A, Wa, a.first ? nullptr : a.ll, a.ll_fstride, a.ll_pitch, a.first != 0, a.Wc, a.Hc, a.dst, l == 1,
+                                a.dst_fstride, a.dst_pitch, H, l, lossy, qs, frames, st);
+      if (rc) return rc;
+      continue;
+    }
     a.nstrips = (a.Wc + kStrip - 1) / kStrip;
     a.rp = rows_per_warp(a.Hc >> 1, a.nstrips, frames);
     a.nchunks = ((a.Hc >> 1) + a.rp - 1) / a.rp;

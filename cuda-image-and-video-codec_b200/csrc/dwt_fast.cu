@@ -51,7 +51,11 @@ __device__ __forceinline__ bool pair_variant(int n, int nW, int ls) {
 template <typename OT> __device__ __forceinline__ OT cvt(float v);
 template <> __device__ __forceinline__ float cvt<float>(float v) { return v; }
 template <> __device__ __forceinline__ int cvt<int>(float v) { return __float2int_rz(v); }  // BPCEngine.cu:49
-template <typename OT> __device__ __forceinline__ OT quant(float v, float q, float qs) { return cvt<OT>(__fmul_rn(__fmul_rn(v, q), qs)); }
+// c * Q * qs, two rounded multiplies left to right (DWTGenerator.cu:403-419); QS1: qs == 1.0f, x * 1.0f == x exactly
+template <typename OT, bool QS1> __device__ __forceinline__ OT quant(float v, float q, float qs) {
+  const float t = __fmul_rn(v, q);
+  return cvt<OT>(QS1 ? t : __fmul_rn(t, qs));
+}
 
 // ---- horizontal analysis, N samples per lane (N = 8: level 1, N = 4: level 2) ----------------------
 // 5/3 (DWTGenerator.cu:72-76,279-292).  left: the lane holds image column 0 (d[-1] := d[0]);
@@ -75,15 +79,15 @@ __device__ __forceinline__ void hfwd53(int (&x)[N], bool left, bool right) {
 
 // 9/7 (DWTGenerator.cu:91-104,311-323) of a row whose vertical-pass scale S is still pending; see
 // dwt.cu hfwd97 for the operation shapes (they are the reference binary's, FMA contractions included).
-template <int N>
-__device__ __forceinline__ void hfwd97(float (&x)[N], float S, bool fused_sum, bool left, bool right) {
+template <int N, bool FUSED_SUM>
+__device__ __forceinline__ void hfwd97(float (&x)[N], float S, bool left, bool right) {
   constexpr int P = N / 2;
   float e[P], o[P];
 #pragma unroll
   for (int k = 0; k < P; ++k) e[k] = __fmul_rn(x[2 * k], S);
   float n0 = __shfl_down_sync(kFullMask, e[0], 1);
   if (right) n0 = e[P - 1];
-  if (fused_sum) {
+  if constexpr (FUSED_SUM) {
 #pragma unroll
     for (int k = 0; k < P; ++k) o[k] = __fmaf_rn(x[2 * k], S, k + 1 < P ? e[k + 1] : n0);
   } else {
@@ -206,7 +210,7 @@ __device__ __forceinline__ void st2(OT* p, OT a, OT b) {
 }
 
 // Stores the three (or four) subband rows of one row pair.  NS = samples per lane per row (8 or 4).
-template <bool LOSSY, typename OT, typename T, int NS>
+template <bool LOSSY, bool QS1, typename OT, typename T, int NS>
 __device__ __forceinline__ void emit_pair(const T (&lo)[NS], const T (&hi)[NS], OT* row_lo, OT* row_hi, int hw, const float (&q)[4], float qs,
                                           bool ll_to_out, T* ll_dst) {
   constexpr int P = NS / 2;
@@ -214,8 +218,8 @@ __device__ __forceinline__ void emit_pair(const T (&lo)[NS], const T (&hi)[NS], 
 #pragma unroll
   for (int k = 0; k < P; ++k) {
     if constexpr (LOSSY) {
-      v[0][k] = quant<OT>(lo[2 * k], q[0], qs); v[1][k] = quant<OT>(lo[2 * k + 1], q[1], qs);
-      v[2][k] = quant<OT>(hi[2 * k], q[2], qs); v[3][k] = quant<OT>(hi[2 * k + 1], q[3], qs);
+      v[0][k] = quant<OT, QS1>(lo[2 * k], q[0], qs); v[1][k] = quant<OT, QS1>(lo[2 * k + 1], q[1], qs);
+      v[2][k] = quant<OT, QS1>(hi[2 * k], q[2], qs); v[3][k] = quant<OT, QS1>(hi[2 * k + 1], q[3], qs);
     } else {
       v[0][k] = lo[2 * k]; v[1][k] = lo[2 * k + 1]; v[2][k] = hi[2 * k]; v[3][k] = hi[2 * k + 1];
     }
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(128, 3) dwt_forward_fused(const FastFwdArgs a)
   const T* const srcT = static_cast<const T*>(a.src) + (size_t)frame * a.src_fstride + cl;
   OT* const out = static_cast<OT*>(a.out) + (size_t)frame * a.out_fstride;
   T* const llbase = a.last ? nullptr : static_cast<T*>(a.ll) + (size_t)frame * a.ll_fstride;
-  const float qs = QS1 ? 1.0f : a.qs;  // x * 1.0f == x: the second quantiser multiply folds away
+  const float qs = a.qs;
 
   // first-level row pairs [n0, n1) and second-level row pairs [m2_0, m2_1) are written by this chunk
   const int n0 = chunk * a.rp, n1 = min(n0 + a.rp, hh1);
@@ -294,31 +298,33 @@ __global__ void __launch_bounds__(128, 3) dwt_forward_fused(const FastFwdArgs a)
     unpack8(load_row(2 * ms), r);
     v1.init(r);
   }
-  RowT pa = load_row(2 * ms + 1), pb = load_row(2 * ms + 2);  // rows of the current step
-  RowT qa = load_row(2 * ms + 3), qb = load_row(2 * ms + 4);  // rows of the next step (prefetch)
+  // rows of the current step, prefetched one step ahead; the narrow u8 rows a second step ahead as well
+  // (rows past the chunk's last step fold to valid rows and are simply not used)
+  RowT pa = load_row(2 * ms + 1), pb = load_row(2 * ms + 2);
+  RowT qa, qb;
+  if constexpr (SRC_U8) { qa = load_row(2 * ms + 3); qb = load_row(2 * ms + 4); }
 
 #pragma unroll 2
   for (int m = ms; m <= mend; ++m) {
     T xo[8], x2[8], lo[8], hi[8];
     unpack8(pa, xo); unpack8(pb, x2);
-    pa = qa; pb = qb;
-    if (m + 2 <= mend) { qa = load_row(2 * m + 5); qb = load_row(2 * m + 6); }
+    if constexpr (SRC_U8) { pa = qa; pb = qb; qa = load_row(2 * m + 5); qb = load_row(2 * m + 6); }
+    else { pa = load_row(2 * m + 3); pb = load_row(2 * m + 4); }
     // borders of this level come from the folded loads, so no explicit rule here
     if constexpr (LOSSY) v1.step(xo, x2, false, false, false, lo, hi);
     else v1.step(xo, x2, false, lo, hi);
     const int pr = m - VP1::kDelay;  // row pair leaving the vertical pipeline
     if (pr < P0) continue;           // warm-up (warp-uniform)
     if constexpr (LOSSY) {
-      const bool var = pair_variant(pr, a.nW1, a.ls1);
-      hfwd97<8>(lo, kIK, var, left, right);
-      hfwd97<8>(hi, kK, var, left, right);
+      if (pair_variant(pr, a.nW1, a.ls1)) { hfwd97<8, true>(lo, kIK, left, right); hfwd97<8, true>(hi, kK, left, right); }
+      else { hfwd97<8, false>(lo, kIK, left, right); hfwd97<8, false>(hi, kK, left, right); }
     } else {
       hfwd53<8>(lo, left, right);
       hfwd53<8>(hi, left, right);
     }
     if (wlane && pr >= n0 && pr < n1) {
       const int oc1 = c0 >> 1;
-      emit_pair<LOSSY, OT, T, 8>(lo, hi, out + (size_t)pr * a.pitch + oc1, out + (size_t)(pr + hh1) * a.pitch + oc1, hw1, a.q1, qs,
+      emit_pair<LOSSY, QS1, OT, T, 8>(lo, hi, out + (size_t)pr * a.pitch + oc1, out + (size_t)(pr + hh1) * a.pitch + oc1, hw1, a.q1, qs,
                                  LEVELS == 1 && a.last, (LEVELS == 1 && !a.last) ? llbase + (size_t)pr * a.ll_pitch + oc1 : nullptr);
     }
     if constexpr (LEVELS == 2) {
@@ -345,16 +351,16 @@ __global__ void __launch_bounds__(128, 3) dwt_forward_fused(const FastFwdArgs a)
         const int p2 = M - VP2::kDelay;
         if (p2 < m2_0 || p2 >= m2_1) continue;
         if constexpr (LOSSY) {
-          const bool var = pair_variant(p2, a.nW2, a.ls2);
-          hfwd97<4>(lo2, kIK, var, left, right);  // the same lanes hold the second level's borders
-          hfwd97<4>(hi2, kK, var, left, right);
+          // the same lanes hold the second level's borders
+          if (pair_variant(p2, a.nW2, a.ls2)) { hfwd97<4, true>(lo2, kIK, left, right); hfwd97<4, true>(hi2, kK, left, right); }
+          else { hfwd97<4, false>(lo2, kIK, left, right); hfwd97<4, false>(hi2, kK, left, right); }
         } else {
           hfwd53<4>(lo2, left, right);
           hfwd53<4>(hi2, left, right);
         }
         if (!wlane) continue;
         const int oc2 = c0 >> 2;
-        emit_pair<LOSSY, OT, T, 4>(lo2, hi2, out + (size_t)p2 * a.pitch + oc2, out + (size_t)(p2 + hh2) * a.pitch + oc2, hw2, a.q2, qs,
+        emit_pair<LOSSY, QS1, OT, T, 4>(lo2, hi2, out + (size_t)p2 * a.pitch + oc2, out + (size_t)(p2 + hh2) * a.pitch + oc2, hw2, a.q2, qs,
                                    a.last != 0, a.last ? nullptr : llbase + (size_t)p2 * a.ll_pitch + oc2);
       }
     }
@@ -378,6 +384,237 @@ template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS>
 void launch(const FastFwdArgs& a, dim3 grid, cudaStream_t st) {
   if (a.qs == 1.0f) dwt_forward_fused<LOSSY, OT, SRC_U8, LEVELS, true><<<grid, 128, 0, st>>>(a);
   else dwt_forward_fused<LOSSY, OT, SRC_U8, LEVELS, false><<<grid, 128, 0, st>>>(a);
+}
+
+
+// =================================================================================================
+// inverse
+// =================================================================================================
+struct FastInvArgs {
+  const int32_t* q; long long q_fstride; int pitch;        // quantised Mallat plane, row pitch = adapted frame width
+  const void* ll; long long ll_fstride; int ll_pitch;      // LL source (scratch, type T) unless `first`
+  int first;                                               // coarsest level: LL comes from q (de-quantised)
+  int Wc, Hc;                                              // size of this level's OUTPUT
+  void* dst; long long dst_fstride; int dst_pitch;         // scratch plane (T) or the u8 frame
+  int H;                                                   // u8 output: rows >= H are padding and are not stored
+  float r[4], rqs;                                         // reciprocal quantiser steps LL, HL, LH, HH and 1/qs
+  int nstrips, nchunks, rp;
+};
+
+// 5/3 horizontal synthesis (DWTGenerator.cu:79-85,295-308): x = s0,d0,s1,d1,... -> e0,o0,e1,o1,...
+template <int N>
+__device__ __forceinline__ void hinv53(int (&x)[N], bool left, bool right) {
+  constexpr int P = N / 2;
+  int pd = __shfl_up_sync(kFullMask, x[N - 1], 1);
+  if (left) pd = x[1];
+  int e[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) e[k] = x[2 * k] - (((k ? x[2 * k - 1] : pd) + x[2 * k + 1] + 2) >> 2);
+  int ne = __shfl_down_sync(kFullMask, e[0], 1);
+  if (right) ne = e[P - 1];
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    x[2 * k + 1] = x[2 * k + 1] + ((e[k] + (k + 1 < P ? e[k + 1] : ne)) >> 1);
+    x[2 * k] = e[k];
+  }
+}
+
+// 9/7 horizontal synthesis (DWTGenerator.cu:110-122,326-339); divisions by K and 1/K as multiplications by
+// the rounded reciprocals, as in dwt.cu and the oracle.
+template <int N>
+__device__ __forceinline__ void hinv97(float (&x)[N], float rK, float rIK, bool left, bool right) {
+  constexpr int P = N / 2;
+  float e[P], o[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) o[k] = __fmul_rn(x[2 * k + 1], rK);
+  float p1 = __shfl_up_sync(kFullMask, o[P - 1], 1);
+  if (left) p1 = o[0];
+#pragma unroll
+  for (int k = 0; k < P; ++k) e[k] = __fmaf_rn(-__fadd_rn(k ? o[k - 1] : p1, o[k]), kD, __fmul_rn(x[2 * k], rIK));
+  float n0 = __shfl_down_sync(kFullMask, e[0], 1);
+  if (right) n0 = e[P - 1];
+#pragma unroll
+  for (int k = 0; k < P; ++k) o[k] = __fmaf_rn(-__fadd_rn(e[k], k + 1 < P ? e[k + 1] : n0), kG, o[k]);
+  p1 = __shfl_up_sync(kFullMask, o[P - 1], 1);
+  if (left) p1 = o[0];
+#pragma unroll
+  for (int k = P - 1; k >= 0; --k) e[k] = __fmaf_rn(-__fadd_rn(k ? o[k - 1] : p1, o[k]), kB, e[k]);
+  n0 = __shfl_down_sync(kFullMask, e[0], 1);
+  if (right) n0 = e[P - 1];
+#pragma unroll
+  for (int k = 0; k < P; ++k) o[k] = __fmaf_rn(-__fadd_rn(e[k], k + 1 < P ? e[k + 1] : n0), kA, o[k]);
+#pragma unroll
+  for (int k = 0; k < P; ++k) { x[2 * k] = e[k]; x[2 * k + 1] = o[k]; }
+}
+
+// vertical synthesis pipelines.  step(m) takes row pair m (after the horizontal pass) and releases an even
+// row kEven(m) and an odd row kOdd(m).
+template <int N>
+struct IV53 {  // x[2n] = s[n] - ((d[n-1]+d[n]+2)>>2);  x[2n-1] = d[n-1] + ((x[2n-2]+x[2n])>>1)  (DWTGenerator.cu:79-85,160-181)
+  int dp[N], xp[N];
+  static constexpr int kLead = 1, kTail = 0;  // steps before the first / after the last pair of the chunk
+  __device__ __forceinline__ static int even_row(int m) { return 2 * m; }
+  __device__ __forceinline__ static int odd_row(int m) { return 2 * m - 1; }
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int j = 0; j < N; ++j) { dp[j] = 0; xp[j] = 0; }
+  }
+  __device__ __forceinline__ void step(const int (&s)[N], const int (&d)[N], int (&re)[N], int (&ro)[N]) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const int xe = s[j] - ((dp[j] + d[j] + 2) >> 2);
+      ro[j] = dp[j] + ((xp[j] + xe) >> 1);
+      re[j] = xe; xp[j] = xe; dp[j] = d[j];
+    }
+  }
+};
+template <int N>
+struct IV97 {  // DWTGenerator.cu:110-122,230-272
+  float opp[N], e1p[N], o1pp[N], e0pp[N];
+  static constexpr int kLead = 2, kTail = 1;
+  __device__ __forceinline__ static int even_row(int m) { return 2 * (m - 1); }
+  __device__ __forceinline__ static int odd_row(int m) { return 2 * m - 3; }
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int j = 0; j < N; ++j) { opp[j] = 0.f; e1p[j] = 0.f; o1pp[j] = 0.f; e0pp[j] = 0.f; }
+  }
+  __device__ __forceinline__ void step(const float (&lo)[N], const float (&hi)[N], float (&re)[N], float (&ro)[N]) {
+    const float rK = 1.0f / kK, rIK = 1.0f / kIK;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const float op = __fmul_rn(hi[j], rK);
+      const float e1 = __fmaf_rn(-__fadd_rn(opp[j], op), kD, __fmul_rn(lo[j], rIK));
+      const float o1p = __fmaf_rn(-__fadd_rn(e1p[j], e1), kG, opp[j]);    // o1[m-1]
+      const float e0p = __fmaf_rn(-__fadd_rn(o1pp[j], o1p), kB, e1p[j]);  // x[2(m-1)]
+      ro[j] = __fmaf_rn(-__fadd_rn(e0pp[j], e0p), kA, o1pp[j]);           // x[2(m-2)+1]
+      re[j] = e0p;
+      opp[j] = op; e1p[j] = e1; o1pp[j] = o1p; e0pp[j] = e0p;
+    }
+  }
+};
+template <bool LOSSY, int N> struct IVSel { using type = IV53<N>; };
+template <int N> struct IVSel<true, N> { using type = IV97<N>; };
+
+// De-quantiser on subband read (DWTGenerator.cu:513-553): 0 -> 0, else (|q|+0.5)*sgn / Q / qs, the two
+// divisions as multiplications by rounded reciprocals.  |q| -> float through the 2^23 mantissa trick
+// (exact for |q| < 2^23, which the decoder guarantees) instead of an I2F on the quarter-rate pipe.
+template <bool QS1>
+__device__ __forceinline__ float dequant(int q, float rq, float rqs) {
+  const unsigned aq = (unsigned)abs(q);
+  const float mag = __fadd_rn(__fadd_rn(__uint_as_float(0x4B000000u | aq), -8388608.0f), 0.5f);
+  float t = __fmul_rn(mag, rq);
+  if (!QS1) t = __fmul_rn(t, rqs);
+  t = __uint_as_float(__float_as_uint(t) | ((unsigned)q & 0x80000000u));
+  return q == 0 ? 0.0f : t;
+}
+
+__device__ __forceinline__ unsigned sat_u8(float v) {  // clamp(rn(v), 0, 255)
+  unsigned r;
+  asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+
+template <bool LOSSY, bool DST_U8, bool FIRST, bool QS1>
+__global__ void __launch_bounds__(128, 3) dwt_inverse_fast_kernel(const FastInvArgs a) {
+  using T = typename VSel<LOSSY, 8>::T;
+  using VP = typename IVSel<LOSSY, 8>::type;
+  using T4 = typename std::conditional<LOSSY, float4, int4>::type;
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= a.nstrips * a.nchunks) return;
+  const int frame = blockIdx.y;
+  const int strip = item % a.nstrips, chunk = item / a.nstrips;
+  const int Wc = a.Wc, Hc = a.Hc, hw = Wc >> 1, hh = Hc >> 1;
+  const int c0 = strip * 240 - 8 + 8 * lane;
+  const bool inimg = c0 >= 0 && c0 < Wc;
+  const bool wlane = lane >= 1 && lane <= 30 && inimg;
+  const bool left = c0 == 0, right = c0 + 8 == Wc;
+  const int oc = min(max(c0, 0), Wc - 8) >> 1;  // subband column of the lane's 4 low / 4 high samples
+  const int32_t* const q = a.q + (size_t)frame * a.q_fstride + oc;
+  const T* const lls = FIRST ? nullptr : static_cast<const T*>(a.ll) + (size_t)frame * a.ll_fstride + oc;
+
+  struct Raw { int4 hl, lh, hh; T4 ll; };
+  // row pair n: low row n of (LL|HL), high row n of (LH|HH); whole-sample fold of the row index
+  auto load_pair = [&](int n) -> Raw {
+    int rl, rh;
+    if (n < 0) { rl = -n; rh = -n - 1; }
+    else if (n >= hh) { rl = Hc - 1 - n; rh = Hc - 2 - n; }
+    else { rl = n; rh = n; }
+    const int32_t* row_lo = q + (size_t)rl * a.pitch;
+    const int32_t* row_hi = q + (size_t)(rh + hh) * a.pitch;
+    Raw r;
+    r.hl = __ldg(reinterpret_cast<const int4*>(row_lo + hw));
+    r.lh = __ldg(reinterpret_cast<const int4*>(row_hi));
+    r.hh = __ldg(reinterpret_cast<const int4*>(row_hi + hw));
+    if constexpr (FIRST) {
+      const int4 t = __ldg(reinterpret_cast<const int4*>(row_lo));
+      if constexpr (LOSSY) r.ll = make_float4(dequant<QS1>(t.x, a.r[0], a.rqs), dequant<QS1>(t.y, a.r[0], a.rqs), dequant<QS1>(t.z, a.r[0], a.rqs), dequant<QS1>(t.w, a.r[0], a.rqs));
+      else r.ll = t;
+    } else {
+      r.ll = __ldg(reinterpret_cast<const T4*>(lls + (size_t)rl * a.ll_pitch));
+    }
+    return r;
+  };
+  auto expand = [&](const Raw& r, T (&lo)[8], T (&hi)[8]) {
+    lo[0] = r.ll.x; lo[2] = r.ll.y; lo[4] = r.ll.z; lo[6] = r.ll.w;
+    if constexpr (LOSSY) {
+      lo[1] = dequant<QS1>(r.hl.x, a.r[1], a.rqs); lo[3] = dequant<QS1>(r.hl.y, a.r[1], a.rqs);
+      lo[5] = dequant<QS1>(r.hl.z, a.r[1], a.rqs); lo[7] = dequant<QS1>(r.hl.w, a.r[1], a.rqs);
+      hi[0] = dequant<QS1>(r.lh.x, a.r[2], a.rqs); hi[2] = dequant<QS1>(r.lh.y, a.r[2], a.rqs);
+      hi[4] = dequant<QS1>(r.lh.z, a.r[2], a.rqs); hi[6] = dequant<QS1>(r.lh.w, a.r[2], a.rqs);
+      hi[1] = dequant<QS1>(r.hh.x, a.r[3], a.rqs); hi[3] = dequant<QS1>(r.hh.y, a.r[3], a.rqs);
+      hi[5] = dequant<QS1>(r.hh.z, a.r[3], a.rqs); hi[7] = dequant<QS1>(r.hh.w, a.r[3], a.rqs);
+    } else {
+      lo[1] = r.hl.x; lo[3] = r.hl.y; lo[5] = r.hl.z; lo[7] = r.hl.w;
+      hi[0] = r.lh.x; hi[2] = r.lh.y; hi[4] = r.lh.z; hi[6] = r.lh.w;
+      hi[1] = r.hh.x; hi[3] = r.hh.y; hi[5] = r.hh.z; hi[7] = r.hh.w;
+    }
+  };
+  auto store_row = [&](int y, const T (&v)[8]) {
+    if constexpr (DST_U8) {
+      if (y >= a.H) return;
+      unsigned b[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if constexpr (LOSSY) b[j] = sat_u8(__fadd_rn(__fadd_rn(v[j], 128.0f), 0.01f));  // DecodingEngine.cu:714
+        else b[j] = (unsigned)min(max(v[j] + 128, 0), 255);                                // :728
+      }
+      uint2 w;
+      w.x = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+      w.y = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+      *reinterpret_cast<uint2*>(static_cast<unsigned char*>(a.dst) + (size_t)frame * a.dst_fstride + (size_t)y * a.dst_pitch + c0) = w;
+    } else {
+      T* d = static_cast<T*>(a.dst) + (size_t)frame * a.dst_fstride + (size_t)y * a.dst_pitch + c0;
+      T4 t0, t1;
+      t0.x = v[0]; t0.y = v[1]; t0.z = v[2]; t0.w = v[3]; t1.x = v[4]; t1.y = v[5]; t1.z = v[6]; t1.w = v[7];
+      reinterpret_cast<T4*>(d)[0] = t0; reinterpret_cast<T4*>(d)[1] = t1;
+    }
+  };
+
+  const int n0 = chunk * a.rp, n1 = min(n0 + a.rp, hh);
+  VP vp; vp.init();
+  const int ms = n0 - VP::kLead, mend = n1 + VP::kTail;
+  Raw cur = load_pair(ms);
+#pragma unroll 2
+  for (int m = ms; m <= mend; ++m) {
+    T lo[8], hi[8], re[8], ro[8];
+    expand(cur, lo, hi);
+    cur = load_pair(m + 1);  // prefetch (pairs past the chunk fold to valid rows and are not used)
+    if constexpr (LOSSY) { hinv97<8>(lo, 1.0f / kK, 1.0f / kIK, left, right); hinv97<8>(hi, 1.0f / kK, 1.0f / kIK, left, right); }
+    else { hinv53<8>(lo, left, right); hinv53<8>(hi, left, right); }
+    vp.step(lo, hi, re, ro);
+    const int yo = VP::odd_row(m), ye = VP::even_row(m);
+    if (wlane) {
+      if (yo >= 2 * n0 && yo < 2 * n1) store_row(yo, ro);
+      if (ye >= 2 * n0 && ye < 2 * n1) store_row(ye, re);
+    }
+  }
+}
+
+template <bool LOSSY, bool DST_U8, bool FIRST>
+void launch_inv(const FastInvArgs& a, dim3 grid, bool qs1, cudaStream_t st) {
+  if (qs1) dwt_inverse_fast_kernel<LOSSY, DST_U8, FIRST, true><<<grid, 128, 0, st>>>(a);
+  else dwt_inverse_fast_kernel<LOSSY, DST_U8, FIRST, false><<<grid, 128, 0, st>>>(a);
 }
 
 }  // namespace
@@ -433,6 +670,44 @@ int dwt_forward_fast(const void* src, bool src_u8, long long src_fstride, int sr
     if (!lossy) launch<false, int, false, 1>(a, grid, st);
     else if (out_int) launch<true, int, false, 1>(a, grid, st);
     else launch<true, float, false, 1>(a, grid, st);
+  }
+  ++g_launches;
+  return (int)cudaGetLastError();
+}
+
+// Can the streaming inverse kernel produce the Wc x Hc output of one level?
+bool dwt_inverse_fast_ok(const void* q, const void* ll, const void* dst, bool dst_u8, int dst_pitch, long long dst_fstride, int ll_pitch,
+                         long long ll_fstride, int Wc, int Hc) {
+  if (Wc % 8 || Hc % 2 || Wc < 64 || Hc < 16) return false;
+  if (reinterpret_cast<uintptr_t>(q) & 15) return false;
+  if (ll && ((reinterpret_cast<uintptr_t>(ll) & 15) || ll_pitch % 4 || ll_fstride % 4)) return false;
+  if (dst_u8) return !(reinterpret_cast<uintptr_t>(dst) & 7) && dst_pitch == Wc && dst_fstride % 8 == 0;
+  return !(reinterpret_cast<uintptr_t>(dst) & 15) && dst_pitch % 4 == 0 && dst_fstride % 4 == 0;
+}
+
+int dwt_inverse_fast(const int32_t* d_q, long long q_fstride, int pitch, const void* ll, long long ll_fstride, int ll_pitch, bool first,
+                     int Wc, int Hc, void* dst, bool dst_u8, long long dst_fstride, int dst_pitch, int H, int level, bool lossy, float qs,
+                     int frames, cudaStream_t st) {
+  FastInvArgs a{};
+  a.q = d_q; a.q_fstride = q_fstride; a.pitch = pitch;
+  a.ll = ll; a.ll_fstride = ll_fstride; a.ll_pitch = ll_pitch; a.first = first;
+  a.Wc = Wc; a.Hc = Hc; a.dst = dst; a.dst_fstride = dst_fstride; a.dst_pitch = dst_pitch; a.H = dst_u8 ? H : Hc;
+  for (int i = 0; i < 4; ++i) a.r[i] = 1.0f / kQ[level - 1][i];
+  a.rqs = 1.0f / qs;
+  a.nstrips = (Wc + 239) / 240;
+  const int hh = Hc >> 1;
+  int rp = 128;
+  while (rp > 4 && (long long)a.nstrips * ((hh + rp - 1) / rp) * frames < 148LL * 12) rp >>= 1;
+  a.rp = rp;
+  a.nchunks = (hh + rp - 1) / rp;
+  dim3 grid((a.nstrips * a.nchunks + 3) / 4, frames);
+  const bool qs1 = a.rqs == 1.0f;
+  if (!lossy) {
+    if (dst_u8) { if (first) launch_inv<false, true, true>(a, grid, qs1, st); else launch_inv<false, true, false>(a, grid, qs1, st); }
+    else { if (first) launch_inv<false, false, true>(a, grid, qs1, st); else launch_inv<false, false, false>(a, grid, qs1, st); }
+  } else {
+    if (dst_u8) { if (first) launch_inv<true, true, true>(a, grid, qs1, st); else launch_inv<true, true, false>(a, grid, qs1, st); }
+    else { if (first) launch_inv<true, false, true>(a, grid, qs1, st); else launch_inv<true, false, false>(a, grid, qs1, st); }
   }
   ++g_launches;
   return (int)cudaGetLastError();
