@@ -183,6 +183,17 @@ __device__ __forceinline__ void unpack8(uint2 p, int (&v)[8]) {
   }
 }
 
+// ---- cp.async staging: every lane copies its own bytes of future rows into a per-warp shared-memory ring and
+// reads them back itself, so no barrier is needed; depth D steps hides the DRAM latency at low occupancy ----
+__device__ __forceinline__ void cp_async8(void* smem, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <typename T> struct Row8 { typename std::conditional<std::is_same<T, float>::value, float4, int4>::type a, b; };
 __device__ __forceinline__ void unpack8(const Row8<float>& r, float (&v)[8]) {
   v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
@@ -275,14 +286,29 @@ __global__ void __launch_bounds__(128, 3) dwt_forward_fused(const FastFwdArgs a)
   const int P0 = LEVELS == 2 ? min(n0, 2 * M0) : n0;
   const int Plast = LEVELS == 2 ? min(max(n1 - 1, 2 * (m2_1 - 1 + VP2::kDelay) + 2), hh1 - 1) : n1 - 1;
 
-  auto load_row = [&](int y) -> RowT {  // whole-sample fold at the borders of the level input, then the pad mapping
+  // Row staging.  u8 input (level 1, the bandwidth-critical launch): every lane cp.async-copies its own 8
+  // bytes of the rows of the next kDepth steps into a per-warp shared-memory ring and reads them back
+  // itself (no barrier needed); the deep prefetch hides the DRAM latency at 16 warps per SM.  32-bit
+  // input (deeper levels, small): plain register prefetch one step ahead.
+  constexpr int kDepth = 6;
+  __shared__ __align__(16) unsigned char s_ring[SRC_U8 ? 4 : 1][SRC_U8 ? kDepth : 1][2][32][8];
+  auto& ring = s_ring[SRC_U8 ? (threadIdx.x >> 5) : 0];
+  auto row_index = [&](int y) -> int {  // whole-sample fold at the borders of the level input, then the pad mapping
     int ys = y < 0 ? -y : (y >= Hc ? 2 * (Hc - 1) - y : y);
+    if constexpr (SRC_U8) ys = ys < a.H ? ys : 2 * a.H - 1 - ys;
+    return ys;
+  };
+  auto issue_step = [&](int m, int slot) {  // rows 2m+1, 2m+2 (rows past the chunk fold to valid rows and are not used)
+    cp_async8(&ring[slot][0][lane][0], src8 + (size_t)row_index(2 * m + 1) * a.src_pitch);
+    cp_async8(&ring[slot][1][lane][0], src8 + (size_t)row_index(2 * m + 2) * a.src_pitch);
+    cp_async_commit();
+  };
+  auto load_row = [&](int y) -> RowT {
     if constexpr (SRC_U8) {
-      ys = ys < a.H ? ys : 2 * a.H - 1 - ys;
-      return __ldg(reinterpret_cast<const uint2*>(src8 + (size_t)ys * a.src_pitch));
+      return __ldg(reinterpret_cast<const uint2*>(src8 + (size_t)row_index(y) * a.src_pitch));
     } else {
       RowT r;
-      const auto* p4 = reinterpret_cast<const decltype(r.a)*>(srcT + (size_t)ys * a.src_pitch);
+      const auto* p4 = reinterpret_cast<const decltype(r.a)*>(srcT + (size_t)row_index(y) * a.src_pitch);
       r.a = __ldg(p4); r.b = __ldg(p4 + 1);
       return r;
     }
@@ -293,23 +319,33 @@ __global__ void __launch_bounds__(128, 3) dwt_forward_fused(const FastFwdArgs a)
   T ll_odd[4] = {};  // buffered odd LL row for the second level
   const int ms = P0 - VP1::kWarm;          // first step: pair P0 is the first valid one
   const int mend = Plast + VP1::kDelay;    // last step
+  RowT pa, pb;
+  if constexpr (SRC_U8) {
+#pragma unroll
+    for (int d = 0; d < kDepth; ++d) issue_step(ms + d, d);
+  } else {
+    pa = load_row(2 * ms + 1); pb = load_row(2 * ms + 2);
+  }
   {
     T r[8];
     unpack8(load_row(2 * ms), r);
     v1.init(r);
   }
-  // rows of the current step, prefetched one step ahead; the narrow u8 rows a second step ahead as well
-  // (rows past the chunk's last step fold to valid rows and are simply not used)
-  RowT pa = load_row(2 * ms + 1), pb = load_row(2 * ms + 2);
-  RowT qa, qb;
-  if constexpr (SRC_U8) { qa = load_row(2 * ms + 3); qb = load_row(2 * ms + 4); }
+  int slot = 0;
 
 #pragma unroll 2
   for (int m = ms; m <= mend; ++m) {
     T xo[8], x2[8], lo[8], hi[8];
-    unpack8(pa, xo); unpack8(pb, x2);
-    if constexpr (SRC_U8) { pa = qa; pb = qb; qa = load_row(2 * m + 5); qb = load_row(2 * m + 6); }
-    else { pa = load_row(2 * m + 3); pb = load_row(2 * m + 4); }
+    if constexpr (SRC_U8) {
+      cp_async_wait<kDepth - 1>();  // the group of step m has landed
+      unpack8(*reinterpret_cast<const uint2*>(&ring[slot][0][lane][0]), xo);
+      unpack8(*reinterpret_cast<const uint2*>(&ring[slot][1][lane][0]), x2);
+      issue_step(m + kDepth, slot);
+      slot = slot + 1 == kDepth ? 0 : slot + 1;
+    } else {
+      unpack8(pa, xo); unpack8(pb, x2);
+      pa = load_row(2 * m + 3); pb = load_row(2 * m + 4);
+    }
     // borders of this level come from the folded loads, so no explicit rule here
     if constexpr (LOSSY) v1.step(xo, x2, false, false, false, lo, hi);
     else v1.step(xo, x2, false, lo, hi);
