@@ -571,24 +571,52 @@ __global__ void __launch_bounds__(128, 3) dwt_inverse_fast_kernel(const FastInvA
 
   struct Raw { int4 hl, lh, hh; T4 ll; };
   // row pair n: low row n of (LL|HL), high row n of (LH|HH); whole-sample fold of the row index
-  auto load_pair = [&](int n) -> Raw {
-    int rl, rh;
+  auto pair_rows = [&](int n, int& rl, int& rh) {
     if (n < 0) { rl = -n; rh = -n - 1; }
     else if (n >= hh) { rl = Hc - 1 - n; rh = Hc - 2 - n; }
     else { rl = n; rh = n; }
+  };
+  auto ll_from_q = [&](int4 t) -> T4 {
+    if constexpr (LOSSY) return make_float4(dequant<QS1>(t.x, a.r[0], a.rqs), dequant<QS1>(t.y, a.r[0], a.rqs), dequant<QS1>(t.z, a.r[0], a.rqs), dequant<QS1>(t.w, a.r[0], a.rqs));
+    else return t;
+  };
+  auto load_pair = [&](int n) -> Raw {
+    int rl, rh;
+    pair_rows(n, rl, rh);
     const int32_t* row_lo = q + (size_t)rl * a.pitch;
     const int32_t* row_hi = q + (size_t)(rh + hh) * a.pitch;
     Raw r;
     r.hl = __ldg(reinterpret_cast<const int4*>(row_lo + hw));
     r.lh = __ldg(reinterpret_cast<const int4*>(row_hi));
     r.hh = __ldg(reinterpret_cast<const int4*>(row_hi + hw));
-    if constexpr (FIRST) {
-      const int4 t = __ldg(reinterpret_cast<const int4*>(row_lo));
-      if constexpr (LOSSY) r.ll = make_float4(dequant<QS1>(t.x, a.r[0], a.rqs), dequant<QS1>(t.y, a.r[0], a.rqs), dequant<QS1>(t.z, a.r[0], a.rqs), dequant<QS1>(t.w, a.r[0], a.rqs));
-      else r.ll = t;
-    } else {
-      r.ll = __ldg(reinterpret_cast<const T4*>(lls + (size_t)rl * a.ll_pitch));
-    }
+    if constexpr (FIRST) r.ll = ll_from_q(__ldg(reinterpret_cast<const int4*>(row_lo)));
+    else r.ll = __ldg(reinterpret_cast<const T4*>(lls + (size_t)rl * a.ll_pitch));
+    return r;
+  };
+  // The finest level (u8 output) moves 4 of the 5 bytes per pixel on its READ side: stage its subband rows
+  // through a per-warp cp.async ring kDepth steps deep, as the forward level-1 kernel does.
+  constexpr int kDepth = 4;
+  __shared__ __align__(16) unsigned char s_ring[DST_U8 ? 4 : 1][DST_U8 ? kDepth : 1][4][32][16];
+  auto& ring = s_ring[DST_U8 ? (threadIdx.x >> 5) : 0];
+  auto issue_pair = [&](int n, int slot) {
+    int rl, rh;
+    pair_rows(n, rl, rh);
+    const int32_t* row_lo = q + (size_t)rl * a.pitch;
+    const int32_t* row_hi = q + (size_t)(rh + hh) * a.pitch;
+    cp_async16(&ring[slot][0][lane][0], row_lo + hw);
+    cp_async16(&ring[slot][1][lane][0], row_hi);
+    cp_async16(&ring[slot][2][lane][0], row_hi + hw);
+    if constexpr (FIRST) cp_async16(&ring[slot][3][lane][0], row_lo);
+    else cp_async16(&ring[slot][3][lane][0], lls + (size_t)rl * a.ll_pitch);
+    cp_async_commit();
+  };
+  auto read_pair = [&](int slot) -> Raw {
+    Raw r;
+    r.hl = *reinterpret_cast<const int4*>(&ring[slot][0][lane][0]);
+    r.lh = *reinterpret_cast<const int4*>(&ring[slot][1][lane][0]);
+    r.hh = *reinterpret_cast<const int4*>(&ring[slot][2][lane][0]);
+    if constexpr (FIRST) r.ll = ll_from_q(*reinterpret_cast<const int4*>(&ring[slot][3][lane][0]));
+    else r.ll = *reinterpret_cast<const T4*>(&ring[slot][3][lane][0]);
     return r;
   };
   auto expand = [&](const Raw& r, T (&lo)[8], T (&hi)[8]) {
@@ -630,12 +658,27 @@ __global__ void __launch_bounds__(128, 3) dwt_inverse_fast_kernel(const FastInvA
   const int n0 = chunk * a.rp, n1 = min(n0 + a.rp, hh);
   VP vp; vp.init();
   const int ms = n0 - VP::kLead, mend = n1 + VP::kTail;
-  Raw cur = load_pair(ms);
+  Raw cur;
+  int slot = 0;
+  if constexpr (DST_U8) {
+#pragma unroll
+    for (int d = 0; d < kDepth; ++d) issue_pair(ms + d, d);
+  } else {
+    cur = load_pair(ms);
+  }
 #pragma unroll 2
   for (int m = ms; m <= mend; ++m) {
     T lo[8], hi[8], re[8], ro[8];
-    expand(cur, lo, hi);
-    cur = load_pair(m + 1);  // prefetch (pairs past the chunk fold to valid rows and are not used)
+    if constexpr (DST_U8) {
+      cp_async_wait<kDepth - 1>();  // pair m has landed
+      cur = read_pair(slot);
+      issue_pair(m + kDepth, slot);  // pairs past the chunk fold to valid rows and are not used
+      slot = slot + 1 == kDepth ? 0 : slot + 1;
+      expand(cur, lo, hi);
+    } else {
+      expand(cur, lo, hi);
+      cur = load_pair(m + 1);  // prefetch
+    }
     if constexpr (LOSSY) { hinv97<8>(lo, 1.0f / kK, 1.0f / kIK, left, right); hinv97<8>(hi, 1.0f / kK, 1.0f / kIK, left, right); }
     else { hinv53<8>(lo, left, right); hinv53<8>(hi, left, right); }
     vp.step(lo, hi, re, ro);
