@@ -34,7 +34,7 @@ import numpy as np  # noqa: E402
 WORKLOADS = {
     # name: (W, H, wl, lossy, qs, lut folder, frames per step, description)
     "cfg1": (512, 512, 5, 0, 1.0, "n1_lossless", 16, "configs[0]: 512x512 8-bit grey, lossless 5/3, wl=5, 64x64 codeblocks"),
-    "cfg2": (4096, 4096, 5, 1, 1.0, "n1_lossy", 4, "configs[1]: 4096x4096 8-bit grey, lossy 9/7 qs=1.0, wl=5, 64x64 codeblocks"),
+    "cfg2": (4096, 4096, 5, 1, 1.0, "n1_lossy", 8, "configs[1]: 4096x4096 8-bit grey, lossy 9/7 qs=1.0, wl=5, 64x64 codeblocks"),
     "cfg3": (7680, 4320, 6, 0, 1.0, "n1_lossless", 2, "configs[2]: 7680x4320 8-bit grey, lossless 5/3, wl=6, 64x64 codeblocks"),
     "cfg4": (3840, 2160, 5, 1, 1.0, "video_lossy", 8, "configs[3]: 3840x2160 8-bit grey video frames, lossy 9/7 qs=1, wl=5, frame-sharded"),
 }
@@ -74,6 +74,15 @@ def materialize_luts():
     root = tempfile.mkdtemp(prefix="pcs_lut_")
     lut_fixture.materialize_all(root)
     return root
+
+
+def measured_traffic():
+    """dram__bytes_read+write of the forward-DWT launches of one pcs_dwt_forward call, from the committed ncu
+    capture of this same command (profiles/dwt_traffic.json, written by scripts/ncu_summary.py traffic)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "dwt_traffic.json")))
+    except Exception:
+        return None
 
 
 def peaks():
@@ -219,8 +228,13 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"kernel": "dwt_forward (all levels of the batch; u8 in -> 32-bit Mallat coefficients out)", "bound": "hbm",
                      "achieved": dwt_gbs, "peak": hbm, "peak_source": hbm_src, "unit": "GB/s", "frac": dwt_gbs / hbm,
-                     "algorithmic_bytes_per_launch": 5 * A * B, "ms": dwt_ms, "traffic": None},
+                     "algorithmic_bytes_per_launch": 5 * A * B, "ms": dwt_ms, "traffic": None,
+                     "launches_per_call": "one per wavelet level (5)"},
     }
+    tr = measured_traffic()
+    if tr and tr.get("frames") == B and tr.get("workload") == args.workload:
+        res["roofline"]["traffic"] = tr["dram_bytes"]
+        res["roofline"]["traffic_source"] = tr.get("source")
     if args.stage_detail:
         m = stage.mean(axis=0)
         res["stage_ms"] = {"enc_dwt": m[0], "enc_bpc": m[1], "enc_bsb": m[2], "dec_bsb": m[3], "dec_bpc": m[4], "dec_dwt": m[5]}

@@ -49,7 +49,16 @@ struct pcs_ctx {
   int32_t* d_sizes = nullptr;      // [max_batch][ncb]
   uint16_t* d_stream = nullptr;    // [max_batch * max_words]
   long long* d_off = nullptr;      // [max_batch + 1]
-  long long* h_off = nullptr;      // pinned
+  long long* h_off = nullptr;      // pinned, [kSlots][max_batch + 1]
+  // host-buffer pipeline (pcs_encode_frames / pcs_decode_frames): the workspace is cut into kSlots slots of
+  // max_batch / kSlots frames, each with its own stream, so that the H2D copy of one chunk, the kernels of
+  // another and the D2H copy of a third overlap (PCIe is full duplex; copy engines run beside the SMs)
+  static constexpr int kSlots = 4;
+  cudaStream_t sstream[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t sev[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  long long* d_soff = nullptr;     // [kSlots][max_batch + 1]
+  void* d_sstatus = nullptr;       // [kSlots] look-back status areas
+  size_t status_bytes = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool timing = false;
@@ -176,8 +185,15 @@ int32_t pcs_create(const pcs_params* params, pcs_ctx** out) {
   alloc((void**)&c->d_sizes, B * c->ncb * 4);
   alloc((void**)&c->d_stream, B * c->max_words * 2);
   alloc((void**)&c->d_off, (B + 1) * sizeof(long long));
-  if (e == cudaSuccess) e = cudaHostAlloc((void**)&c->h_off, (B + 1) * sizeof(long long), cudaHostAllocDefault);
+  c->status_bytes = (bsb_status_bytes(c->ncb, p.max_batch) + 255) / 256 * 256;
+  alloc(&c->d_sstatus, pcs_ctx::kSlots * c->status_bytes);
+  alloc((void**)&c->d_soff, pcs_ctx::kSlots * (B + 1) * sizeof(long long));
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&c->h_off, pcs_ctx::kSlots * (B + 1) * sizeof(long long), cudaHostAllocDefault);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < pcs_ctx::kSlots && e == cudaSuccess; ++i) {
+    e = cudaStreamCreateWithFlags(&c->sstream[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->sev[i], cudaEventDisableTiming);
+  }
   for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
   if (e != cudaSuccess) { pcs_destroy(c); return (int)e; }
   *out = c;
@@ -190,6 +206,9 @@ void pcs_destroy(pcs_ctx* c) {
   cudaFree(c->d_scratch); cudaFree(c->d_status); cudaFree(c->d_px); cudaFree(c->d_coeff); cudaFree(c->d_cw);
   cudaFree(c->d_sizes); cudaFree(c->d_stream); cudaFree(c->d_off);
   if (c->h_off) cudaFreeHost(c->h_off);
+  cudaFree(c->d_sstatus); cudaFree(c->d_soff);
+  for (auto& s2 : c->sstream) if (s2) cudaStreamDestroy(s2);
+  for (auto& e2 : c->sev) if (e2) cudaEventDestroy(e2);
   if (c->stream) cudaStreamDestroy(c->stream);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   delete c;
@@ -280,25 +299,76 @@ int32_t pcs_last_stage_ms(pcs_ctx* c, float ms[3]) {
   return PCS_OK;
 }
 
+namespace {
+
+// One slot of the workspace: frames [k*sb, (k+1)*sb) of every per-frame buffer.
+struct Slot {
+  void* scratch; void* status; uint8_t* px; int32_t* coeff; uint16_t* cw; int32_t* sizes; uint16_t* stream;
+  long long* d_off; long long* h_off; cudaStream_t st; cudaEvent_t ev;
+};
+Slot make_slot(pcs_ctx* c, int k, int sb) {
+  const size_t f0 = (size_t)k * sb, B1 = (size_t)c->p.max_batch + 1;
+  Slot s;
+  s.scratch = static_cast<char*>(c->d_scratch) + f0 * c->scratch_elems * 4;
+  s.status = static_cast<char*>(c->d_sstatus) + (size_t)k * c->status_bytes;
+  s.px = c->d_px + f0 * (size_t)c->p.width * c->p.height;
+  s.coeff = c->d_coeff + f0 * c->A;
+  s.cw = c->d_cw + f0 * c->A;
+  s.sizes = c->d_sizes + f0 * c->ncb;
+  s.stream = c->d_stream + f0 * c->max_words;
+  s.d_off = c->d_soff + (size_t)k * B1;
+  s.h_off = c->h_off + (size_t)k * B1;
+  s.st = c->sstream[k]; s.ev = c->sev[k];
+  return s;
+}
+int slots_for(const pcs_ctx* c, int* sb) {
+  // chunks of max_batch / (2 * slots) frames: fine enough that the first upload and the last download (the
+  // parts of a call that cannot overlap anything) are short, coarse enough that a launch still fills the GPU
+  const int n = std::min<int>(pcs_ctx::kSlots, c->p.max_batch);
+  *sb = std::max(1, c->p.max_batch / (2 * n));
+  return n;
+}
+
+}  // namespace
+
 int32_t pcs_encode_frames(pcs_ctx* c, const uint8_t* h_px, int32_t nframes, int32_t first, uint16_t* h_stream, size_t cap,
                           int32_t* h_len, size_t* total_words) {
   if (!c || !h_px || !h_stream || nframes < 1) return PCS_E_ARG;
   const size_t fpx = (size_t)c->p.width * c->p.height;
+  int sb;
+  const int nslots = slots_for(c, &sb);
+  const int nchunks = (nframes + sb - 1) / sb;
   size_t written = 0;
-  for (int f0 = 0; f0 < nframes; f0 += c->p.max_batch) {
-    const int b = std::min(c->p.max_batch, nframes - f0);
-    PCS_CUDA_TRY(cudaMemcpyAsync(c->d_px, h_px + (size_t)f0 * fpx, (size_t)b * fpx, cudaMemcpyHostToDevice, c->stream));
-    int rc = pcs_encode_device(c, c->d_px, b, first + f0, c->d_stream, reinterpret_cast<int64_t*>(c->d_off), c->stream);
-    if (rc) return rc;
-    PCS_CUDA_TRY(cudaMemcpyAsync(c->h_off, c->d_off, (size_t)(b + 1) * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-    PCS_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    const size_t words = (size_t)c->h_off[b];
+  // second half of a chunk's work: its frame offsets are on the host -> copy its packed frames out
+  auto finish = [&](int j) -> int {
+    Slot s = make_slot(c, j % nslots, sb);
+    const int f0 = j * sb, b = std::min(sb, nframes - f0);
+    PCS_CUDA_TRY(cudaEventSynchronize(s.ev));
+    const size_t words = (size_t)s.h_off[b];
     if (written + words > cap) return fail(c, PCS_E_NOMEM, "output capacity too small");
-    PCS_CUDA_TRY(cudaMemcpyAsync(h_stream + written, c->d_stream, words * 2, cudaMemcpyDeviceToHost, c->stream));
-    PCS_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    if (h_len) for (int f = 0; f < b; ++f) h_len[f0 + f] = (int32_t)(c->h_off[f + 1] - c->h_off[f]);
+    PCS_CUDA_TRY(cudaMemcpyAsync(h_stream + written, s.stream, words * 2, cudaMemcpyDeviceToHost, s.st));
+    if (h_len) for (int f = 0; f < b; ++f) h_len[f0 + f] = (int32_t)(s.h_off[f + 1] - s.h_off[f]);
     written += words;
+    // the next user of this slot's h_off must not overwrite it before it was read: it was, just above
+    return PCS_OK;
+  };
+  for (int i = 0; i < nchunks; ++i) {
+    if (i >= nslots) { int rc = finish(i - nslots); if (rc) return rc; }  // frees the slot (same stream: ordered)
+    Slot s = make_slot(c, i % nslots, sb);
+    const int f0 = i * sb, b = std::min(sb, nframes - f0);
+    PCS_CUDA_TRY(cudaMemcpyAsync(s.px, h_px + (size_t)f0 * fpx, (size_t)b * fpx, cudaMemcpyHostToDevice, s.st));
+    int rc = dwt_forward(s.px, s.coeff, s.scratch, c->p.width, c->p.height, c->Wa, c->Ha, c->p.wavelet_levels, c->p.lossy != 0,
+                         c->p.quant_size, true, b, s.st);
+    if (rc) return rc;
+    rc = bpc_encode(s.coeff, false, s.cw, s.sizes, bpc_args(c, b), s.st);
+    if (rc) return rc;
+    rc = bsb_pack(s.cw, s.sizes, s.stream, s.d_off, s.status, bsb_args(c, b, first + f0), s.st);
+    if (rc) return rc;
+    PCS_CUDA_TRY(cudaMemcpyAsync(s.h_off, s.d_off, (size_t)(b + 1) * sizeof(long long), cudaMemcpyDeviceToHost, s.st));
+    PCS_CUDA_TRY(cudaEventRecord(s.ev, s.st));
   }
+  for (int j = std::max(0, nchunks - nslots); j < nchunks; ++j) { int rc = finish(j); if (rc) return rc; }
+  for (int k = 0; k < nslots; ++k) PCS_CUDA_TRY(cudaStreamSynchronize(c->sstream[k]));
   if (total_words) *total_words = written;
   return PCS_OK;
 }
@@ -306,24 +376,35 @@ int32_t pcs_encode_frames(pcs_ctx* c, const uint8_t* h_px, int32_t nframes, int3
 int32_t pcs_decode_frames(pcs_ctx* c, const uint16_t* h_stream, const int32_t* h_len, int32_t nframes, uint8_t* h_px) {
   if (!c || !h_stream || !h_len || !h_px || nframes < 1) return PCS_E_ARG;
   const size_t fpx = (size_t)c->p.width * c->p.height;
+  int sb;
+  const int nslots = slots_for(c, &sb);
+  const int nchunks = (nframes + sb - 1) / sb;
   size_t consumed = 0;
-  for (int f0 = 0; f0 < nframes; f0 += c->p.max_batch) {
-    const int b = std::min(c->p.max_batch, nframes - f0);
+  for (int i = 0; i < nchunks; ++i) {
+    Slot s = make_slot(c, i % nslots, sb);
+    const int f0 = i * sb, b = std::min(sb, nframes - f0);
+    if (i >= nslots) PCS_CUDA_TRY(cudaEventSynchronize(s.ev));  // the slot's pinned offsets have been uploaded
     long long off = 0;
     for (int f = 0; f < b; ++f) {
       const int len = h_len[f0 + f];
       if (len < 2 * c->ncb + 10 || (size_t)len > c->max_words) return fail(c, PCS_E_STREAM, "frame length out of range");
-      c->h_off[f] = off; off += len;
+      s.h_off[f] = off; off += len;
     }
-    c->h_off[b] = off;
-    PCS_CUDA_TRY(cudaMemcpyAsync(c->d_stream, h_stream + consumed, (size_t)off * 2, cudaMemcpyHostToDevice, c->stream));
-    PCS_CUDA_TRY(cudaMemcpyAsync(c->d_off, c->h_off, (size_t)(b + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
-    int rc = pcs_decode_device(c, c->d_stream, reinterpret_cast<const int64_t*>(c->d_off), b, c->d_px, c->stream);
+    s.h_off[b] = off;
+    PCS_CUDA_TRY(cudaMemcpyAsync(s.stream, h_stream + consumed, (size_t)off * 2, cudaMemcpyHostToDevice, s.st));
+    PCS_CUDA_TRY(cudaMemcpyAsync(s.d_off, s.h_off, (size_t)(b + 1) * sizeof(long long), cudaMemcpyHostToDevice, s.st));
+    PCS_CUDA_TRY(cudaEventRecord(s.ev, s.st));
+    int rc = bsb_unpack(s.stream, s.d_off, s.cw, s.sizes, s.status, bsb_args(c, b, 1), s.st);
     if (rc) return rc;
-    PCS_CUDA_TRY(cudaMemcpyAsync(h_px + (size_t)f0 * fpx, c->d_px, (size_t)b * fpx, cudaMemcpyDeviceToHost, c->stream));
-    PCS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    rc = bpc_decode(s.cw, s.sizes, s.coeff, bpc_args(c, b), s.st);
+    if (rc) return rc;
+    rc = dwt_inverse(s.coeff, s.px, s.scratch, c->p.width, c->p.height, c->Wa, c->Ha, c->p.wavelet_levels, c->p.lossy != 0,
+                     c->p.quant_size, (c->p.flags & PCS_F_REF_FLAT_CROP) != 0, b, s.st);
+    if (rc) return rc;
+    PCS_CUDA_TRY(cudaMemcpyAsync(h_px + (size_t)f0 * fpx, s.px, (size_t)b * fpx, cudaMemcpyDeviceToHost, s.st));
     consumed += (size_t)off;
   }
+  for (int k = 0; k < nslots; ++k) PCS_CUDA_TRY(cudaStreamSynchronize(c->sstream[k]));
   return PCS_OK;
 }
 
