@@ -73,5 +73,26 @@ def full(path, out):
             f.write("\n")
 
 
+def traffic(path, out, workload="cfg2", frames=8, nlaunch=5):
+    """dram bytes (read + write) of the first `nlaunch` dwt_forward launches of a --set full capture = one
+    pcs_dwt_forward call over the bench batch -> profiles/dwt_traffic.json (bench.py's roofline.traffic)."""
+    import json
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units = rows[0], rows[1]
+    ir, iw, ik, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name"), hdr.index("gpu__time_duration.sum")
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, t_us, n = 0.0, 0.0, 0
+    for r in rows[2:]:
+        if "dwt_forward" not in r[ik] or n >= nlaunch:
+            continue
+        tot += float(r[ir].replace(",", "")) * scale[units[ir]] + float(r[iw].replace(",", "")) * scale[units[iw]]
+        t_us += float(r[it].replace(",", "")) * {"us": 1, "ms": 1e3, "ns": 1e-3}.get(units[it], 1)
+        n += 1
+    json.dump({"workload": workload, "frames": frames, "dram_bytes": int(tot), "launches": n, "ncu_sum_us": t_us,
+               "source": f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum over the {n} forward-DWT launches of one call ({path})"},
+              open(out, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
