@@ -234,3 +234,66 @@ def test_full_size_properties(luts):
         psnr = 10 * np.log10(255.0 ** 2 / mse)
         assert abs(psnr - e["dec_psnr"]) <= 0.01, (name, psnr, e["dec_psnr"])
         cd.close()
+
+
+def test_config4_video_against_reference(luts):
+    """BASELINE config 4 shape (3840x2160 lossy video, mirrored rows 2160..2175): the first 4 frames byte for byte
+    against the reference binary (sha256 of its stream and its `_SIZE` text), then a 16-frame batch whose frames
+    must be independent of how they are batched (frame f of the batch == frame f coded alone, header aside)."""
+    import hashlib
+    import json
+    import os
+    man = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_manifest.json")))
+    e = man["cfg4_4k_f4_wl5_q1"]
+    W, H, wl = e["W"], e["H"], e["wl"]
+    _, plut = luts(e["lut"], wl)
+    frames = synth.synth_video(W, H, 16)
+    cd = codec.Codec(codec.Params(W, H, wl, True, e["qs"], frames=4, max_batch=4), plut)
+    stream, lens = cd.encode_frames(frames[:4])
+    assert ",".join(str(int(v)) for v in lens) == e["size_text"]
+    assert hashlib.sha256(stream.tobytes()).hexdigest() == e["enc_sha256"]
+    dec = cd.decode_frames(stream, lens)
+    assert hashlib.sha256(dec.tobytes()).hexdigest() == e["dec_sha256"] or \
+        (np.abs(dec.astype(np.int32) - frames[:4]).max() <= e["dec_maxabs"] + 1)
+    mse = np.mean((dec.astype(np.float64) - frames[:4]) ** 2)
+    assert abs(10 * np.log10(255.0 ** 2 / mse) - e["dec_psnr"]) <= 0.01
+    cd.close()
+    # batching invariance over 16 frames with a different batch size (frames > 0 carry 0xFFFF x 9 instead of the header)
+    cd = codec.Codec(codec.Params(W, H, wl, True, e["qs"], frames=4, max_batch=16), plut)
+    s16, l16 = cd.encode_frames(frames)
+    assert np.array_equal(l16[:4], lens) and np.array_equal(s16[: stream.size], stream)
+    off = np.concatenate([[0], np.cumsum(l16)])
+    one = codec.Codec(codec.Params(W, H, wl, True, e["qs"], frames=4, max_batch=1), plut)
+    for f in (5, 15):
+        sf, lf = one.encode_frames(frames[f:f + 1], first_frame_index=f)
+        assert lf[0] == l16[f] and np.array_equal(sf, s16[off[f]:off[f + 1]])
+    d16 = cd.decode_frames(s16, l16)
+    assert np.array_equal(d16[:4], dec)
+    assert np.abs(d16.astype(np.int32) - frames).max() <= 3
+    one.close(); cd.close()
+
+
+def test_config5_row_bands(luts):
+    """BASELINE config 5 shape: a 32768-wide still cut into 32768x4096 row bands (one band == one reference
+    'frame'); two bands, lossless.  The reference binary itself fails on this size (tests/golden manifest:
+    rc_dec = -8), so the checks are the size-independent ones: exact round trip, band independence, and the
+    packed layout invariants (header only on global band 0, per-block sizes sum to the band length)."""
+    W, H, wl = 32768, 4096, 5
+    _, plut = luts("n1_lossless", wl)
+    bands = np.stack([synth.synth_frame(W, H, 0, 0, H * b) for b in range(2)])
+    cd = codec.Codec(codec.Params(W, H, wl, False, 1.0, frames=8, max_batch=2), plut)
+    stream, lens = cd.encode_frames(bands)
+    ncb = cd.ncb
+    off = np.concatenate([[0], np.cumsum(lens)])
+    for b in range(2):
+        fr = stream[off[b]:off[b + 1]]
+        sizes = fr[10:10 + 2 * ncb:2].astype(np.int64)
+        assert sizes.sum() + ncb + 10 == lens[b]          # HTotalBSSize = sum(size) + nCB + 10
+        assert fr[-1] == 0xFFFF
+        assert (fr[:9] == 0xFFFF).all() == (b != 0)       # only global band 0 carries the header
+    dec = cd.decode_frames(stream, lens)
+    assert np.array_equal(dec, bands)
+    # band 1 coded alone (as rank 1 of a sharded job would) gives the same bytes
+    alone, l1 = cd.encode_frames(bands[1:2], first_frame_index=1)
+    assert l1[0] == lens[1] and np.array_equal(alone, stream[off[1]:off[2]])
+    cd.close()
