@@ -20,8 +20,8 @@ namespace pcs {
 unsigned long long g_launches = 0;
 
 size_t dwt_scratch_elems(int Wa, int Ha, int wl);
-int dwt_forward(const uint8_t*, void*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t);
-int dwt_inverse(const int32_t*, uint8_t*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t);
+int dwt_forward(const uint8_t*, void*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t, DwtAux*);
+int dwt_inverse(const int32_t*, uint8_t*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t, DwtAux*);
 int bpc_encode(const void*, bool, uint16_t*, int32_t*, const BpcArgs&, cudaStream_t);
 int bpc_decode(const uint16_t*, const int32_t*, int32_t*, const BpcArgs&, cudaStream_t);
 int export_ref_codestream(const uint16_t*, const int32_t*, int32_t*, long long, cudaStream_t);
@@ -59,6 +59,7 @@ struct pcs_ctx {
   long long* d_soff = nullptr;     // [kSlots][max_batch + 1]
   void* d_sstatus = nullptr;       // [kSlots] look-back status areas
   size_t status_bytes = 0;
+  DwtAux* aux = nullptr;           // auxiliary streams of the batched DWT calls (device-buffer entry points)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool timing = false;
@@ -190,6 +191,7 @@ int32_t pcs_create(const pcs_params* params, pcs_ctx** out) {
   alloc((void**)&c->d_soff, pcs_ctx::kSlots * (B + 1) * sizeof(long long));
   if (e == cudaSuccess) e = cudaHostAlloc((void**)&c->h_off, pcs_ctx::kSlots * (B + 1) * sizeof(long long), cudaHostAllocDefault);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) { c->aux = dwt_aux_create(); if (!c->aux) e = cudaErrorMemoryAllocation; }
   for (int i = 0; i < pcs_ctx::kSlots && e == cudaSuccess; ++i) {
     e = cudaStreamCreateWithFlags(&c->sstream[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->sev[i], cudaEventDisableTiming);
@@ -209,6 +211,7 @@ void pcs_destroy(pcs_ctx* c) {
   cudaFree(c->d_sstatus); cudaFree(c->d_soff);
   for (auto& s2 : c->sstream) if (s2) cudaStreamDestroy(s2);
   for (auto& e2 : c->sev) if (e2) cudaEventDestroy(e2);
+  dwt_aux_destroy(c->aux);
   if (c->stream) cudaStreamDestroy(c->stream);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   delete c;
@@ -227,13 +230,13 @@ uint64_t pcs_kernel_launch_count(void) { return g_launches; }
 int32_t pcs_dwt_forward(pcs_ctx* c, const uint8_t* d_px, void* d_coeff, int32_t trunc, int32_t batch, void* st) {
   CHECK_BATCH(c, batch);
   return dwt_forward(d_px, d_coeff, c->d_scratch, c->p.width, c->p.height, c->Wa, c->Ha, c->p.wavelet_levels, c->p.lossy != 0,
-                     c->p.quant_size, trunc != 0, batch, (cudaStream_t)st);
+                     c->p.quant_size, trunc != 0, batch, (cudaStream_t)st, c->aux);
 }
 
 int32_t pcs_dwt_inverse(pcs_ctx* c, const int32_t* d_q, uint8_t* d_px, int32_t batch, void* st) {
   CHECK_BATCH(c, batch);
   return dwt_inverse(d_q, d_px, c->d_scratch, c->p.width, c->p.height, c->Wa, c->Ha, c->p.wavelet_levels, c->p.lossy != 0,
-                     c->p.quant_size, (c->p.flags & PCS_F_REF_FLAT_CROP) != 0, batch, (cudaStream_t)st);
+                     c->p.quant_size, (c->p.flags & PCS_F_REF_FLAT_CROP) != 0, batch, (cudaStream_t)st, c->aux);
 }
 
 int32_t pcs_bpc_encode(pcs_ctx* c, const void* d_coeff, int32_t is_float, uint16_t* d_cw, int32_t* d_sizes, int32_t batch, void* st) {
@@ -358,7 +361,7 @@ int32_t pcs_encode_frames(pcs_ctx* c, const uint8_t* h_px, int32_t nframes, int3
     const int f0 = i * sb, b = std::min(sb, nframes - f0);
     PCS_CUDA_TRY(cudaMemcpyAsync(s.px, h_px + (size_t)f0 * fpx, (size_t)b * fpx, cudaMemcpyHostToDevice, s.st));
     int rc = dwt_forward(s.px, s.coeff, s.scratch, c->p.width, c->p.height, c->Wa, c->Ha, c->p.wavelet_levels, c->p.lossy != 0,
-                         c->p.quant_size, true, b, s.st);
+                         c->p.quant_size, true, b, s.st, nullptr);
     if (rc) return rc;
     rc = bpc_encode(s.coeff, false, s.cw, s.sizes, bpc_args(c, b), s.st);
     if (rc) return rc;
@@ -399,7 +402,7 @@ int32_t pcs_decode_frames(pcs_ctx* c, const uint16_t* h_stream, const int32_t* h
     rc = bpc_decode(s.cw, s.sizes, s.coeff, bpc_args(c, b), s.st);
     if (rc) return rc;
     rc = dwt_inverse(s.coeff, s.px, s.scratch, c->p.width, c->p.height, c->Wa, c->Ha, c->p.wavelet_levels, c->p.lossy != 0,
-                     c->p.quant_size, (c->p.flags & PCS_F_REF_FLAT_CROP) != 0, b, s.st);
+                     c->p.quant_size, (c->p.flags & PCS_F_REF_FLAT_CROP) != 0, b, s.st, nullptr);
     if (rc) return rc;
     PCS_CUDA_TRY(cudaMemcpyAsync(h_px + (size_t)f0 * fpx, s.px, (size_t)b * fpx, cudaMemcpyDeviceToHost, s.st));
     consumed += (size_t)off;

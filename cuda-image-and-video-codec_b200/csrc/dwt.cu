@@ -20,6 +20,7 @@
 // 9/7 arithmetic uses explicit __fmaf_rn/__fadd_rn/__fmul_rn so that the operation shapes are
 // exactly those of the reference binary, including its one cross-statement FMA contraction
 // (vertical scale fused into horizontal step one on odd columns; see oracle/picsong_oracle.c).
+#include <algorithm>
 #include <cstdlib>
 
 #include "pcs_common.cuh"
@@ -547,18 +548,18 @@ static int fuse_mode() {
 
 // Host loop over levels (replaces DWTEngine::DWTForward, DWT/DWTGenerator.cu:1268-1342; no host
 // synchronisation between levels).  out_int: 9/7 only, write (int)c instead of c.
-int dwt_forward(const uint8_t* d_px, void* d_coeff, void* d_scratch, int W, int H, int Wa, int Ha, int wl,
-                bool lossy, float qs, bool out_int, int frames, cudaStream_t st) {
+static int dwt_forward_levels(const uint8_t* d_px, void* d_coeff, void* d_scratch, int W, int H, int Wa, int Ha, int wl,
+                              bool lossy, float qs, bool out_int, int frames, int lfirst, int llast, cudaStream_t st) {
   const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl);
-  int first = 1;
+  int first = lfirst;
   // leading levels through the streaming kernel of dwt_fast.cu while the geometry allows it
-  while (fuse_mode() > 0 && first <= wl) {
+  while (fuse_mode() > 0 && first <= llast) {
     const int l = first, Wc = Wa >> (l - 1), Hc = Ha >> (l - 1);
     const bool u8 = l == 1;
     const void* src = u8 ? static_cast<const void*>(d_px) : static_cast<const char*>(d_scratch) + ll_offset(Wa, Ha, l - 1) * 4;
     const long long sfs = u8 ? (long long)W * H : (long long)S;
     const int sp = u8 ? W : Wc;
-    int lv = (u8 && fuse_mode() == 2 && wl >= 2) ? 2 : 1;
+    int lv = (u8 && fuse_mode() == 2 && llast >= 2) ? 2 : 1;
     void* ll = (l + lv - 1 == wl) ? nullptr : static_cast<char*>(d_scratch) + ll_offset(Wa, Ha, l + lv - 1) * 4;
     if (!dwt_forward_fast_ok(src, d_coeff, ll, u8, sp, sfs, H, Wc, Hc, lv)) {
       if (lv == 2) { lv = 1; ll = (l == wl) ? nullptr : static_cast<char*>(d_scratch) + ll_offset(Wa, Ha, l) * 4; }
@@ -570,7 +571,7 @@ int dwt_forward(const uint8_t* d_px, void* d_coeff, void* d_scratch, int W, int 
     if (rc) return rc;
     first = l + lv;
   }
-  for (int l = first; l <= wl; ++l) {
+  for (int l = first; l <= llast; ++l) {
     FwdArgs a{};
     a.Wc = Wa >> (l - 1); a.Hc = Ha >> (l - 1);
     a.W = W; a.H = H; a.Wa = Wa;
@@ -608,10 +609,10 @@ int dwt_forward(const uint8_t* d_px, void* d_coeff, void* d_scratch, int W, int 
 }
 
 // Replaces DWTEngine::DWTReverse (DWT/DWTGenerator.cu:1349-1424) + removeOffsetAndApplyMaxMin[Lossy].
-int dwt_inverse(const int32_t* d_q, uint8_t* d_px, void* d_scratch, int W, int H, int Wa, int Ha, int wl, bool lossy,
-                float qs, bool flat_crop, int frames, cudaStream_t st) {
+static int dwt_inverse_levels(const int32_t* d_q, uint8_t* d_px, void* d_scratch, int W, int H, int Wa, int Ha, int wl, bool lossy,
+                              float qs, bool flat_crop, int frames, int lhigh, int llow, cudaStream_t st) {
   const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl);
-  for (int l = wl; l >= 1; --l) {
+  for (int l = lhigh; l >= llow; --l) {
     InvArgs a{};
     a.q = d_q; a.q_fstride = (long long)A; a.Wa = Wa;
     a.Wc = Wa >> (l - 1); a.Hc = Ha >> (l - 1);
@@ -651,6 +652,92 @@ int dwt_inverse(const int32_t* d_q, uint8_t* d_px, void* d_scratch, int W, int H
     }
     ++g_launches;
   }
+  return (int)cudaGetLastError();
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Batch drivers.  Level 1 moves 5 of the ~7 bytes per pixel; the deeper levels are small, latency-bound
+// launches.  With a batch of frames the two are overlapped: the batch is cut into groups of `gf` frames,
+// level 1 of group g runs on one auxiliary stream while levels 2..wl of group g-1 run on the other (and
+// find the LL planes group g-1 just wrote still in L2).  The caller's stream forks into / joins from the
+// two auxiliary streams with events; nothing synchronises the host.
+// ---------------------------------------------------------------------------------------------
+DwtAux* dwt_aux_create() {
+  DwtAux* x = new DwtAux();
+  bool ok = cudaStreamCreateWithFlags(&x->a, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&x->b, cudaStreamNonBlocking) == cudaSuccess;
+  for (auto& e : x->ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { dwt_aux_destroy(x); return nullptr; }
+  return x;
+}
+void dwt_aux_destroy(DwtAux* x) {
+  if (!x) return;
+  if (x->a) cudaStreamDestroy(x->a);
+  if (x->b) cudaStreamDestroy(x->b);
+  for (auto& e : x->ev) if (e) cudaEventDestroy(e);
+  delete x;
+}
+static int group_frames(int frames, int wl) {  // PCS_DWT_GROUP: frames per group; default 0 = off (measured slower)
+  static int g = -1;
+  if (g < 0) { const char* e = getenv("PCS_DWT_GROUP"); g = e ? atoi(e) : 0; if (g < 0) g = 0; }
+  if (g == 0 || wl < 2 || frames < 2 * g) return 0;
+  return (frames + g - 1) / g <= DwtAux::kMaxGroups ? g : (frames + DwtAux::kMaxGroups - 1) / DwtAux::kMaxGroups;
+}
+
+int dwt_forward(const uint8_t* d_px, void* d_coeff, void* d_scratch, int W, int H, int Wa, int Ha, int wl, bool lossy, float qs,
+                bool out_int, int frames, cudaStream_t st, DwtAux* aux) {
+  const int gf = aux ? group_frames(frames, wl) : 0;
+  if (!gf) return dwt_forward_levels(d_px, d_coeff, d_scratch, W, H, Wa, Ha, wl, lossy, qs, out_int, frames, 1, wl, st);
+  const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl), P = (size_t)W * H;
+  const int ng = (frames + gf - 1) / gf;
+  PCS_CUDA_TRY(cudaEventRecord(aux->ev[0], st));
+  PCS_CUDA_TRY(cudaStreamWaitEvent(aux->a, aux->ev[0], 0));
+  PCS_CUDA_TRY(cudaStreamWaitEvent(aux->b, aux->ev[0], 0));
+  for (int g = 0; g < ng; ++g) {
+    const int f0 = g * gf, n = std::min(gf, frames - f0);
+    const uint8_t* px = d_px + f0 * P;
+    void* co = static_cast<char*>(d_coeff) + f0 * A * 4;
+    void* sc = static_cast<char*>(d_scratch) + f0 * S * 4;
+    int rc = dwt_forward_levels(px, co, sc, W, H, Wa, Ha, wl, lossy, qs, out_int, n, 1, 1, aux->a);
+    if (rc) return rc;
+    PCS_CUDA_TRY(cudaEventRecord(aux->ev[3 + g], aux->a));
+    PCS_CUDA_TRY(cudaStreamWaitEvent(aux->b, aux->ev[3 + g], 0));
+    rc = dwt_forward_levels(px, co, sc, W, H, Wa, Ha, wl, lossy, qs, out_int, n, 2, wl, aux->b);
+    if (rc) return rc;
+  }
+  PCS_CUDA_TRY(cudaEventRecord(aux->ev[1], aux->a));
+  PCS_CUDA_TRY(cudaEventRecord(aux->ev[2], aux->b));
+  PCS_CUDA_TRY(cudaStreamWaitEvent(st, aux->ev[1], 0));
+  PCS_CUDA_TRY(cudaStreamWaitEvent(st, aux->ev[2], 0));
+  return (int)cudaGetLastError();
+}
+
+int dwt_inverse(const int32_t* d_q, uint8_t* d_px, void* d_scratch, int W, int H, int Wa, int Ha, int wl, bool lossy, float qs,
+                bool flat_crop, int frames, cudaStream_t st, DwtAux* aux) {
+  const int gf = aux ? group_frames(frames, wl) : 0;
+  if (!gf) return dwt_inverse_levels(d_q, d_px, d_scratch, W, H, Wa, Ha, wl, lossy, qs, flat_crop, frames, wl, 1, st);
+  const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl), P = (size_t)W * H;
+  const int ng = (frames + gf - 1) / gf;
+  PCS_CUDA_TRY(cudaEventRecord(aux->ev[0], st));
+  PCS_CUDA_TRY(cudaStreamWaitEvent(aux->a, aux->ev[0], 0));
+  PCS_CUDA_TRY(cudaStreamWaitEvent(aux->b, aux->ev[0], 0));
+  for (int g = 0; g < ng; ++g) {
+    const int f0 = g * gf, n = std::min(gf, frames - f0);
+    const int32_t* q = d_q + f0 * A;
+    uint8_t* px = d_px + f0 * P;
+    void* sc = static_cast<char*>(d_scratch) + f0 * S * 4;
+    int rc = dwt_inverse_levels(q, px, sc, W, H, Wa, Ha, wl, lossy, qs, flat_crop, n, wl, 2, aux->b);  // coarse levels
+    if (rc) return rc;
+    PCS_CUDA_TRY(cudaEventRecord(aux->ev[3 + g], aux->b));
+    PCS_CUDA_TRY(cudaStreamWaitEvent(aux->a, aux->ev[3 + g], 0));
+    rc = dwt_inverse_levels(q, px, sc, W, H, Wa, Ha, wl, lossy, qs, flat_crop, n, 1, 1, aux->a);        // finest level
+    if (rc) return rc;
+  }
+  PCS_CUDA_TRY(cudaEventRecord(aux->ev[1], aux->a));
+  PCS_CUDA_TRY(cudaEventRecord(aux->ev[2], aux->b));
+  PCS_CUDA_TRY(cudaStreamWaitEvent(st, aux->ev[1], 0));
+  PCS_CUDA_TRY(cudaStreamWaitEvent(st, aux->ev[2], 0));
   return (int)cudaGetLastError();
 }
 

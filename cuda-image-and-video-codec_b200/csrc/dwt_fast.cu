@@ -416,6 +416,20 @@ void variant_params(int Hc, int* nW, int* ls) {
   *ls = (*nW - 1) * 10 - ((10 - ((Hc - 8) % 10)) % 10);
 }
 
+// Row pairs per chunk.  A chunk costs (rp + warm-up) serial steps and the grid runs in ceil(CTAs / resident CTAs)
+// waves, so pick the rp that minimises waves * steps: long chunks amortise the warm-up rows, but a grid that
+// spills a few CTAs into a second wave doubles the time of the small, latency-bound levels.
+int choose_rp(int nstrips, int hh, int frames, int warm, int step) {
+  const long long slots = 148LL * 4;  // CTAs of 128 threads resident at <= 128 registers per thread
+  int best = step; long long best_cost = -1;
+  for (int rp = step; rp <= 128; rp += step) {
+    const long long ctas = (long long)((nstrips * ((hh + rp - 1) / rp) + 3) / 4) * frames;
+    const long long cost = ((ctas + slots - 1) / slots) * (rp + warm);
+    if (best_cost < 0 || cost <= best_cost) { best = rp; best_cost = cost; }
+  }
+  return best;
+}
+
 template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS>
 void launch(const FastFwdArgs& a, dim3 grid, cudaStream_t st) {
   if (a.qs == 1.0f) dwt_forward_fused<LOSSY, OT, SRC_U8, LEVELS, true><<<grid, 128, 0, st>>>(a);
@@ -729,11 +743,8 @@ int dwt_forward_fast(const void* src, bool src_u8, long long src_fstride, int sr
   const int eff = (32 - 2 * levels) * 8;
   a.nstrips = (Wc + eff - 1) / eff;
   const int hh1 = Hc >> 1;
-  // chunk length: long enough to amortise the warm-up rows, short enough to fill 148 SMs with >= 12 warps each
-  int rp = 128;
-  while (rp > 4 && (long long)a.nstrips * ((hh1 + rp - 1) / rp) * frames < 148LL * 12) rp >>= 1;
-  a.rp = rp;
-  a.nchunks = (hh1 + rp - 1) / rp;
+  a.rp = choose_rp(a.nstrips, hh1, frames, levels == 2 ? 12 : 3, 4);
+  a.nchunks = (hh1 + a.rp - 1) / a.rp;
   dim3 grid((a.nstrips * a.nchunks + 3) / 4, frames);
   if (src_u8) {
     if (levels == 2) {
@@ -775,10 +786,8 @@ int dwt_inverse_fast(const int32_t* d_q, long long q_fstride, int pitch, const v
   a.rqs = 1.0f / qs;
   a.nstrips = (Wc + 239) / 240;
   const int hh = Hc >> 1;
-  int rp = 128;
-  while (rp > 4 && (long long)a.nstrips * ((hh + rp - 1) / rp) * frames < 148LL * 12) rp >>= 1;
-  a.rp = rp;
-  a.nchunks = (hh + rp - 1) / rp;
+  a.rp = choose_rp(a.nstrips, hh, frames, 4, 2);
+  a.nchunks = (hh + a.rp - 1) / a.rp;
   dim3 grid((a.nstrips * a.nchunks + 3) / 4, frames);
   const bool qs1 = a.rqs == 1.0f;
   if (!lossy) {

@@ -297,3 +297,23 @@ def test_config5_row_bands(luts):
     alone, l1 = cd.encode_frames(bands[1:2], first_frame_index=1)
     assert l1[0] == lens[1] and np.array_equal(alone, stream[off[1]:off[2]])
     cd.close()
+
+
+@pytest.mark.parametrize("lossy", [0, 1])
+def test_batched_dwt_matches_single_frames(lossy, luts):
+    """The batched DWT drivers overlap level 1 with the deeper levels of the previous frame group on auxiliary
+    streams; a batch must give, frame by frame, exactly what single-frame calls give (forward and inverse)."""
+    W, H, wl, B = 512, 384, 4, 7
+    _, plut = luts(LUTS[(lossy, 1)], wl)
+    cd = codec.Codec(codec.Params(W, H, wl, bool(lossy), 0.7, max_batch=B), plut)
+    px = torch.from_numpy(synth.synth_video(W, H, B)).cuda()
+    for it in range(3):  # repeated calls reuse the fork/join events
+        c_all = cd.dwt_forward(px, trunc_to_int=True)
+        c_one = torch.cat([cd.dwt_forward(px[f:f + 1], trunc_to_int=True) for f in range(B)])
+        assert torch.equal(c_all, c_one)
+        p_all = cd.dwt_inverse(c_all)
+        p_one = torch.cat([cd.dwt_inverse(c_all[f:f + 1]) for f in range(B)])
+        assert torch.equal(p_all, p_one)
+    if not lossy:
+        assert torch.equal(p_all, px)
+    cd.close()
