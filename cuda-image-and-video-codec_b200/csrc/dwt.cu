@@ -678,6 +678,16 @@ void dwt_aux_destroy(DwtAux* x) {
   for (auto& e : x->ev) if (e) cudaEventDestroy(e);
   delete x;
 }
+// Frames per sub-batch such that their LL1 planes (A/4 32-bit samples each) fit the part of the 126 MB L2 we
+// ask it to keep (PCS_DWT_L2_MB; default 0 = off: splitting the launches was measured to cost more than the L2 hits
+// gain, 0.240 vs 0.226 ms for 8 frames of 4096^2).
+static int l2_sub_batch(int Wa, int Ha, int frames, int wl) {
+  static long long mb = -1;
+  if (mb < 0) { const char* e = getenv("PCS_DWT_L2_MB"); mb = e ? atoll(e) : 0; }
+  if (wl < 2 || mb <= 0) return frames;
+  const long long ll1 = (long long)Wa * Ha;  // bytes of one frame's LL1 plane
+  return (int)std::max<long long>(1, std::min<long long>(frames, (mb << 20) / ll1));
+}
 static int group_frames(int frames, int wl) {  // PCS_DWT_GROUP: frames per group; default 0 = off (measured slower)
   static int g = -1;
   if (g < 0) { const char* e = getenv("PCS_DWT_GROUP"); g = e ? atoi(e) : 0; if (g < 0) g = 0; }
@@ -688,7 +698,20 @@ static int group_frames(int frames, int wl) {  // PCS_DWT_GROUP: frames per grou
 int dwt_forward(const uint8_t* d_px, void* d_coeff, void* d_scratch, int W, int H, int Wa, int Ha, int wl, bool lossy, float qs,
                 bool out_int, int frames, cudaStream_t st, DwtAux* aux) {
   const int gf = aux ? group_frames(frames, wl) : 0;
-  if (!gf) return dwt_forward_levels(d_px, d_coeff, d_scratch, W, H, Wa, Ha, wl, lossy, qs, out_int, frames, 1, wl, st);
+  if (!gf) {
+    // Levels 1 and 2 go sub-batch by sub-batch so that the LL1 planes level 1 writes (evict-last) are still in
+    // L2 when level 2 reads them; the remaining levels (LL2 and below are small) run over the whole batch.
+    const int sb = l2_sub_batch(Wa, Ha, frames, wl);
+    if (sb >= frames) return dwt_forward_levels(d_px, d_coeff, d_scratch, W, H, Wa, Ha, wl, lossy, qs, out_int, frames, 1, wl, st);
+    const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl), P = (size_t)W * H;
+    for (int f0 = 0; f0 < frames; f0 += sb) {
+      const int n = std::min(sb, frames - f0);
+      int rc = dwt_forward_levels(d_px + f0 * P, static_cast<char*>(d_coeff) + f0 * A * 4, static_cast<char*>(d_scratch) + f0 * S * 4, W, H,
+                                  Wa, Ha, wl, lossy, qs, out_int, n, 1, 2, st);
+      if (rc) return rc;
+    }
+    return wl > 2 ? dwt_forward_levels(d_px, d_coeff, d_scratch, W, H, Wa, Ha, wl, lossy, qs, out_int, frames, 3, wl, st) : 0;
+  }
   const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl), P = (size_t)W * H;
   const int ng = (frames + gf - 1) / gf;
   PCS_CUDA_TRY(cudaEventRecord(aux->ev[0], st));
@@ -716,7 +739,19 @@ int dwt_forward(const uint8_t* d_px, void* d_coeff, void* d_scratch, int W, int 
 int dwt_inverse(const int32_t* d_q, uint8_t* d_px, void* d_scratch, int W, int H, int Wa, int Ha, int wl, bool lossy, float qs,
                 bool flat_crop, int frames, cudaStream_t st, DwtAux* aux) {
   const int gf = aux ? group_frames(frames, wl) : 0;
-  if (!gf) return dwt_inverse_levels(d_q, d_px, d_scratch, W, H, Wa, Ha, wl, lossy, qs, flat_crop, frames, wl, 1, st);
+  if (!gf) {
+    const int sb = l2_sub_batch(Wa, Ha, frames, wl);
+    if (sb >= frames) return dwt_inverse_levels(d_q, d_px, d_scratch, W, H, Wa, Ha, wl, lossy, qs, flat_crop, frames, wl, 1, st);
+    const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl), P = (size_t)W * H;
+    if (wl > 2) { int rc = dwt_inverse_levels(d_q, d_px, d_scratch, W, H, Wa, Ha, wl, lossy, qs, flat_crop, frames, wl, 3, st); if (rc) return rc; }
+    for (int f0 = 0; f0 < frames; f0 += sb) {  // level 2 writes LL1 (evict-last), level 1 reads it while it is still in L2
+      const int n = std::min(sb, frames - f0);
+      int rc = dwt_inverse_levels(d_q + f0 * A, d_px + f0 * P, static_cast<char*>(d_scratch) + f0 * S * 4, W, H, Wa, Ha, wl, lossy, qs,
+                                  flat_crop, n, 2, 1, st);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl), P = (size_t)W * H;
   const int ng = (frames + gf - 1) / gf;
   PCS_CUDA_TRY(cudaEventRecord(aux->ev[0], st));

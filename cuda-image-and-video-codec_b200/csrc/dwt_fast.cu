@@ -209,15 +209,35 @@ template <typename OT> struct V2;
 template <> struct V2<int> { using type = int2; };
 template <> struct V2<float> { using type = float2; };
 
+// Subband / pixel stores are written once and not read again by this transform: streaming (evict-first).
 template <typename OT>
 __device__ __forceinline__ void st4(OT* p, OT a, OT b, OT c, OT d) {
   typename V4<OT>::type t; t.x = a; t.y = b; t.z = c; t.w = d;
-  *reinterpret_cast<typename V4<OT>::type*>(p) = t;
+  __stcs(reinterpret_cast<typename V4<OT>::type*>(p), t);
+}
+// LL planes are read back by the next launch: ask L2 to keep them (evict-last) so that the read is an L2
+// hit instead of a second trip to HBM (126 MB of L2; the host loop sizes sub-batches accordingly).
+__device__ __forceinline__ unsigned long long l2_keep_policy() {
+  unsigned long long pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ unsigned bits(float v) { return __float_as_uint(v); }
+__device__ __forceinline__ unsigned bits(int v) { return (unsigned)v; }
+template <typename T>
+__device__ __forceinline__ void st4_keep(T* p, T a, T b, T c, T d) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(bits(a)), "r"(bits(b)), "r"(bits(c)), "r"(bits(d)),
+               "l"(l2_keep_policy())
+               : "memory");
+}
+template <typename T>
+__device__ __forceinline__ void st2_keep(T* p, T a, T b) {
+  asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(bits(a)), "r"(bits(b)), "l"(l2_keep_policy()) : "memory");
 }
 template <typename OT>
 __device__ __forceinline__ void st2(OT* p, OT a, OT b) {
   typename V2<OT>::type t; t.x = a; t.y = b;
-  *reinterpret_cast<typename V2<OT>::type*>(p) = t;
+  __stcs(reinterpret_cast<typename V2<OT>::type*>(p), t);
 }
 
 // Stores the three (or four) subband rows of one row pair.  NS = samples per lane per row (8 or 4).
@@ -240,13 +260,13 @@ __device__ __forceinline__ void emit_pair(const T (&lo)[NS], const T (&hi)[NS], 
     st4<OT>(row_hi, v[2][0], v[2][1], v[2][2], v[2][3]);
     st4<OT>(row_hi + hw, v[3][0], v[3][1], v[3][2], v[3][3]);
     if (ll_to_out) st4<OT>(row_lo, v[0][0], v[0][1], v[0][2], v[0][3]);
-    else if (ll_dst) st4<T>(ll_dst, lo[0], lo[2], lo[4], lo[6]);
+    else if (ll_dst) st4_keep<T>(ll_dst, lo[0], lo[2], lo[4], lo[6]);
   } else {
     st2<OT>(row_lo + hw, v[1][0], v[1][1]);
     st2<OT>(row_hi, v[2][0], v[2][1]);
     st2<OT>(row_hi + hw, v[3][0], v[3][1]);
     if (ll_to_out) st2<OT>(row_lo, v[0][0], v[0][1]);
-    else if (ll_dst) st2<T>(ll_dst, lo[0], lo[2]);
+    else if (ll_dst) st2_keep<T>(ll_dst, lo[0], lo[2]);
   }
 }
 
@@ -660,12 +680,12 @@ __global__ void __launch_bounds__(128, 3) dwt_inverse_fast_kernel(const FastInvA
       uint2 w;
       w.x = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
       w.y = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
-      *reinterpret_cast<uint2*>(static_cast<unsigned char*>(a.dst) + (size_t)frame * a.dst_fstride + (size_t)y * a.dst_pitch + c0) = w;
+      __stcs(reinterpret_cast<uint2*>(static_cast<unsigned char*>(a.dst) + (size_t)frame * a.dst_fstride + (size_t)y * a.dst_pitch + c0), w);
     } else {
       T* d = static_cast<T*>(a.dst) + (size_t)frame * a.dst_fstride + (size_t)y * a.dst_pitch + c0;
       T4 t0, t1;
       t0.x = v[0]; t0.y = v[1]; t0.z = v[2]; t0.w = v[3]; t1.x = v[4]; t1.y = v[5]; t1.z = v[6]; t1.w = v[7];
-      reinterpret_cast<T4*>(d)[0] = t0; reinterpret_cast<T4*>(d)[1] = t1;
+      st4_keep<T>(d, t0.x, t0.y, t0.z, t0.w); st4_keep<T>(d + 4, t1.x, t1.y, t1.z, t1.w);  // read back by the next finer level
     }
   };
 
