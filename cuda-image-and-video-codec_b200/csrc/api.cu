@@ -355,8 +355,14 @@ int32_t pcs_encode_frames(pcs_ctx* c, const uint8_t* h_px, int32_t nframes, int3
     // the next user of this slot's h_off must not overwrite it before it was read: it was, just above
     return PCS_OK;
   };
+  // A chunk's packed frames can only be copied out once its length is on the host.  Finishing chunk i - lag right
+  // after enqueueing chunk i keeps `lag` chunks of work queued on the GPU while the host waits, and leaves only
+  // `lag` downloads for the end of the call.
+  static const int lag_env = [] { const char* e = std::getenv("PCS_PIPE_LAG"); return e ? std::atoi(e) : 2; }();
+  const int lag = std::max(1, std::min(lag_env, nslots));
+  int finished = 0;
   for (int i = 0; i < nchunks; ++i) {
-    if (i >= nslots) { int rc = finish(i - nslots); if (rc) return rc; }  // frees the slot (same stream: ordered)
+    while (finished <= i - nslots) { int rc = finish(finished++); if (rc) return rc; }  // frees the slot (same stream: ordered)
     Slot s = make_slot(c, i % nslots, sb);
     const int f0 = i * sb, b = std::min(sb, nframes - f0);
     PCS_CUDA_TRY(cudaMemcpyAsync(s.px, h_px + (size_t)f0 * fpx, (size_t)b * fpx, cudaMemcpyHostToDevice, s.st));
@@ -369,8 +375,9 @@ int32_t pcs_encode_frames(pcs_ctx* c, const uint8_t* h_px, int32_t nframes, int3
     if (rc) return rc;
     PCS_CUDA_TRY(cudaMemcpyAsync(s.h_off, s.d_off, (size_t)(b + 1) * sizeof(long long), cudaMemcpyDeviceToHost, s.st));
     PCS_CUDA_TRY(cudaEventRecord(s.ev, s.st));
+    while (finished <= i - lag) { int rc = finish(finished++); if (rc) return rc; }
   }
-  for (int j = std::max(0, nchunks - nslots); j < nchunks; ++j) { int rc = finish(j); if (rc) return rc; }
+  while (finished < nchunks) { int rc = finish(finished++); if (rc) return rc; }
   for (int k = 0; k < nslots; ++k) PCS_CUDA_TRY(cudaStreamSynchronize(c->sstream[k]));
   if (total_words) *total_words = written;
   return PCS_OK;

@@ -1,0 +1,23 @@
+#!/usr/bin/env python
+"""Developer helper (GPU box): host-buffer (pinned) encode/decode times of the bench workload."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "cuda-image-and-video-codec_b200"), os.path.join(ROOT, "tests")]
+import numpy as np, torch
+import bench
+from picsong_b200 import codec
+name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+W, H, wl, lossy, qs, lutname, B, desc = bench.WORKLOADS[name]
+if len(sys.argv) > 2: B = int(sys.argv[2])
+lroot = bench.materialize_luts()
+cd = codec.Codec(codec.Params(W, H, wl, bool(lossy), qs, max_batch=B), codec.load_lut(f"{lroot}/{lutname}/", wl))
+fr = bench.make_frames(W, H, B)
+pin_px = torch.from_numpy(fr).pin_memory(); pin_out = torch.empty_like(pin_px).pin_memory()
+pin_stream = torch.empty(B * cd.max_words, dtype=torch.int16).pin_memory()
+hp, ho, hs = pin_px.numpy(), pin_out.numpy(), pin_stream.numpy().view(np.uint16)
+te, td = [], []
+for i in range(12):
+    t0 = time.perf_counter(); s, lens = cd.encode_frames(hp, 0, hs); t1 = time.perf_counter(); cd.decode_frames(s, lens, ho); t2 = time.perf_counter()
+    if i >= 3: te.append(t1 - t0); td.append(t2 - t1)
+print(json.dumps({"B": B, "enc_ms": 1e3 * float(np.median(te)), "dec_ms": 1e3 * float(np.median(td)), "e2e_mpix_s": W * H * B / 1e6 / float(np.median(te) + np.median(td)),
+                  "lag": os.environ.get("PCS_PIPE_LAG"), "stream_MB": s.nbytes / 1e6}))
