@@ -69,6 +69,28 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this rank to the CPU cores of its GPU's NUMA node BEFORE any pinned host buffer is allocated, so that
+    the buffers the e2e leg copies from/to are local to the GPU's PCIe root (first-touch placement).  Best effort."""
+    try:
+        bdf = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        dom, rest = bdf.split(":", 1)
+        node = int(open(f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def materialize_luts():
     import lut_fixture
     root = tempfile.mkdtemp(prefix="pcs_lut_")
@@ -105,6 +127,7 @@ def run_ours(args):
 
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -220,7 +243,8 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if lossy else "int32", "data": "synthetic",
         "config": {"workload": desc, "frames_per_step_per_gpu": B, "l2": "256 MiB flush write between timed iterations; working set > L2",
-                   "parallelism": f"frame-sharded x{world}" if world > 1 else "single GPU"},
+                   "parallelism": f"frame-sharded x{world}" if world > 1 else "single GPU",
+                   **({"rank0_numa_node": numa} if numa is not None else {})},
         "encode_mpix_s": mpix_step * args.steps / (enc_ms * 1e-3), "decode_mpix_s": mpix_step * args.steps / (dec_ms * 1e-3),
         "e2e": {"value": mpix_step * args.steps / (e2e_ms * 1e-3), "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},
