@@ -6,6 +6,10 @@
 // DecodingEngine.cu:770-859,866-1043) -- minus its per-frame new/delete of stage objects, the
 // memsets, and the host synchronisation after every kernel.  A batch of frames goes through
 // DWT -> BPC -> bit-stream builder as 7 launches on one stream with no host round trip.
+//
+// RGB (CodingEngine.cu:598-630,680-710,764-810; DecodingEngine.cu:738-770): a frame is three
+// colour-transformed component planes, each coded as an independent "frame" with its own probability table.
+// Everything below works on PLANES = frames x components; plane 3f+c is component c of frame f.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +25,10 @@ unsigned long long g_launches = 0;
 
 size_t dwt_scratch_elems(int Wa, int Ha, int wl);
 int dwt_forward(const uint8_t*, void*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t, DwtAux*);
+int dwt_forward_planes(const void*, void*, void*, int, int, int, bool, float, bool, int, cudaStream_t);
+int dwt_inverse_planes(const int32_t*, void*, void*, int, int, int, bool, float, int, cudaStream_t);
+int rgb_forward(const uint8_t*, void*, int, int, int, int, bool, int, cudaStream_t);
+int rgb_inverse(const void*, uint8_t*, int, int, int, int, bool, bool, int, cudaStream_t);
 int dwt_inverse(const int32_t*, uint8_t*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t, DwtAux*);
 int bpc_encode(const void*, bool, uint16_t*, int32_t*, const BpcArgs&, cudaStream_t);
 int bpc_decode(const uint16_t*, const int32_t*, int32_t*, const BpcArgs&, cudaStream_t);
@@ -35,28 +43,28 @@ using namespace pcs;
 
 struct pcs_ctx {
   pcs_params p;
-  int Wa, Ha, ncb;
-  size_t A, scratch_elems, max_words;
+  int Wa, Ha, ncb, ncomp;          // ncomp: planes per frame (1 grey, 3 RGB)
+  size_t A, scratch_elems, max_words, frame_px;  // max_words: per PLANE; frame_px = ncomp * W * H
   std::vector<int32_t> lut;
-  // device: probability tables
-  unsigned long long* d_sigp = nullptr; unsigned* d_sgnp = nullptr; unsigned char* d_refp = nullptr; uint4* d_tab4 = nullptr; int nrows = 0;
-  // device: workspace
-  void* d_scratch = nullptr;       // DWT LL ping-pong, [max_batch][scratch_elems] x 4 bytes
+  uint4* d_tab4 = nullptr; int nrows = 0;  // device: probability rows, [ncomp][nrows]
+  // device: workspace, sized for max_batch frames = max_batch * ncomp planes
+  void* d_scratch = nullptr;       // DWT LL planes, [planes][scratch_elems] x 4 bytes
   void* d_status = nullptr;        // look-back status words
-  uint8_t* d_px = nullptr;         // [max_batch][W*H]
-  int32_t* d_coeff = nullptr;      // [max_batch][A]
-  uint16_t* d_cw = nullptr;        // [max_batch][ncb][4096]
-  int32_t* d_sizes = nullptr;      // [max_batch][ncb]
-  uint16_t* d_stream = nullptr;    // [max_batch * max_words]
-  long long* d_off = nullptr;      // [max_batch + 1]
-  long long* h_off = nullptr;      // pinned, [kSlots][max_batch + 1]
-  // host-buffer pipeline (pcs_encode_frames / pcs_decode_frames): the workspace is cut into kSlots slots of
-  // max_batch / kSlots frames, each with its own stream, so that the H2D copy of one chunk, the kernels of
-  // another and the D2H copy of a third overlap (PCIe is full duplex; copy engines run beside the SMs)
+  uint8_t* d_px = nullptr;         // [max_batch][ncomp][W*H]
+  void* d_tplanes = nullptr;       // RGB only: colour-transformed 32-bit planes [planes][A]
+  int32_t* d_coeff = nullptr;      // [planes][A]
+  uint16_t* d_cw = nullptr;        // [planes][ncb][4096]
+  int32_t* d_sizes = nullptr;      // [planes][ncb]
+  uint16_t* d_stream = nullptr;    // [planes * max_words]
+  long long* d_off = nullptr;      // [planes + 1]
+  long long* h_off = nullptr;      // pinned, [kSlots][planes + 1]
+  // host-buffer pipeline (pcs_encode_frames / pcs_decode_frames): the workspace is cut into kSlots slots,
+  // each with its own stream, so that the H2D copy of one chunk, the kernels of another and the D2H copy of a
+  // third overlap (PCIe is full duplex; copy engines run beside the SMs)
   static constexpr int kSlots = 4;
   cudaStream_t sstream[kSlots] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t sev[kSlots] = {nullptr, nullptr, nullptr, nullptr};
-  long long* d_soff = nullptr;     // [kSlots][max_batch + 1]
+  long long* d_soff = nullptr;     // [kSlots][planes + 1]
   void* d_sstatus = nullptr;       // [kSlots] look-back status areas
   size_t status_bytes = 0;
   DwtAux* aux = nullptr;           // auxiliary streams of the batched DWT calls (device-buffer entry points)
@@ -73,70 +81,111 @@ int fail(pcs_ctx* c, int code, const char* msg) {
   return code;
 }
 
-BpcArgs bpc_args(const pcs_ctx* c, int batch) {
+BpcArgs bpc_args(const pcs_ctx* c, int frames, int comp) {
   BpcArgs a{};
   a.Wa = c->Wa; a.Ha = c->Ha; a.nbx = c->Wa / kCB; a.ncb = c->ncb; a.wl = c->p.wavelet_levels;
   a.nBp = c->p.lut_header[0]; a.nSub = c->p.lut_header[1]; a.nrows = c->nrows; a.prec = c->p.lut_header[5];
-  a.total_cb = c->ncb * batch; a.A = (long long)c->A;
-  a.sigp = c->d_sigp; a.sgnp = c->d_sgnp; a.refp = c->d_refp; a.tab4 = c->d_tab4;
+  a.total_cb = c->ncb * frames; a.A = (long long)c->A;
+  a.pstep = c->ncomp; a.pfirst = comp;
+  a.tab4 = c->d_tab4 + (size_t)comp * c->nrows;
   return a;
 }
 
-BsbArgs bsb_args(const pcs_ctx* c, int batch, int first) {
+// `planes` consecutive planes starting at global plane index `first_plane`
+BsbArgs bsb_args(const pcs_ctx* c, int planes, int first_plane) {
   BsbArgs a{};
-  a.ncb = c->ncb; a.batch = batch; a.first_frame_index = first;
+  a.ncb = c->ncb; a.batch = planes; a.first_frame_index = first_plane;
+  // stills: component i is coded with iter = i, video: every component of frame f with iter = f
+  // (CodingEngine.cu:620,700 vs :790,902) -> the three planes of video frame 0 all carry the header
+  a.hdr_count = (c->ncomp == 3 && c->p.frames > 0) ? 3 : 1;
   uint16_t h[9];
   pcs_header_pack(&c->p, h);
   for (int i = 0; i < 9; ++i) a.hdr[i] = h[i];
   return a;
 }
 
-// Packs the flat int32 table (ref | sig | sign sections, row = (lvl*nSub+sb)*nBp + bp) into per-row
-// registers-friendly words.  Rows past the table keep the reference's unguarded flat indexing
-// (BPCEngine.cu:329-350: MSB >= nBp walks into the next group / section); beyond the table -> 0.
+// Packs the flat int32 tables (ref | sig | sign sections, row = (lvl*nSub+sb)*nBp + bp) of every component
+// into 16-byte rows: bytes 0..8 significance contexts, 9 refinement, 12..15 sign contexts.  Rows past the
+// table keep the reference's unguarded flat indexing (BPCEngine.cu:329-350: MSB >= nBp walks into the next
+// group / section); beyond the table -> 0.
 int build_prob_tables(pcs_ctx* c) {
   const int32_t* h = c->p.lut_header;
   const int nBp = h[0], nSub = h[1], cR = h[2], cG = h[3], cS = h[4], wl = c->p.wavelet_levels;
   if (cR != 1 || cS < 1 || cS > 9 || cG < 1 || cG > 4 || nBp < 1 || nBp > 32 || nSub != 3 || h[5] < 1 || h[5] > 15)
     return PCS_E_LUT_RANGE;
   const int R = (nSub * wl + 1) * nBp * cR, S = (nSub * wl + 1) * nBp * cS;
-  const int n = (int)c->lut.size();
-  if (n < R + S + (nSub * wl + 1) * nBp * cG) return PCS_E_LUT;
+  const int n = R + S + (nSub * wl + 1) * nBp * cG;  // entries per component
+  if ((long long)c->lut.size() < (long long)n * c->ncomp) return PCS_E_LUT;
   const int nrows = (nSub * wl + 1) * nBp + 32;
-  std::vector<unsigned long long> sig(nrows, 0);
-  std::vector<unsigned> sgn(nrows, 0);
-  std::vector<unsigned char> ref(nrows, 0);
-  std::vector<uint4> tab4(nrows, make_uint4(0, 0, 0, 0));
-  auto at = [&](long long i) -> int { return (i >= 0 && i < n) ? c->lut[(size_t)i] : 0; };
-  for (int r = 0; r < nrows; ++r) {
-    for (int k = 0; k < 9; ++k) {
-      const int v = k < cS ? at((long long)R + (long long)r * cS + k) : 0;
+  std::vector<uint4> tab4((size_t)nrows * c->ncomp, make_uint4(0, 0, 0, 0));
+  for (int comp = 0; comp < c->ncomp; ++comp) {
+    const int32_t* lut = c->lut.data() + (size_t)comp * n;
+    auto at = [&](long long i) -> int { return (i >= 0 && i < n) ? lut[(size_t)i] : 0; };
+    for (int r = 0; r < nrows; ++r) {
+      uint4& t = tab4[(size_t)comp * nrows + r];
+      for (int k = 0; k < 9; ++k) {
+        const int v = k < cS ? at((long long)R + (long long)r * cS + k) : 0;
+        if (v < 0 || v > 127) return PCS_E_LUT_RANGE;
+        if (k < 4) t.x |= (unsigned)v << (8 * k);
+        else if (k < 8) t.y |= (unsigned)v << (8 * (k - 4));
+        else t.z |= (unsigned)v;
+      }
+      for (int k = 0; k < 4; ++k) {
+        const int v = k < cG ? at((long long)R + S + (long long)r * cG + k) : 0;
+        if (v < 0 || v > 127) return PCS_E_LUT_RANGE;
+        t.w |= (unsigned)v << (8 * k);
+      }
+      const int v = at((long long)r * cR);
       if (v < 0 || v > 127) return PCS_E_LUT_RANGE;
-      sig[r] |= (unsigned long long)v << (7 * k);
-      if (k < 4) tab4[r].x |= (unsigned)v << (8 * k);
-      else if (k < 8) tab4[r].y |= (unsigned)v << (8 * (k - 4));
-      else tab4[r].z |= (unsigned)v;
+      t.z |= (unsigned)v << 8;
     }
-    for (int k = 0; k < 4; ++k) {
-      const int v = k < cG ? at((long long)R + S + (long long)r * cG + k) : 0;
-      if (v < 0 || v > 127) return PCS_E_LUT_RANGE;
-      sgn[r] |= (unsigned)v << (7 * k);
-      tab4[r].w |= (unsigned)v << (8 * k);
-    }
-    const int v = at((long long)r * cR);
-    if (v < 0 || v > 127) return PCS_E_LUT_RANGE;
-    ref[r] = (unsigned char)v;
-    tab4[r].z |= (unsigned)v << 8;
   }
   c->nrows = nrows;
-  PCS_CUDA_TRY(cudaMalloc(&c->d_sigp, nrows * sizeof(unsigned long long)));
-  PCS_CUDA_TRY(cudaMalloc(&c->d_sgnp, nrows * sizeof(unsigned)));
-  PCS_CUDA_TRY(cudaMalloc(&c->d_refp, nrows));
-  PCS_CUDA_TRY(cudaMalloc(&c->d_tab4, nrows * sizeof(uint4)));
-  PCS_CUDA_TRY(cudaMemcpy(c->d_tab4, tab4.data(), nrows * sizeof(uint4), cudaMemcpyHostToDevice));
-  PCS_CUDA_TRY(cudaMemcpy(c->d_sigp, sig.data(), nrows * sizeof(unsigned long long), cudaMemcpyHostToDevice));
-  PCS_CUDA_TRY(cudaMemcpy(c->d_sgnp, sgn.data(), nrows * sizeof(unsigned), cudaMemcpyHostToDevice));
-  PCS_CUDA_TRY(cudaMemcpy(c->d_refp, ref.data(), nrows, cudaMemcpyHostToDevice));
+  PCS_CUDA_TRY(cudaMalloc(&c->d_tab4, tab4.size() * sizeof(uint4)));
+  PCS_CUDA_TRY(cudaMemcpy(c->d_tab4, tab4.data(), tab4.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+  return PCS_OK;
+}
+
+// ---- the stage chain on explicit workspace pointers (used by the device entry points and by the slots) ----
+struct Ws {
+  void* scratch; void* status; void* tplanes; int32_t* coeff; uint16_t* cw; int32_t* sizes;
+};
+
+int run_dwt_forward(pcs_ctx* c, const Ws& w, const uint8_t* d_px, void* d_coeff, bool out_int, int frames, cudaStream_t st, DwtAux* aux) {
+  const pcs_params& p = c->p;
+  if (c->ncomp == 1)
+    return dwt_forward(d_px, d_coeff, w.scratch, p.width, p.height, c->Wa, c->Ha, p.wavelet_levels, p.lossy != 0, p.quant_size, out_int,
+                       frames, st, aux);
+  int rc = rgb_forward(d_px, w.tplanes, p.width, p.height, c->Wa, c->Ha, p.lossy != 0, frames, st);
+  if (rc) return rc;
+  return dwt_forward_planes(w.tplanes, d_coeff, w.scratch, c->Wa, c->Ha, p.wavelet_levels, p.lossy != 0, p.quant_size, out_int,
+                            frames * 3, st);
+}
+
+int run_dwt_inverse(pcs_ctx* c, const Ws& w, const int32_t* d_q, uint8_t* d_px, int frames, cudaStream_t st, DwtAux* aux) {
+  const pcs_params& p = c->p;
+  const bool flat = (p.flags & PCS_F_REF_FLAT_CROP) != 0;
+  if (c->ncomp == 1)
+    return dwt_inverse(d_q, d_px, w.scratch, p.width, p.height, c->Wa, c->Ha, p.wavelet_levels, p.lossy != 0, p.quant_size, flat, frames,
+                       st, aux);
+  int rc = dwt_inverse_planes(d_q, w.tplanes, w.scratch, c->Wa, c->Ha, p.wavelet_levels, p.lossy != 0, p.quant_size, frames * 3, st);
+  if (rc) return rc;
+  return rgb_inverse(w.tplanes, d_px, p.width, p.height, c->Wa, c->Ha, p.lossy != 0, flat, frames, st);
+}
+
+int run_bpc_encode(pcs_ctx* c, const void* d_coeff, bool is_float, uint16_t* d_cw, int32_t* d_sizes, int frames, cudaStream_t st) {
+  for (int comp = 0; comp < c->ncomp; ++comp) {  // one launch per component: each has its own probability table
+    int rc = bpc_encode(d_coeff, is_float, d_cw, d_sizes, bpc_args(c, frames, comp), st);
+    if (rc) return rc;
+  }
+  return PCS_OK;
+}
+
+int run_bpc_decode(pcs_ctx* c, const uint16_t* d_cw, const int32_t* d_sizes, int32_t* d_q, int frames, cudaStream_t st) {
+  for (int comp = 0; comp < c->ncomp; ++comp) {
+    int rc = bpc_decode(d_cw, d_sizes, d_q, bpc_args(c, frames, comp), st);
+    if (rc) return rc;
+  }
   return PCS_OK;
 }
 
@@ -154,8 +203,10 @@ int32_t pcs_create(const pcs_params* params, pcs_ctx** out) {
       p.coding_passes > 3 || p.k_factor < 0 || p.k_factor > 65.535f || p.max_batch < 1)
     return PCS_E_ARG;
   if (p.lossy && !(p.quant_size > 0)) return PCS_E_ARG;
-  if (p.coding_passes != 2 || p.k_factor != 0 || p.is_rgb || p.is_signed || p.components != 1 || p.bit_depth != 8)
-    return PCS_E_UNSUPPORTED;
+  if (p.coding_passes != 2 || p.k_factor != 0 || p.is_signed || p.bit_depth != 8) return PCS_E_UNSUPPORTED;
+  // RGB: `-isRGB 1` with the default `-components 1` is what the reference's own examples use (README.md:105-115);
+  // `-components 3` is accepted as well.  Grey: one component.
+  if (p.is_rgb ? (p.components != 1 && p.components != 3) : p.components != 1) return PCS_E_UNSUPPORTED;
   if (!p.lut || p.lut_len <= 0) return PCS_E_LUT;
   int Wa, Ha;
   pcs_adapted_dims(p.width, p.height, &Wa, &Ha);
@@ -168,28 +219,31 @@ int32_t pcs_create(const pcs_params* params, pcs_ctx** out) {
   c->p = p;
   c->lut.assign(p.lut, p.lut + p.lut_len);
   c->p.lut = c->lut.data();
+  c->ncomp = p.is_rgb ? 3 : 1;
   c->Wa = Wa; c->Ha = Ha; c->A = (size_t)Wa * Ha; c->ncb = (Wa / kCB) * (Ha / kCB);
   c->max_words = c->A + c->ncb + 10;
+  c->frame_px = (size_t)c->ncomp * p.width * p.height;
   c->scratch_elems = dwt_scratch_elems(Wa, Ha, p.wavelet_levels);
   const char* t = std::getenv("PCS_STAGE_TIMING");
   c->timing = t && t[0] == '1';
   int rc = build_prob_tables(c);
   if (rc != PCS_OK) { pcs_destroy(c); return rc; }
-  const size_t B = (size_t)p.max_batch;
+  const size_t B = (size_t)p.max_batch, PL = B * c->ncomp;  // frames, planes
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes ? bytes : 16); };
-  alloc(&c->d_scratch, B * (c->scratch_elems + 4) * 4);
-  alloc(&c->d_status, bsb_status_bytes(c->ncb, p.max_batch));
-  alloc((void**)&c->d_px, B * (size_t)p.width * p.height + 16);
-  alloc((void**)&c->d_coeff, B * c->A * 4);
-  alloc((void**)&c->d_cw, B * c->A * 2);
-  alloc((void**)&c->d_sizes, B * c->ncb * 4);
-  alloc((void**)&c->d_stream, B * c->max_words * 2);
-  alloc((void**)&c->d_off, (B + 1) * sizeof(long long));
-  c->status_bytes = (bsb_status_bytes(c->ncb, p.max_batch) + 255) / 256 * 256;
+  alloc(&c->d_scratch, PL * (c->scratch_elems + 4) * 4);
+  alloc(&c->d_status, bsb_status_bytes(c->ncb, (int)PL));
+  alloc((void**)&c->d_px, B * c->frame_px + 16);
+  if (c->ncomp == 3) alloc(&c->d_tplanes, PL * c->A * 4);
+  alloc((void**)&c->d_coeff, PL * c->A * 4);
+  alloc((void**)&c->d_cw, PL * c->A * 2);
+  alloc((void**)&c->d_sizes, PL * c->ncb * 4);
+  alloc((void**)&c->d_stream, PL * c->max_words * 2);
+  alloc((void**)&c->d_off, (PL + 1) * sizeof(long long));
+  c->status_bytes = (bsb_status_bytes(c->ncb, (int)PL) + 255) / 256 * 256;
   alloc(&c->d_sstatus, pcs_ctx::kSlots * c->status_bytes);
-  alloc((void**)&c->d_soff, pcs_ctx::kSlots * (B + 1) * sizeof(long long));
-  if (e == cudaSuccess) e = cudaHostAlloc((void**)&c->h_off, pcs_ctx::kSlots * (B + 1) * sizeof(long long), cudaHostAllocDefault);
+  alloc((void**)&c->d_soff, pcs_ctx::kSlots * (PL + 1) * sizeof(long long));
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&c->h_off, pcs_ctx::kSlots * (PL + 1) * sizeof(long long), cudaHostAllocDefault);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) { c->aux = dwt_aux_create(); if (!c->aux) e = cudaErrorMemoryAllocation; }
   for (int i = 0; i < pcs_ctx::kSlots && e == cudaSuccess; ++i) {
@@ -204,8 +258,8 @@ int32_t pcs_create(const pcs_params* params, pcs_ctx** out) {
 
 void pcs_destroy(pcs_ctx* c) {
   if (!c) return;
-  cudaFree(c->d_sigp); cudaFree(c->d_sgnp); cudaFree(c->d_refp); cudaFree(c->d_tab4);
-  cudaFree(c->d_scratch); cudaFree(c->d_status); cudaFree(c->d_px); cudaFree(c->d_coeff); cudaFree(c->d_cw);
+  cudaFree(c->d_tab4);
+  cudaFree(c->d_scratch); cudaFree(c->d_status); cudaFree(c->d_px); cudaFree(c->d_tplanes); cudaFree(c->d_coeff); cudaFree(c->d_cw);
   cudaFree(c->d_sizes); cudaFree(c->d_stream); cudaFree(c->d_off);
   if (c->h_off) cudaFreeHost(c->h_off);
   cudaFree(c->d_sstatus); cudaFree(c->d_soff);
@@ -220,49 +274,51 @@ void pcs_destroy(pcs_ctx* c) {
 const char* pcs_last_error(const pcs_ctx* c) { return c ? c->err.c_str() : "no context"; }
 size_t pcs_frame_pixels(const pcs_ctx* c) { return c->A; }
 int32_t pcs_frame_codeblocks(const pcs_ctx* c) { return c->ncb; }
-size_t pcs_frame_max_stream_words(const pcs_ctx* c) { return c->max_words; }
+size_t pcs_frame_max_stream_words(const pcs_ctx* c) { return c->max_words * c->ncomp; }
+int32_t pcs_frame_planes(const pcs_ctx* c) { return c->ncomp; }
 uint64_t pcs_kernel_launch_count(void) { return g_launches; }
 
 #define CHECK_BATCH(c, batch) \
   if (!(c)) return PCS_E_ARG; \
   if ((batch) < 1 || (batch) > (c)->p.max_batch) return fail((c), PCS_E_BATCH, "batch exceeds max_batch")
+#define FULL_WS(c) Ws{(c)->d_scratch, (c)->d_status, (c)->d_tplanes, (c)->d_coeff, (c)->d_cw, (c)->d_sizes}
 
 int32_t pcs_dwt_forward(pcs_ctx* c, const uint8_t* d_px, void* d_coeff, int32_t trunc, int32_t batch, void* st) {
   CHECK_BATCH(c, batch);
-  return dwt_forward(d_px, d_coeff, c->d_scratch, c->p.width, c->p.height, c->Wa, c->Ha, c->p.wavelet_levels, c->p.lossy != 0,
-                     c->p.quant_size, trunc != 0, batch, (cudaStream_t)st, c->aux);
+  return run_dwt_forward(c, FULL_WS(c), d_px, d_coeff, trunc != 0, batch, (cudaStream_t)st, c->aux);
 }
 
 int32_t pcs_dwt_inverse(pcs_ctx* c, const int32_t* d_q, uint8_t* d_px, int32_t batch, void* st) {
   CHECK_BATCH(c, batch);
-  return dwt_inverse(d_q, d_px, c->d_scratch, c->p.width, c->p.height, c->Wa, c->Ha, c->p.wavelet_levels, c->p.lossy != 0,
-                     c->p.quant_size, (c->p.flags & PCS_F_REF_FLAT_CROP) != 0, batch, (cudaStream_t)st, c->aux);
+  return run_dwt_inverse(c, FULL_WS(c), d_q, d_px, batch, (cudaStream_t)st, c->aux);
 }
 
 int32_t pcs_bpc_encode(pcs_ctx* c, const void* d_coeff, int32_t is_float, uint16_t* d_cw, int32_t* d_sizes, int32_t batch, void* st) {
   CHECK_BATCH(c, batch);
-  return bpc_encode(d_coeff, is_float != 0, d_cw, d_sizes, bpc_args(c, batch), (cudaStream_t)st);
+  return run_bpc_encode(c, d_coeff, is_float != 0, d_cw, d_sizes, batch, (cudaStream_t)st);
 }
 
 int32_t pcs_bpc_decode(pcs_ctx* c, const uint16_t* d_cw, const int32_t* d_sizes, int32_t* d_q, int32_t batch, void* st) {
   CHECK_BATCH(c, batch);
-  return bpc_decode(d_cw, d_sizes, d_q, bpc_args(c, batch), (cudaStream_t)st);
+  return run_bpc_decode(c, d_cw, d_sizes, d_q, batch, (cudaStream_t)st);
 }
 
 int32_t pcs_bsb_pack(pcs_ctx* c, const uint16_t* d_cw, const int32_t* d_sizes, int32_t first, uint16_t* d_out, int64_t* d_off,
                      int32_t batch, void* st) {
   CHECK_BATCH(c, batch);
-  return bsb_pack(d_cw, d_sizes, d_out, reinterpret_cast<long long*>(d_off), c->d_status, bsb_args(c, batch, first), (cudaStream_t)st);
+  return bsb_pack(d_cw, d_sizes, d_out, reinterpret_cast<long long*>(d_off), c->d_status, bsb_args(c, batch * c->ncomp, first * c->ncomp),
+                  (cudaStream_t)st);
 }
 
 int32_t pcs_bsb_unpack(pcs_ctx* c, const uint16_t* d_in, const int64_t* d_off, uint16_t* d_cw, int32_t* d_sizes, int32_t batch, void* st) {
   CHECK_BATCH(c, batch);
-  return bsb_unpack(d_in, reinterpret_cast<const long long*>(d_off), d_cw, d_sizes, c->d_status, bsb_args(c, batch, 1), (cudaStream_t)st);
+  return bsb_unpack(d_in, reinterpret_cast<const long long*>(d_off), d_cw, d_sizes, c->d_status, bsb_args(c, batch * c->ncomp, 1),
+                    (cudaStream_t)st);
 }
 
 int32_t pcs_export_ref_codestream(pcs_ctx* c, const uint16_t* d_cw, const int32_t* d_sizes, int32_t* d_ref, int32_t batch, void* st) {
   CHECK_BATCH(c, batch);
-  return export_ref_codestream(d_cw, d_sizes, d_ref, (long long)c->A * batch, (cudaStream_t)st);
+  return export_ref_codestream(d_cw, d_sizes, d_ref, (long long)c->A * batch * c->ncomp, (cudaStream_t)st);
 }
 
 int32_t pcs_encode_device(pcs_ctx* c, const uint8_t* d_px, int32_t batch, int32_t first, uint16_t* d_stream, int64_t* d_off, void* stv) {
@@ -306,21 +362,21 @@ namespace {
 
 // One slot of the workspace: frames [k*sb, (k+1)*sb) of every per-frame buffer.
 struct Slot {
-  void* scratch; void* status; uint8_t* px; int32_t* coeff; uint16_t* cw; int32_t* sizes; uint16_t* stream;
-  long long* d_off; long long* h_off; cudaStream_t st; cudaEvent_t ev;
+  Ws w; uint8_t* px; uint16_t* stream; long long* d_off; long long* h_off; cudaStream_t st; cudaEvent_t ev;
 };
 Slot make_slot(pcs_ctx* c, int k, int sb) {
-  const size_t f0 = (size_t)k * sb, B1 = (size_t)c->p.max_batch + 1;
+  const size_t f0 = (size_t)k * sb, p0 = f0 * c->ncomp, PL1 = (size_t)c->p.max_batch * c->ncomp + 1;
   Slot s;
-  s.scratch = static_cast<char*>(c->d_scratch) + f0 * c->scratch_elems * 4;
-  s.status = static_cast<char*>(c->d_sstatus) + (size_t)k * c->status_bytes;
-  s.px = c->d_px + f0 * (size_t)c->p.width * c->p.height;
-  s.coeff = c->d_coeff + f0 * c->A;
-  s.cw = c->d_cw + f0 * c->A;
-  s.sizes = c->d_sizes + f0 * c->ncb;
-  s.stream = c->d_stream + f0 * c->max_words;
-  s.d_off = c->d_soff + (size_t)k * B1;
-  s.h_off = c->h_off + (size_t)k * B1;
+  s.w.scratch = static_cast<char*>(c->d_scratch) + p0 * c->scratch_elems * 4;
+  s.w.status = static_cast<char*>(c->d_sstatus) + (size_t)k * c->status_bytes;
+  s.w.tplanes = c->d_tplanes ? static_cast<char*>(c->d_tplanes) + p0 * c->A * 4 : nullptr;
+  s.w.coeff = c->d_coeff + p0 * c->A;
+  s.w.cw = c->d_cw + p0 * c->A;
+  s.w.sizes = c->d_sizes + p0 * c->ncb;
+  s.px = c->d_px + f0 * c->frame_px;
+  s.stream = c->d_stream + p0 * c->max_words;
+  s.d_off = c->d_soff + (size_t)k * PL1;
+  s.h_off = c->h_off + (size_t)k * PL1;
   s.st = c->sstream[k]; s.ev = c->sev[k];
   return s;
 }
@@ -334,25 +390,27 @@ int slots_for(const pcs_ctx* c, int* sb) {
 
 }  // namespace
 
+// h_frame_len receives one length per PLANE (nframes entries for grey, 3 * nframes for RGB: the values the
+// reference appends to `<out>_SIZE`, IO/IOManager.ipp:176-189).
 int32_t pcs_encode_frames(pcs_ctx* c, const uint8_t* h_px, int32_t nframes, int32_t first, uint16_t* h_stream, size_t cap,
                           int32_t* h_len, size_t* total_words) {
   if (!c || !h_px || !h_stream || nframes < 1) return PCS_E_ARG;
-  const size_t fpx = (size_t)c->p.width * c->p.height;
+  const size_t fpx = c->frame_px;
+  const int nc = c->ncomp;
   int sb;
   const int nslots = slots_for(c, &sb);
   const int nchunks = (nframes + sb - 1) / sb;
   size_t written = 0;
-  // second half of a chunk's work: its frame offsets are on the host -> copy its packed frames out
+  // second half of a chunk's work: its plane offsets are on the host -> copy its packed planes out
   auto finish = [&](int j) -> int {
     Slot s = make_slot(c, j % nslots, sb);
     const int f0 = j * sb, b = std::min(sb, nframes - f0);
     PCS_CUDA_TRY(cudaEventSynchronize(s.ev));
-    const size_t words = (size_t)s.h_off[b];
+    const size_t words = (size_t)s.h_off[b * nc];
     if (written + words > cap) return fail(c, PCS_E_NOMEM, "output capacity too small");
     PCS_CUDA_TRY(cudaMemcpyAsync(h_stream + written, s.stream, words * 2, cudaMemcpyDeviceToHost, s.st));
-    if (h_len) for (int f = 0; f < b; ++f) h_len[f0 + f] = (int32_t)(s.h_off[f + 1] - s.h_off[f]);
+    if (h_len) for (int f = 0; f < b * nc; ++f) h_len[(size_t)f0 * nc + f] = (int32_t)(s.h_off[f + 1] - s.h_off[f]);
     written += words;
-    // the next user of this slot's h_off must not overwrite it before it was read: it was, just above
     return PCS_OK;
   };
   // A chunk's packed frames can only be copied out once its length is on the host.  Finishing chunk i - lag right
@@ -366,16 +424,15 @@ int32_t pcs_encode_frames(pcs_ctx* c, const uint8_t* h_px, int32_t nframes, int3
     Slot s = make_slot(c, i % nslots, sb);
     const int f0 = i * sb, b = std::min(sb, nframes - f0);
     PCS_CUDA_TRY(cudaMemcpyAsync(s.px, h_px + (size_t)f0 * fpx, (size_t)b * fpx, cudaMemcpyHostToDevice, s.st));
-    int rc = dwt_forward(s.px, s.coeff, s.scratch, c->p.width, c->p.height, c->Wa, c->Ha, c->p.wavelet_levels, c->p.lossy != 0,
-                         c->p.quant_size, true, b, s.st, nullptr);
+    int rc = run_dwt_forward(c, s.w, s.px, s.w.coeff, true, b, s.st, nullptr);
     if (rc) return rc;
-    rc = bpc_encode(s.coeff, false, s.cw, s.sizes, bpc_args(c, b), s.st);
+    rc = run_bpc_encode(c, s.w.coeff, false, s.w.cw, s.w.sizes, b, s.st);
     if (rc) return rc;
-    rc = bsb_pack(s.cw, s.sizes, s.stream, s.d_off, s.status, bsb_args(c, b, first + f0), s.st);
+    rc = bsb_pack(s.w.cw, s.w.sizes, s.stream, s.d_off, s.w.status, bsb_args(c, b * nc, (first + f0) * nc), s.st);
     if (rc) return rc;
-    PCS_CUDA_TRY(cudaMemcpyAsync(s.h_off, s.d_off, (size_t)(b + 1) * sizeof(long long), cudaMemcpyDeviceToHost, s.st));
+    PCS_CUDA_TRY(cudaMemcpyAsync(s.h_off, s.d_off, (size_t)(b * nc + 1) * sizeof(long long), cudaMemcpyDeviceToHost, s.st));
     PCS_CUDA_TRY(cudaEventRecord(s.ev, s.st));
-    while (finished <= i - lag) { int rc = finish(finished++); if (rc) return rc; }
+    while (finished <= i - lag) { int rc2 = finish(finished++); if (rc2) return rc2; }
   }
   while (finished < nchunks) { int rc = finish(finished++); if (rc) return rc; }
   for (int k = 0; k < nslots; ++k) PCS_CUDA_TRY(cudaStreamSynchronize(c->sstream[k]));
@@ -385,7 +442,8 @@ int32_t pcs_encode_frames(pcs_ctx* c, const uint8_t* h_px, int32_t nframes, int3
 
 int32_t pcs_decode_frames(pcs_ctx* c, const uint16_t* h_stream, const int32_t* h_len, int32_t nframes, uint8_t* h_px) {
   if (!c || !h_stream || !h_len || !h_px || nframes < 1) return PCS_E_ARG;
-  const size_t fpx = (size_t)c->p.width * c->p.height;
+  const size_t fpx = c->frame_px;
+  const int nc = c->ncomp;
   int sb;
   const int nslots = slots_for(c, &sb);
   const int nchunks = (nframes + sb - 1) / sb;
@@ -395,21 +453,20 @@ int32_t pcs_decode_frames(pcs_ctx* c, const uint16_t* h_stream, const int32_t* h
     const int f0 = i * sb, b = std::min(sb, nframes - f0);
     if (i >= nslots) PCS_CUDA_TRY(cudaEventSynchronize(s.ev));  // the slot's pinned offsets have been uploaded
     long long off = 0;
-    for (int f = 0; f < b; ++f) {
-      const int len = h_len[f0 + f];
+    for (int f = 0; f < b * nc; ++f) {
+      const int len = h_len[(size_t)f0 * nc + f];
       if (len < 2 * c->ncb + 10 || (size_t)len > c->max_words) return fail(c, PCS_E_STREAM, "frame length out of range");
       s.h_off[f] = off; off += len;
     }
-    s.h_off[b] = off;
+    s.h_off[b * nc] = off;
     PCS_CUDA_TRY(cudaMemcpyAsync(s.stream, h_stream + consumed, (size_t)off * 2, cudaMemcpyHostToDevice, s.st));
-    PCS_CUDA_TRY(cudaMemcpyAsync(s.d_off, s.h_off, (size_t)(b + 1) * sizeof(long long), cudaMemcpyHostToDevice, s.st));
+    PCS_CUDA_TRY(cudaMemcpyAsync(s.d_off, s.h_off, (size_t)(b * nc + 1) * sizeof(long long), cudaMemcpyHostToDevice, s.st));
     PCS_CUDA_TRY(cudaEventRecord(s.ev, s.st));
-    int rc = bsb_unpack(s.stream, s.d_off, s.cw, s.sizes, s.status, bsb_args(c, b, 1), s.st);
+    int rc = bsb_unpack(s.stream, s.d_off, s.w.cw, s.w.sizes, s.w.status, bsb_args(c, b * nc, 1), s.st);
     if (rc) return rc;
-    rc = bpc_decode(s.cw, s.sizes, s.coeff, bpc_args(c, b), s.st);
+    rc = run_bpc_decode(c, s.w.cw, s.w.sizes, s.w.coeff, b, s.st);
     if (rc) return rc;
-    rc = dwt_inverse(s.coeff, s.px, s.scratch, c->p.width, c->p.height, c->Wa, c->Ha, c->p.wavelet_levels, c->p.lossy != 0,
-                     c->p.quant_size, (c->p.flags & PCS_F_REF_FLAT_CROP) != 0, b, s.st, nullptr);
+    rc = run_dwt_inverse(c, s.w, s.w.coeff, s.px, b, s.st, nullptr);
     if (rc) return rc;
     PCS_CUDA_TRY(cudaMemcpyAsync(h_px + (size_t)f0 * fpx, s.px, (size_t)b * fpx, cudaMemcpyDeviceToHost, s.st));
     consumed += (size_t)off;

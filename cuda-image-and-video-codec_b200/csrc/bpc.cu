@@ -67,49 +67,6 @@ __device__ __forceinline__ int lane_group(int X, int Y, const BpcArgs& p) {
   return p.wl * p.nSub;
 }
 
-struct Probs { u64 sig; unsigned sgn, ref; };
-__device__ __forceinline__ Probs load_probs(const BpcArgs& p, int row) {
-  Probs r;
-  const bool ok = row >= 0 && row < p.nrows;
-  r.sig = ok ? __ldg(p.sigp + row) : 0ull;
-  r.sgn = ok ? __ldg(p.sgnp + row) : 0u;
-  r.ref = ok ? (unsigned)__ldg(p.refp + row) : 0u;
-  return r;
-}
-
-// Per-lane interval coder + per-warp codeword counter (BPCEngine.cu:371-442).
-struct Coder {
-  unsigned lower, size, slot, count, lt, prec;
-  __device__ __forceinline__ void init(int lane, int prec_) { lower = 0; size = 0; slot = 0; count = 0; lt = (1u << lane) - 1u; prec = prec_; }
-  // lanes in `need` restart and reserve slots in ascending lane order; returns whether this lane did
-  __device__ __forceinline__ bool reserve(bool need) {
-    const unsigned m = __ballot_sync(kFull, need);
-    if (m) {
-      if (need) { slot = 1u + min(count + __popc(m & lt), 4094u); lower = 0; size = 0xFFFFu; }
-      count = min(count + __popc(m), 4095u);
-    }
-    return need;
-  }
-  __device__ __forceinline__ void encode(bool act, unsigned b, unsigned p, unsigned short* out) {
-    reserve(act && size == 0);
-    if (act) {
-      const unsigned t = ((size * p) >> prec) + b;
-      if (b) { size -= t; lower += t; } else { size = t; }
-      if (size == 0) out[slot] = (unsigned short)lower;
-    }
-  }
-  __device__ __forceinline__ unsigned decode(bool act, unsigned p, unsigned& code, const unsigned short* in) {
-    if (reserve(act && size == 0)) code = in[slot];
-    unsigned b = 0;
-    if (act) {
-      const unsigned t = ((size * p) >> prec) + 1u;
-      const unsigned lim = lower + t;
-      if (code >= lim) { b = 1; size -= t; lower = lim; } else { size = t - 1u; }
-    }
-    return b;
-  }
-};
-
 template <typename T> __device__ __forceinline__ void load2(const T* p, int& a, int& b);
 template <> __device__ __forceinline__ void load2<int>(const int* p, int& a, int& b) {
   const int2 v = __ldg(reinterpret_cast<const int2*>(p)); a = v.x; b = v.y;
@@ -119,9 +76,6 @@ template <> __device__ __forceinline__ void load2<float>(const float* p, int& a,
   a = __float2int_rz(v.x); b = __float2int_rz(v.y);  // (int)c, BPCEngine.cu:49,55
 }
 __device__ __forceinline__ unsigned umag(int v) { return v < 0 ? 0u - (unsigned)v : (unsigned)v; }
-
-__device__ __forceinline__ unsigned prob_sig(u64 pack, unsigned ctx) { return (unsigned)(pack >> (7u * ctx)) & 127u; }
-__device__ __forceinline__ unsigned prob_sgn(unsigned pack, unsigned idx) { return (pack >> (7u * idx)) & 127u; }
 
 // ---------------------------------------------------------------------------------------------
 // encoder
@@ -251,10 +205,11 @@ __global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* 
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int w = blockIdx.x * (blockDim.x >> 5) + wib;
   if (w >= p.total_cb) return;
-  const int frame = w / p.ncb, cb = w - frame * p.ncb;
+  const int frame = (w / p.ncb) * p.pstep + p.pfirst, cb = w % p.ncb;
   const int bx = cb % p.nbx, by = cb / p.nbx;
   const T* src = coeff + (size_t)frame * p.A + (size_t)(by * kCB) * p.Wa + bx * kCB + 2 * lane;
-  unsigned short* out = cw + (size_t)w * kCBWords;
+  const size_t blk = (size_t)frame * p.ncb + cb;  // index of this block in the codeword / size arrays
+  unsigned short* out = cw + blk * kCBWords;
   unsigned (*pl)[32] = s_pl[wib];
 
   // pass 0: MSB of the block, sign masks (BPCEngine.cu:41-63,176-192), bit-plane transposition
@@ -280,7 +235,7 @@ __global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* 
   ormag = __reduce_or_sync(kFull, ormag);
   const int MSB = ormag ? 31 - __clz(ormag) : 32;
   if (MSB == 32) {  // nothing is coded; sizeArray = 1 (BPCEngine.cu:1998-2010)
-    if (lane == 0) { out[0] = 32; sizes[w] = 1; }
+    if (lane == 0) { out[0] = 32; sizes[blk] = 1; }
     return;
   }
   __syncwarp();
@@ -422,7 +377,7 @@ __global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* 
   } else if (lane == 0) {
     out[0] = (unsigned short)MSB;
   }
-  if (lane == 0) sizes[w] = size;
+  if (lane == 0) sizes[blk] = size;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -515,11 +470,12 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int w = blockIdx.x * (blockDim.x >> 5) + wib;
   if (w >= p.total_cb) return;
-  const int frame = w / p.ncb, cb = w - frame * p.ncb;
+  const int frame = (w / p.ncb) * p.pstep + p.pfirst, cb = w % p.ncb;
   const int bx = cb % p.nbx, by = cb / p.nbx;
   int* dst = q + (size_t)frame * p.A + (size_t)(by * kCB) * p.Wa + bx * kCB + 2 * lane;
-  const unsigned short* in = cw + (size_t)w * kCBWords;
-  const int size = sizes[w];
+  const size_t blk = (size_t)frame * p.ncb + cb;
+  const unsigned short* in = cw + blk * kCBWords;
+  const int size = sizes[blk];
   const int MSB = in[0];
   unsigned (*pl)[32] = s_pl[wib];
 

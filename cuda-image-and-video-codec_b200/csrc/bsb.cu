@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) bsb_pack_kernel(const unsigned short* __r
     const int f = (int)(g / n);
     const long long S = s_excl[k] + (long long)f * (n + 10);
     if (threadIdx.x == 0) { frame_off[f] = S; if (f > 0) out[S - 1] = 0xFFFFu; }
-    if (threadIdx.x < 9) out[S + threadIdx.x] = (a.first_frame_index + f == 0) ? a.hdr[threadIdx.x] : (unsigned short)0xFFFFu;
+    if (threadIdx.x < 9) out[S + threadIdx.x] = (a.first_frame_index + f < a.hdr_count) ? a.hdr[threadIdx.x] : (unsigned short)0xFFFFu;
     for (int cb = threadIdx.x; cb < n; cb += blockDim.x) {
       out[S + 9 + 2 * cb] = cw[(size_t)(g + cb) * kCBWords];
       out[S + 10 + 2 * cb] = (unsigned short)sizes[g + cb];

@@ -548,16 +548,18 @@ static int fuse_mode() {
 
 // Host loop over levels (replaces DWTEngine::DWTForward, DWT/DWTGenerator.cu:1268-1342; no host
 // synchronisation between levels).  out_int: 9/7 only, write (int)c instead of c.
+// tplane != nullptr (RGB path): level 1 reads colour-transformed 32-bit planes [frames][Ha][Wa] instead of u8 pixels.
 static int dwt_forward_levels(const uint8_t* d_px, void* d_coeff, void* d_scratch, int W, int H, int Wa, int Ha, int wl,
-                              bool lossy, float qs, bool out_int, int frames, int lfirst, int llast, cudaStream_t st) {
+                              bool lossy, float qs, bool out_int, int frames, int lfirst, int llast, cudaStream_t st,
+                              const void* tplane = nullptr) {
   const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl);
   int first = lfirst;
   // leading levels through the streaming kernel of dwt_fast.cu while the geometry allows it
   while (fuse_mode() > 0 && first <= llast) {
     const int l = first, Wc = Wa >> (l - 1), Hc = Ha >> (l - 1);
-    const bool u8 = l == 1;
-    const void* src = u8 ? static_cast<const void*>(d_px) : static_cast<const char*>(d_scratch) + ll_offset(Wa, Ha, l - 1) * 4;
-    const long long sfs = u8 ? (long long)W * H : (long long)S;
+    const bool u8 = l == 1 && !tplane;
+    const void* src = u8 ? static_cast<const void*>(d_px) : l == 1 ? tplane : static_cast<const char*>(d_scratch) + ll_offset(Wa, Ha, l - 1) * 4;
+    const long long sfs = u8 ? (long long)W * H : l == 1 ? (long long)A : (long long)S;
     const int sp = u8 ? W : Wc;
     int lv = (u8 && fuse_mode() == 2 && llast >= 2) ? 2 : 1;
     void* ll = (l + lv - 1 == wl) ? nullptr : static_cast<char*>(d_scratch) + ll_offset(Wa, Ha, l + lv - 1) * 4;
@@ -575,9 +577,13 @@ static int dwt_forward_levels(const uint8_t* d_px, void* d_coeff, void* d_scratc
     FwdArgs a{};
     a.Wc = Wa >> (l - 1); a.Hc = Ha >> (l - 1);
     a.W = W; a.H = H; a.Wa = Wa;
-    if (l == 1) {
+    const bool px_in = l == 1 && !tplane;
+    if (px_in) {
       a.src = d_px; a.src_fstride = (long long)W * H; a.src_pitch = W;
       a.src_vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_px) & 3) == 0) && (((long long)W * H) % 4 == 0);
+    } else if (l == 1) {
+      a.src = tplane; a.src_fstride = (long long)A; a.src_pitch = Wa;
+      a.src_vec = (reinterpret_cast<uintptr_t>(tplane) & 15) == 0;
     } else {
       a.src = static_cast<char*>(d_scratch) + ll_offset(Wa, Ha, l - 1) * 4; a.src_fstride = (long long)S;
       a.src_pitch = a.Wc; a.src_vec = (a.Wc % 4 == 0) && (ll_offset(Wa, Ha, l - 1) % 4 == 0) && (S % 4 == 0);
@@ -594,13 +600,13 @@ static int dwt_forward_levels(const uint8_t* d_px, void* d_coeff, void* d_scratc
     a.nchunks = ((a.Hc >> 1) + a.rp - 1) / a.rp;
     dim3 grid((a.nstrips * a.nchunks + 3) / 4, frames), block(128);
     if (!lossy) {
-      if (l == 1) dwt_forward_level<int, int, false, true><<<grid, block, 0, st>>>(a);
+      if (px_in) dwt_forward_level<int, int, false, true><<<grid, block, 0, st>>>(a);
       else dwt_forward_level<int, int, false, false><<<grid, block, 0, st>>>(a);
     } else if (out_int) {
-      if (l == 1) dwt_forward_level<float, int, true, true><<<grid, block, 0, st>>>(a);
+      if (px_in) dwt_forward_level<float, int, true, true><<<grid, block, 0, st>>>(a);
       else dwt_forward_level<float, int, true, false><<<grid, block, 0, st>>>(a);
     } else {
-      if (l == 1) dwt_forward_level<float, float, true, true><<<grid, block, 0, st>>>(a);
+      if (px_in) dwt_forward_level<float, float, true, true><<<grid, block, 0, st>>>(a);
       else dwt_forward_level<float, float, true, false><<<grid, block, 0, st>>>(a);
     }
     ++g_launches;
@@ -609,8 +615,10 @@ static int dwt_forward_levels(const uint8_t* d_px, void* d_coeff, void* d_scratc
 }
 
 // Replaces DWTEngine::DWTReverse (DWT/DWTGenerator.cu:1349-1424) + removeOffsetAndApplyMaxMin[Lossy].
+// tplane != nullptr (RGB path): level 1 writes 32-bit planes [frames][Ha][Wa] for the inverse colour transform
+// instead of clamped u8 pixels.
 static int dwt_inverse_levels(const int32_t* d_q, uint8_t* d_px, void* d_scratch, int W, int H, int Wa, int Ha, int wl, bool lossy,
-                              float qs, bool flat_crop, int frames, int lhigh, int llow, cudaStream_t st) {
+                              float qs, bool flat_crop, int frames, int lhigh, int llow, cudaStream_t st, void* tplane = nullptr) {
   const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl);
   for (int l = lhigh; l >= llow; --l) {
     InvArgs a{};
@@ -622,9 +630,13 @@ static int dwt_inverse_levels(const int32_t* d_q, uint8_t* d_px, void* d_scratch
     }
     a.in_vec = (a.Wc % 4 == 0) && (S % 2 == 0) && (ll_offset(Wa, Ha, l) % 2 == 0);
     a.W = W; a.H = H; a.flat_crop = flat_crop ? 1 : 0;
-    if (l == 1) {
+    const bool px_out = l == 1 && !tplane;
+    if (px_out) {
       a.dst = d_px; a.dst_fstride = (long long)W * H; a.dst_pitch = W;
       a.dst_vec = (W == Wa) && ((reinterpret_cast<uintptr_t>(d_px) & 3) == 0) && (((long long)W * H) % 4 == 0);
+    } else if (l == 1) {
+      a.dst = tplane; a.dst_fstride = (long long)A; a.dst_pitch = Wa;
+      a.dst_vec = (reinterpret_cast<uintptr_t>(tplane) & 15) == 0;
     } else {
       a.dst = static_cast<char*>(d_scratch) + ll_offset(Wa, Ha, l - 1) * 4; a.dst_fstride = (long long)S; a.dst_pitch = a.Wc;
       a.dst_vec = (a.Wc % 4 == 0) && (S % 4 == 0) && (ll_offset(Wa, Ha, l - 1) % 4 == 0);
@@ -632,9 +644,9 @@ static int dwt_inverse_levels(const int32_t* d_q, uint8_t* d_px, void* d_scratch
     a.r_ll = 1.0f / kQStep[l - 1][0]; a.r_hl = 1.0f / kQStep[l - 1][1];
     a.r_lh = 1.0f / kQStep[l - 1][2]; a.r_hh = 1.0f / kQStep[l - 1][3];
     a.rqs = 1.0f / qs;
-    if (fuse_mode() > 0 && S % 4 == 0 && !(l == 1 && flat_crop && W != Wa) &&
-        dwt_inverse_fast_ok(d_q, a.first ? nullptr : a.ll, a.dst, l == 1, a.dst_pitch, a.dst_fstride, a.ll_pitch, a.ll_fstride, a.Wc, a.Hc)) {
-      int rc = dwt_inverse_fast(d_q, (long long)A, Wa, a.first ? nullptr : a.ll, a.ll_fstride, a.ll_pitch, a.first != 0, a.Wc, a.Hc, a.dst, l == 1,
+    if (fuse_mode() > 0 && S % 4 == 0 && !(px_out && flat_crop && W != Wa) &&
+        dwt_inverse_fast_ok(d_q, a.first ? nullptr : a.ll, a.dst, px_out, a.dst_pitch, a.dst_fstride, a.ll_pitch, a.ll_fstride, a.Wc, a.Hc)) {
+      int rc = dwt_inverse_fast(d_q, (long long)A, Wa, a.first ? nullptr : a.ll, a.ll_fstride, a.ll_pitch, a.first != 0, a.Wc, a.Hc, a.dst, px_out,
                                 a.dst_fstride, a.dst_pitch, H, l, lossy, qs, frames, st);
       if (rc) return rc;
       continue;
@@ -644,10 +656,10 @@ static int dwt_inverse_levels(const int32_t* d_q, uint8_t* d_px, void* d_scratch
     a.nchunks = ((a.Hc >> 1) + a.rp - 1) / a.rp;
     dim3 grid((a.nstrips * a.nchunks + 3) / 4, frames), block(128);
     if (!lossy) {
-      if (l == 1) dwt_inverse_level<int, false, true><<<grid, block, 0, st>>>(a);
+      if (px_out) dwt_inverse_level<int, false, true><<<grid, block, 0, st>>>(a);
       else dwt_inverse_level<int, false, false><<<grid, block, 0, st>>>(a);
     } else {
-      if (l == 1) dwt_inverse_level<float, true, true><<<grid, block, 0, st>>>(a);
+      if (px_out) dwt_inverse_level<float, true, true><<<grid, block, 0, st>>>(a);
       else dwt_inverse_level<float, true, false><<<grid, block, 0, st>>>(a);
     }
     ++g_launches;
@@ -774,6 +786,16 @@ int dwt_inverse(const int32_t* d_q, uint8_t* d_px, void* d_scratch, int W, int H
   PCS_CUDA_TRY(cudaStreamWaitEvent(st, aux->ev[1], 0));
   PCS_CUDA_TRY(cudaStreamWaitEvent(st, aux->ev[2], 0));
   return (int)cudaGetLastError();
+}
+
+// RGB path: the same transforms on colour-transformed 32-bit planes (`planes` = frames x 3 components).
+int dwt_forward_planes(const void* d_tplanes, void* d_coeff, void* d_scratch, int Wa, int Ha, int wl, bool lossy, float qs, bool out_int,
+                       int planes, cudaStream_t st) {
+  return dwt_forward_levels(nullptr, d_coeff, d_scratch, Wa, Ha, Wa, Ha, wl, lossy, qs, out_int, planes, 1, wl, st, d_tplanes);
+}
+int dwt_inverse_planes(const int32_t* d_q, void* d_tplanes, void* d_scratch, int Wa, int Ha, int wl, bool lossy, float qs, int planes,
+                       cudaStream_t st) {
+  return dwt_inverse_levels(d_q, nullptr, d_scratch, Wa, Ha, Wa, Ha, wl, lossy, qs, false, planes, wl, 1, st, d_tplanes);
 }
 
 }  // namespace pcs

@@ -88,7 +88,13 @@ extern "C" {
 // Greyscale / k == 0 / 2 coding passes: with three component files the suffixes are R,G,B and grey
 // uses "R" (Engines/Engine.cu:124-139, Engines/CodingEngine.cu:662); suffix _0 is the k == 0 set.
 int32_t pcs_lut_load(const char* folder, int32_t wl, int32_t header[8], int32_t* table, int32_t capacity) {
-  if (!folder || wl < 1 || wl > 10) return PCS_E_ARG;
+  return pcs_lut_load_component(folder, wl, 0, header, table, capacity);
+}
+
+// RGB path: component i is coded with the i-th table set, files "R", "G", "B" (Engines/Engine.cu:124-139,
+// Engines/CodingEngine.cu:616,696,790).
+int32_t pcs_lut_load_component(const char* folder, int32_t wl, int32_t component, int32_t header[8], int32_t* table, int32_t capacity) {
+  if (!folder || wl < 1 || wl > 10 || component < 0 || component > 2) return PCS_E_ARG;
   const std::string dir(folder);
   if (!read_lut_header(dir, header)) return PCS_E_LUT;
   const int nBp = header[0], nSub = header[1], cR = header[2], cG = header[3], cS = header[4];
@@ -97,7 +103,8 @@ int32_t pcs_lut_load(const char* folder, int32_t wl, int32_t header[8], int32_t*
   if (n > capacity) return PCS_E_NOMEM;
   std::vector<int32_t> t(n, 0);  // undefined entries are 0 (the reference relies on fresh zero pages)
   const int R = (nSub * wl + 1) * nBp * cR, S = (nSub * wl + 1) * nBp * cS;
-  const std::string comp = header[6] == 1 ? "" : "R";
+  static const char* const kComp[3] = {"R", "G", "B"};
+  const std::string comp = header[6] == 1 ? "" : kComp[component];
   if (!read_lut_section(dir + "ref" + comp + ".txt_0", t, 0, nBp, cR, wl)) return PCS_E_LUT;
   if (!read_lut_section(dir + "sig" + comp + ".txt_0", t, R, nBp, cS, wl)) return PCS_E_LUT;
   if (!read_lut_section(dir + "sign" + comp + ".txt_0", t, R + S, nBp, cG, wl)) return PCS_E_LUT;

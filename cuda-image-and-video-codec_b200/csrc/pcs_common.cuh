@@ -30,17 +30,16 @@ extern unsigned long long g_launches;  // host-side counter of kernel launches (
 // Arguments of the bit-plane coder kernels (bpc.cu)
 struct BpcArgs {
   int Wa, Ha, nbx, ncb, wl, nBp, nSub, nrows, prec, total_cb;
+  int pstep, pfirst;               // plane of the launch's frame f = f * pstep + pfirst (RGB: one launch per component, pstep = 3)
   long long A;
-  const unsigned long long* sigp;  // [nrows] 9 x 7-bit P(0) per significance context
-  const unsigned* sgnp;            // [nrows] 4 x 7-bit per sign context
-  const unsigned char* refp;       // [nrows] refinement probability
-  const uint4* tab4;               // [nrows] the same as bytes: x = sig ctx 0..3, y = sig ctx 4..7, z = sig ctx 8 | ref << 8, w = sign ctx 0..3
+  const uint4* tab4;               // [nrows] probability rows of this launch's component, as bytes: x = sig ctx 0..3, y = sig ctx 4..7, z = sig ctx 8 | ref << 8, w = sign ctx 0..3
 };
 // Arguments of the bit-stream builder kernels (bsb.cu)
 struct BsbArgs {
   int ncb;                // codeblocks per frame
   int batch;              // frames
-  int first_frame_index;  // global index of frame 0 of this batch (only global frame 0 carries the header)
+  int first_frame_index;  // global index of frame 0 of this batch
+  int hdr_count;          // global frames 0 .. hdr_count-1 carry the header (1; RGB video: 3, BitStreamBuilder.cpp:104 with iter = frame)
   unsigned short hdr[9];
 };
 

@@ -27,6 +27,8 @@ SYMBOLS = {
     "pcs_adapted_dims": (None, [_I32, _I32, C.POINTER(_I32), C.POINTER(_I32)]),
     "pcs_lut_load": (_I32, [C.c_char_p, _I32, C.POINTER(_I32), C.POINTER(_I32), _I32]),
     "pcs_lut_size": (_I32, [C.POINTER(_I32), _I32]),
+    "pcs_lut_load_component": (_I32, [C.c_char_p, _I32, _I32, C.POINTER(_I32), C.POINTER(_I32), _I32]),
+    "pcs_frame_planes": (_I32, [_VP]),
     "pcs_header_pack": (None, [C.POINTER(PcsParams), _U16P]),
     "pcs_header_unpack": (_I32, [_U16P, C.POINTER(PcsParams)]),
     "pcs_frame_pixels": (C.c_size_t, [_VP]),

@@ -41,16 +41,20 @@ class Lut:
     table: np.ndarray
 
 
-def load_lut(folder: str, wl: int) -> Lut:
-    """Engine::initLUT for greyscale / k=0 (Engines/Engine.cu:101-141 of the reference)."""
+def load_lut(folder: str, wl: int, rgb: bool = False) -> Lut:
+    """Engine::initLUT for k=0 (Engines/Engine.cu:101-141 of the reference): the "R" table set for greyscale,
+    the R, G and B sets back to back for the RGB path."""
     lib = _lib.load()
     hdr = (C.c_int32 * 8)()
     cap = 1 << 16
-    tab = (C.c_int32 * cap)()
-    n = lib.pcs_lut_load(folder.encode(), wl, hdr, tab, cap)
-    if n <= 0:
-        raise PcsError(f"pcs_lut_load({folder!r}, wl={wl}) failed: {n}")
-    return Lut(np.array(hdr[:], dtype=np.int32), np.array(tab[:n], dtype=np.int32))
+    parts = []
+    for comp in range(3 if rgb else 1):
+        tab = (C.c_int32 * cap)()
+        n = lib.pcs_lut_load_component(folder.encode(), wl, comp, hdr, tab, cap)
+        if n <= 0:
+            raise PcsError(f"pcs_lut_load_component({folder!r}, wl={wl}, {comp}) failed: {n}")
+        parts.append(np.array(tab[:n], dtype=np.int32))
+    return Lut(np.array(hdr[:], dtype=np.int32), np.concatenate(parts))
 
 
 @dataclass
@@ -67,6 +71,7 @@ class Params:
     k: float = 0.0
     cb_width: int = 64
     cb_height: int = 18
+    rgb: bool = False
     extra: dict = field(default_factory=dict)
 
     def to_c(self, lut: Lut) -> "_lib.PcsParams":
@@ -75,7 +80,7 @@ class Params:
         p.quant_size, p.coding_passes, p.k_factor = self.qs, self.cp, self.k
         p.cb_width, p.cb_height, p.frames = self.cb_width, self.cb_height, self.frames
         p.bit_depth, p.bits_per_sample, p.endianess, p.is_signed = 8, 8, 0, 0
-        p.components, p.is_rgb = 1, 0
+        p.components, p.is_rgb = 1, int(self.rgb)
         for k, v in self.extra.items():
             setattr(p, k, v)
         p.max_batch, p.flags = self.max_batch, self.flags
@@ -117,7 +122,8 @@ class Codec:
         self.ctx = ctx
         self.A = int(self.lib.pcs_frame_pixels(ctx))
         self.ncb = int(self.lib.pcs_frame_codeblocks(ctx))
-        self.max_words = int(self.lib.pcs_frame_max_stream_words(ctx))
+        self.max_words = int(self.lib.pcs_frame_max_stream_words(ctx))  # per frame (all its planes)
+        self.planes = int(self.lib.pcs_frame_planes(ctx))               # 1 grey, 3 RGB
         self.Wa, self.Ha = adapted_dims(params.width, params.height)
 
     def close(self):
@@ -132,6 +138,11 @@ class Codec:
             pass
 
     # ---- helpers -------------------------------------------------------------------------
+    def _px_shape(self, n):
+        """u8 pixels of n frames: [n, H, W] grey, [n, 3, H, W] planar RGB."""
+        p = self.params
+        return (n, 3, p.height, p.width) if self.planes == 3 else (n, p.height, p.width)
+
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
 
@@ -145,57 +156,57 @@ class Codec:
         t = self.torch
         B = px.shape[0]
         dt = t.int32 if (not self.params.lossy or trunc_to_int) else t.float32
-        out = t.empty((B, self.Ha, self.Wa), dtype=dt, device=px.device)
+        out = t.empty((B * self.planes, self.Ha, self.Wa), dtype=dt, device=px.device)
         _check(self.lib.pcs_dwt_forward(self.ctx, self._p(px), self._p(out), int(trunc_to_int), B, self._stream()),
                "pcs_dwt_forward", self.ctx)
         return out
 
     def dwt_inverse(self, q):
         t = self.torch
-        B = q.shape[0]
-        out = t.empty((B, self.params.height, self.params.width), dtype=t.uint8, device=q.device)
+        B = q.shape[0] // self.planes
+        out = t.empty(self._px_shape(B), dtype=t.uint8, device=q.device)
         _check(self.lib.pcs_dwt_inverse(self.ctx, self._p(q), self._p(out), B, self._stream()), "pcs_dwt_inverse", self.ctx)
         return out
 
     def bpc_encode(self, coeff):
         t = self.torch
-        B = coeff.shape[0]
-        cw = t.empty((B, self.ncb, 4096), dtype=t.int16, device=coeff.device)
-        sizes = t.empty((B, self.ncb), dtype=t.int32, device=coeff.device)
+        B = coeff.shape[0] // self.planes
+        cw = t.empty((B * self.planes, self.ncb, 4096), dtype=t.int16, device=coeff.device)
+        sizes = t.empty((B * self.planes, self.ncb), dtype=t.int32, device=coeff.device)
         _check(self.lib.pcs_bpc_encode(self.ctx, self._p(coeff), int(coeff.dtype == t.float32), self._p(cw), self._p(sizes),
                                        B, self._stream()), "pcs_bpc_encode", self.ctx)
         return cw, sizes
 
     def bpc_decode(self, cw, sizes):
         t = self.torch
-        B = cw.shape[0]
-        q = t.empty((B, self.Ha, self.Wa), dtype=t.int32, device=cw.device)
+        B = cw.shape[0] // self.planes
+        q = t.empty((B * self.planes, self.Ha, self.Wa), dtype=t.int32, device=cw.device)
         _check(self.lib.pcs_bpc_decode(self.ctx, self._p(cw), self._p(sizes), self._p(q), B, self._stream()),
                "pcs_bpc_decode", self.ctx)
         return q
 
     def bsb_pack(self, cw, sizes, first_frame_index: int = 0):
         t = self.torch
-        B = cw.shape[0]
+        B = cw.shape[0] // self.planes
         out = t.empty(B * self.max_words, dtype=t.int16, device=cw.device)
-        off = t.empty(B + 1, dtype=t.int64, device=cw.device)
+        off = t.empty(B * self.planes + 1, dtype=t.int64, device=cw.device)
         _check(self.lib.pcs_bsb_pack(self.ctx, self._p(cw), self._p(sizes), first_frame_index, self._p(out), self._p(off),
                                      B, self._stream()), "pcs_bsb_pack", self.ctx)
         return out, off
 
     def bsb_unpack(self, stream, off):
         t = self.torch
-        B = off.numel() - 1
-        cw = t.empty((B, self.ncb, 4096), dtype=t.int16, device=stream.device)
-        sizes = t.empty((B, self.ncb), dtype=t.int32, device=stream.device)
+        B = (off.numel() - 1) // self.planes
+        cw = t.empty((B * self.planes, self.ncb, 4096), dtype=t.int16, device=stream.device)
+        sizes = t.empty((B * self.planes, self.ncb), dtype=t.int32, device=stream.device)
         _check(self.lib.pcs_bsb_unpack(self.ctx, self._p(stream), self._p(off), self._p(cw), self._p(sizes), B, self._stream()),
                "pcs_bsb_unpack", self.ctx)
         return cw, sizes
 
     def export_ref_codestream(self, cw, sizes):
         t = self.torch
-        B = cw.shape[0]
-        ref = t.empty((B, self.A), dtype=t.int32, device=cw.device)
+        B = cw.shape[0] // self.planes
+        ref = t.empty((B * self.planes, self.A), dtype=t.int32, device=cw.device)
         _check(self.lib.pcs_export_ref_codestream(self.ctx, self._p(cw), self._p(sizes), self._p(ref), B, self._stream()),
                "pcs_export_ref_codestream", self.ctx)
         return ref
@@ -206,16 +217,16 @@ class Codec:
         if out is None:
             out = t.empty(B * self.max_words, dtype=t.int16, device=px.device)
         if off is None:
-            off = t.empty(B + 1, dtype=t.int64, device=px.device)
+            off = t.empty(B * self.planes + 1, dtype=t.int64, device=px.device)
         _check(self.lib.pcs_encode_device(self.ctx, self._p(px), B, first_frame_index, self._p(out), self._p(off),
                                           self._stream()), "pcs_encode_device", self.ctx)
         return out, off
 
     def decode_device(self, stream, off, out=None):
         t = self.torch
-        B = off.numel() - 1
+        B = (off.numel() - 1) // self.planes
         if out is None:
-            out = t.empty((B, self.params.height, self.params.width), dtype=t.uint8, device=stream.device)
+            out = t.empty(self._px_shape(B), dtype=t.uint8, device=stream.device)
         _check(self.lib.pcs_decode_device(self.ctx, self._p(stream), self._p(off), B, self._p(out), self._stream()),
                "pcs_decode_device", self.ctx)
         return out
@@ -232,7 +243,7 @@ class Codec:
         n = frames.shape[0]
         if out is None:
             out = np.empty(n * self.max_words, dtype=np.uint16)
-        lens = np.zeros(n, dtype=np.int32)
+        lens = np.zeros(n * self.planes, dtype=np.int32)  # one length per plane (the `_SIZE` sidecar values)
         total = C.c_size_t()
         _check(self.lib.pcs_encode_frames(self.ctx, frames.ctypes.data, n, first_frame_index, out.ctypes.data, out.size,
                                           lens.ctypes.data, C.byref(total)), "pcs_encode_frames", self.ctx)
@@ -241,9 +252,9 @@ class Codec:
     def decode_frames(self, stream: np.ndarray, lens: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
         stream = np.ascontiguousarray(stream, dtype=np.uint16)
         lens = np.ascontiguousarray(lens, dtype=np.int32)
-        n = lens.size
+        n = lens.size // self.planes
         if out is None:
-            out = np.empty((n, self.params.height, self.params.width), dtype=np.uint8)
+            out = np.empty(self._px_shape(n), dtype=np.uint8)
         _check(self.lib.pcs_decode_frames(self.ctx, stream.ctypes.data, lens.ctypes.data, n, out.ctypes.data),
                "pcs_decode_frames", self.ctx)
         return out

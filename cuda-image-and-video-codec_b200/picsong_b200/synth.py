@@ -35,6 +35,15 @@ def synth_frame(width: int, height: int, f: int = 0, x0: int = 0, y0: int = 0,
     return px.astype(np.uint8)
 
 
+def synth_rgb(width: int, height: int, f: int = 0) -> np.ndarray:
+    """Planar (3, height, width) RGB test frame: the grey content with a per-component phase shift, so the
+    three planes are correlated the way natural colour images are (exercises the colour transforms)."""
+    g = synth_frame(width, height, f).astype(np.int32)
+    r = synth_frame(width, height, f, x0=5, y0=3).astype(np.int32)
+    b = synth_frame(width, height, f, x0=11, y0=7).astype(np.int32)
+    return np.stack([np.clip((3 * g + r) // 4 + 6, 0, 255), g, np.clip((3 * g + b) // 4 - 5, 0, 255)]).astype(np.uint8)
+
+
 def synth_video(width: int, height: int, frames: int, first: int = 0) -> np.ndarray:
     return np.stack([synth_frame(width, height, f) for f in range(first, first + frames)])
 

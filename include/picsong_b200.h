@@ -31,7 +31,7 @@ enum {
   PCS_E_ARG = -1,        /* invalid parameter ("Incorrect parameters", Launcher.cu:132-136) */
   PCS_E_LUT = -2,        /* LUT folder unreadable / malformed */
   PCS_E_LUT_RANGE = -3,  /* LUT shape or probability outside what the coder supports */
-  PCS_E_UNSUPPORTED = -4,/* cp==3, k>0, RGB, signed input: out of scope */
+  PCS_E_UNSUPPORTED = -4,/* cp==3, k>0, signed / 16-bit input: out of scope */
   PCS_E_NOMEM = -5,
   PCS_E_STREAM = -6,     /* malformed codestream */
   PCS_E_BATCH = -7       /* batch larger than pcs_params.max_batch */
@@ -74,6 +74,10 @@ void pcs_adapted_dims(int32_t width, int32_t height, int32_t* adapted_w, int32_t
 int32_t pcs_lut_load(const char* folder, int32_t wavelet_levels, int32_t header[8], int32_t* table,
                      int32_t capacity);
 int32_t pcs_lut_size(const int32_t header[8], int32_t wavelet_levels);
+/* RGB path: the table set of component 0/1/2 = files "R"/"G"/"B" (Engines/Engine.cu:124-139).  For an RGB
+ * context pcs_params.lut is the three component tables back to back (lut_len = 3 * pcs_lut_size). */
+int32_t pcs_lut_load_component(const char* folder, int32_t wavelet_levels, int32_t component, int32_t header[8],
+                               int32_t* table, int32_t capacity);
 
 /* BitStreamBuilder::setExtraInformation (BitStreamBuilder/BitStreamBuilder.cpp:35-94) */
 void pcs_header_pack(const pcs_params* p, uint16_t out[9]);
@@ -84,7 +88,14 @@ int32_t pcs_header_unpack(const uint16_t in[9], pcs_params* p);
 /* Sizes a caller needs to allocate buffers (all per frame). */
 size_t pcs_frame_pixels(const pcs_ctx*);        /* W_a*H_a = coefficient count A */
 int32_t pcs_frame_codeblocks(const pcs_ctx*);   /* nCB = A/4096 */
-size_t pcs_frame_max_stream_words(const pcs_ctx*); /* A + nCB + 10 uint16: upper bound of one frame */
+size_t pcs_frame_max_stream_words(const pcs_ctx*); /* planes * (A + nCB + 10) uint16: upper bound of one frame */
+/* RGB (pcs_params.is_rgb = 1; Engines/CodingEngine.cu:598-630,680-710,764-810, Engines/DecodingEngine.cu:738-770):
+ * a frame is u8 planar [3][height][width]; after the colour transform (RCT for 5/3, ICT for 9/7) its three
+ * component planes are coded as three independent "frames" with the R/G/B probability tables.  Every batched
+ * layout below then holds batch * 3 PLANES where it says [batch] (plane 3f+c = component c of frame f), frame
+ * offset / length arrays have one entry per plane, and only plane 0 of a still (planes 0..2 of video frame 0)
+ * carries the 9-word header.  1 for greyscale. */
+int32_t pcs_frame_planes(const pcs_ctx*);
 
 /* ---- context ------------------------------------------------------------------------------- */
 

@@ -62,7 +62,7 @@ def main():
         if os.path.exists(enc) and os.path.getsize(enc) > 0 and os.path.getsize(enc) < (1 << 20):
             arrays[name + ".enc"] = np.fromfile(enc, dtype=np.uint16)
             dec = os.path.join(fdir, name + ".dec")
-            npx = e["W"] * e["H"] * max(e["frames"], 1)
+            npx = e["W"] * e["H"] * max(e["frames"], 1) * (3 if e.get("kind") == "rgb" else 1)
             if os.path.exists(dec) and (e["type"] == 1 or not e.get("dec_equal_input")):
                 d = np.fromfile(dec, dtype=np.uint8)
                 arrays[name + ".dec"] = d[d.size - npx:]
@@ -77,6 +77,8 @@ def main():
         lut[folder + ".header"] = np.asarray(hdr, dtype=np.int32)
         for sec in ("ref", "sig", "sign"):
             lut[f"{folder}.{sec}"] = parse_rows(os.path.join(REF_LUT, folder, f"{sec}R.txt_0"))
+            for comp in "GB":  # RGB path: one table set per component (Engines/Engine.cu:124-139)
+                lut[f"{folder}.{sec}{comp}"] = parse_rows(os.path.join(REF_LUT, folder, f"{sec}{comp}.txt_0"))
     np.savez_compressed(os.path.join(DST, "lut_tables.npz"), **lut)
     for f in sorted(os.listdir(DST)):
         print(f, os.path.getsize(os.path.join(DST, f)))

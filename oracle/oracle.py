@@ -99,11 +99,11 @@ class Lut:
         self.table = np.ascontiguousarray(table, dtype=np.int32)
 
 
-def lut_load(folder: str, wl: int) -> Lut:
+def lut_load(folder: str, wl: int, component: int = 0) -> Lut:
     hdr = np.zeros(8, dtype=np.int32)
     cap = 1 << 16
     table = np.zeros(cap, dtype=np.int32)
-    n = lib().pcso_lut_load(folder.encode(), wl, _p(hdr, C.c_int), _p(table, C.c_int32), cap)
+    n = lib().pcso_lut_load_component(folder.encode(), wl, component, _p(hdr, C.c_int), _p(table, C.c_int32), cap)
     if n < 0:
         raise RuntimeError(f"oracle lut_load({folder!r}, wl={wl}) failed: {n}")
     return Lut(hdr, table[:n].copy())
@@ -186,3 +186,67 @@ def decode_frame(stream: np.ndarray, Wa: int, Ha: int, wl: int, lossy: bool, qs:
     cs, sizes, _ = bsb_unpack(stream, ncb)
     q = bpc_decode(cs, sizes, Wa, Ha, wl, lut)
     return dwt97_inverse(q, wl, qs) if lossy else dwt53_inverse(q, wl)
+
+
+# ---- RGB path: colour transform, then three independently coded component planes ----
+def rgb_forward(planes: np.ndarray, lossy: bool):
+    """planes: u8 (3, Ha, Wa), already mirror-padded -> three transformed planes (int32 | float32): Y, B-G, R-G."""
+    planes = np.ascontiguousarray(planes, dtype=np.uint8)
+    n = planes[0].size
+    dt, ct = (np.float32, C.c_float) if lossy else (np.int32, C.c_int32)
+    out = [np.empty(planes[0].shape, dtype=dt) for _ in range(3)]
+    fn = lib().pcso_ict_forward if lossy else lib().pcso_rct_forward
+    fn(_p(planes[0], C.c_uint8), _p(planes[1], C.c_uint8), _p(planes[2], C.c_uint8), C.c_size_t(n),
+       _p(out[0], ct), _p(out[1], ct), _p(out[2], ct))
+    return out
+
+
+def rgb_inverse(comps, lossy: bool) -> np.ndarray:
+    dt, ct = (np.float32, C.c_float) if lossy else (np.int32, C.c_int32)
+    comps = [np.ascontiguousarray(c, dtype=dt) for c in comps]
+    out = np.empty((3,) + comps[0].shape, dtype=np.uint8)
+    fn = lib().pcso_ict_inverse if lossy else lib().pcso_rct_inverse
+    fn(_p(comps[0], ct), _p(comps[1], ct), _p(comps[2], ct), C.c_size_t(comps[0].size),
+       _p(out[0], C.c_uint8), _p(out[1], C.c_uint8), _p(out[2], C.c_uint8))
+    return out
+
+
+def encode_rgb_frame(rgb: np.ndarray, wl: int, lossy: bool, qs: float, luts, header_on, frames: int = 0):
+    """Engines/CodingEngine.cu:598-630,680-710 (stills: component i is coded with iter = i, so only component 0
+    carries the header) and :764-810 (video: iter = frame index for all three components).
+    rgb: u8 (3, H, W); luts: the three component tables; header_on: 3 bools.  Returns the three streams."""
+    _, H, W = rgb.shape
+    padded = np.stack([pad_mirror(rgb[c]) for c in range(3)])
+    comps = rgb_forward(padded, lossy)
+    Ha, Wa = padded[0].shape
+    streams = []
+    for c in range(3):
+        if lossy:
+            cf = np.empty((Ha, Wa), dtype=np.float32)
+            assert lib().pcso_dwt97_forward_plane(_p(comps[c], C.c_float), Wa, Ha, wl, C.c_float(qs), _p(cf, C.c_float)) == 0
+            q = truncate(cf)
+        else:
+            q = np.empty((Ha, Wa), dtype=np.int32)
+            assert lib().pcso_dwt53_forward_plane(_p(comps[c], C.c_int32), Wa, Ha, wl, _p(q, C.c_int32)) == 0
+        cs, sizes = bpc_encode(q, wl, luts[c])
+        hdr = header_pack(W, H, wl, lossy, qs, frames, isRGB=1) if header_on[c] else None
+        streams.append(bsb_pack(cs, sizes, hdr))
+    return streams
+
+
+def decode_rgb_frame(streams, Wa: int, Ha: int, wl: int, lossy: bool, qs: float, luts) -> np.ndarray:
+    """Engines/DecodingEngine.cu:738-770 + :599-650: three component streams -> u8 (3, Ha, Wa)."""
+    ncb = (Wa // 64) * (Ha // 64)
+    comps = []
+    for c in range(3):
+        cs, sizes, _ = bsb_unpack(streams[c], ncb)
+        q = bpc_decode(cs, sizes, Wa, Ha, wl, luts[c])
+        if lossy:
+            f = np.empty((Ha, Wa), dtype=np.float32)
+            assert lib().pcso_dwt97_inverse(_p(q, C.c_int32), Wa, Ha, wl, C.c_float(qs), None, _p(f, C.c_float)) == 0
+            comps.append(f)
+        else:
+            o = np.empty((Ha, Wa), dtype=np.int32)
+            assert lib().pcso_dwt53_inverse_plane(_p(q, C.c_int32), Wa, Ha, wl, _p(o, C.c_int32)) == 0
+            comps.append(o)
+    return rgb_inverse(comps, lossy)

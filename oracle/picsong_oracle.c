@@ -169,11 +169,21 @@ static const float QSTEP[10][4] = {
 
 /* Forward 5/3: u8 pixels (W_a x H_a, already padded) -> int32 Mallat plane out[0..A).
  * Level shift Engines/CodingEngine.cu:581-588 (px - 2^(bps-1)); host loop DWTGenerator.cu:1268-1342. */
+static int dwt53_forward_core(int Wa, int Ha, int wl, int32_t* out);
 int pcso_dwt53_forward(const uint8_t* px, int Wa, int Ha, int wl, int32_t* out) {
+  size_t A = (size_t)Wa * Ha;
+  for (size_t i = 0; i < A; i++) out[i] = (int32_t)px[i] - 128;
+  return dwt53_forward_core(Wa, Ha, wl, out);
+}
+/* RGB path: the plane is already level-shifted and colour-transformed (Engines/CodingEngine.cu:613) */
+int pcso_dwt53_forward_plane(const int32_t* in, int Wa, int Ha, int wl, int32_t* out) {
+  memcpy(out, in, (size_t)Wa * Ha * sizeof(int32_t));
+  return dwt53_forward_core(Wa, Ha, wl, out);
+}
+static int dwt53_forward_core(int Wa, int Ha, int wl, int32_t* out) {
   size_t A = (size_t)Wa * Ha;
   int32_t* tmp = (int32_t*)malloc(A * sizeof(int32_t));
   if (!tmp) return -1;
-  for (size_t i = 0; i < A; i++) out[i] = (int32_t)px[i] - 128;
   int Wc = Wa, Hc = Ha;
   for (int l = 1; l <= wl; l++) {
     for (int x = 0; x < Wc; x++) fwd53_1d(out + x, Hc, Wa);           /* vertical */
@@ -191,7 +201,15 @@ int pcso_dwt53_forward(const uint8_t* px, int Wa, int Ha, int wl, int32_t* out) 
 
 /* Inverse 5/3: int32 Mallat plane -> u8 pixels.  Host loop DWTGenerator.cu:1349-1424; pixel post
  * Engines/DecodingEngine.cu:719-729 clamp(v+128,0,255); narrowing IO/IOManager.ipp:332-335. */
+static int dwt53_inverse_core(const int32_t* q, int Wa, int Ha, int wl, uint8_t* px, int32_t* iout);
 int pcso_dwt53_inverse(const int32_t* q, int Wa, int Ha, int wl, uint8_t* px) {
+  return dwt53_inverse_core(q, Wa, Ha, wl, px, NULL);
+}
+/* RGB path: the reconstructed plane before the inverse colour transform (no +128, no clamp) */
+int pcso_dwt53_inverse_plane(const int32_t* q, int Wa, int Ha, int wl, int32_t* out) {
+  return dwt53_inverse_core(q, Wa, Ha, wl, NULL, out);
+}
+static int dwt53_inverse_core(const int32_t* q, int Wa, int Ha, int wl, uint8_t* px, int32_t* iout) {
   size_t A = (size_t)Wa * Ha;
   int32_t* w = (int32_t*)malloc(A * sizeof(int32_t));
   int32_t* tmp = (int32_t*)malloc(A * sizeof(int32_t));
@@ -208,8 +226,11 @@ int pcso_dwt53_inverse(const int32_t* q, int Wa, int Ha, int wl, uint8_t* px) {
     for (int y = 0; y < Hc; y++) memcpy(w + (size_t)y * Wa, tmp + (size_t)y * Wc, Wc * sizeof(int32_t));
   }
   for (size_t i = 0; i < A; i++) {
-    int32_t v = w[i] + 128;
-    px[i] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    if (iout) iout[i] = w[i];
+    if (px) {
+      int32_t v = w[i] + 128;
+      px[i] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
   }
   free(w); free(tmp);
   return 0;
@@ -218,11 +239,21 @@ int pcso_dwt53_inverse(const int32_t* q, int Wa, int Ha, int wl, uint8_t* px) {
 /* Forward 9/7 + quantiser multiply: u8 -> f32 Mallat plane.  Quantiser on subband write,
  * DWTGenerator.cu:403-419: c * Q[l-1][sb] * qs (two fp32 multiplies, left to right); LL only at
  * the last level.  Level index: currentLevel = wl - currentWLevel (:1292), i.e. 0 = finest. */
+static int dwt97_forward_core(int Wa, int Ha, int wl, float qs, float* out);
 int pcso_dwt97_forward(const uint8_t* px, int Wa, int Ha, int wl, float qs, float* out) {
+  size_t A = (size_t)Wa * Ha;
+  for (size_t i = 0; i < A; i++) out[i] = (float)((int)px[i] - 128);
+  return dwt97_forward_core(Wa, Ha, wl, qs, out);
+}
+/* RGB path: colour-transformed float plane in (Engines/CodingEngine.cu:693) */
+int pcso_dwt97_forward_plane(const float* in, int Wa, int Ha, int wl, float qs, float* out) {
+  memcpy(out, in, (size_t)Wa * Ha * sizeof(float));
+  return dwt97_forward_core(Wa, Ha, wl, qs, out);
+}
+static int dwt97_forward_core(int Wa, int Ha, int wl, float qs, float* out) {
   size_t A = (size_t)Wa * Ha;
   float* tmp = (float*)malloc(A * sizeof(float));
   if (!tmp) return -1;
-  for (size_t i = 0; i < A; i++) out[i] = (float)((int)px[i] - 128);
   int Wc = Wa, Hc = Ha;
   for (int l = 1; l <= wl; l++) {
     for (int x = 0; x < Wc; x++) fwd97_vert(out + x, Hc, Wa);
@@ -277,6 +308,7 @@ int pcso_dwt97_inverse(const int32_t* q, int Wa, int Ha, int wl, float qs, uint8
   }
   for (size_t i = 0; i < A; i++) {
     if (fout) fout[i] = w[i];
+    if (!px) continue;
     float r = nearbyintf((w[i] + 128.0f) + 0.01f); /* __float2int_rn: round half to even */
     r = r > 255.0f ? 255.0f : r;
     r = r < 0.0f ? 0.0f : r;
@@ -284,6 +316,54 @@ int pcso_dwt97_inverse(const int32_t* q, int Wa, int Ha, int wl, float qs, uint8
   }
   free(w); free(tmp);
   return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Colour transforms of the RGB path.  Planes are u8, already mirror-padded.
+ * Plane order out: 0 = Y, 1 = B-G (Cb), 2 = R-G (Cr)  (Engines/CodingEngine.cu:357-405).
+ * ---------------------------------------------------------------------------------------- */
+static int32_t floordiv4(int32_t v) { return (v >= 0) ? v / 4 : -((-v + 3) / 4); }
+/* Engines/CodingEngine.cu:357-379 RGBTransformLossless: floor((R+2G+B)/4), B-G, R-G on level-shifted samples */
+void pcso_rct_forward(const uint8_t* r, const uint8_t* g, const uint8_t* b, size_t n, int32_t* y, int32_t* cb, int32_t* cr) {
+  for (size_t i = 0; i < n; i++) {
+    int32_t R = (int32_t)r[i] - 128, G = (int32_t)g[i] - 128, B = (int32_t)b[i] - 128;
+    y[i] = floordiv4(R + 2 * G + B); cb[i] = B - G; cr[i] = R - G;
+  }
+}
+/* Engines/DecodingEngine.cu:599-624: G = Y - floor((Cb+Cr)/4), R = Cr + G, B = Cb + G, +128, clamp */
+void pcso_rct_inverse(const int32_t* y, const int32_t* cb, const int32_t* cr, size_t n, uint8_t* r, uint8_t* g, uint8_t* b) {
+  for (size_t i = 0; i < n; i++) {
+    int32_t G = y[i] - floordiv4(cb[i] + cr[i]), R = cr[i] + G, B = cb[i] + G;
+    R += 128; G += 128; B += 128;
+    r[i] = (uint8_t)(R < 0 ? 0 : (R > 255 ? 255 : R));
+    g[i] = (uint8_t)(G < 0 ? 0 : (G > 255 ? 255 : G));
+    b[i] = (uint8_t)(B < 0 ? 0 : (B > 255 ? 255 : B));
+  }
+}
+/* Engines/CodingEngine.cu:384-405 RGBTransformLossy with the matrix of CodingEngine.cuh:25.  Operation shapes as
+ * in the reference binary (sm_100 SASS): t = G*m1; t = fma(R, m0, t); t = fma(B, m2, t). */
+void pcso_ict_forward(const uint8_t* r, const uint8_t* g, const uint8_t* b, size_t n, float* y, float* cb, float* cr) {
+  static const float M[3][3] = {{0.299f, 0.587f, 0.114f}, {-0.168736f, -0.331264f, 0.5f}, {0.5f, -0.418688f, -0.081312f}};
+  float* out[3] = {y, cb, cr};
+  for (size_t i = 0; i < n; i++) {
+    float R = (float)r[i] - 128.0f, G = (float)g[i] - 128.0f, B = (float)b[i] - 128.0f;
+    for (int k = 0; k < 3; k++) out[k][i] = ftz(fmaf(B, M[k][2], ftz(fmaf(R, M[k][0], ftz(G * M[k][1])))));
+  }
+}
+/* Engines/DecodingEngine.cu:628-650 with DecodingEngine.cuh:41: rn(M*v + 0.01f) + 128, clamp.  SASS shapes:
+ * R = fma(Cr, 1.402, Y); G = fma(Cr, -0.714136, fma(Cb, -0.344136, Y)); B = fma(Cb, 1.772, Y). */
+void pcso_ict_inverse(const float* y, const float* cb, const float* cr, size_t n, uint8_t* r, uint8_t* g, uint8_t* b) {
+  for (size_t i = 0; i < n; i++) {
+    float v[3];
+    v[0] = ftz(fmaf(cr[i], 1.402f, y[i]));
+    v[1] = ftz(fmaf(cr[i], -0.714136f, ftz(fmaf(cb[i], -0.344136f, y[i]))));
+    v[2] = ftz(fmaf(cb[i], 1.772f, y[i]));
+    uint8_t* o[3] = {r, g, b};
+    for (int k = 0; k < 3; k++) {
+      int t = (int)nearbyintf(v[k] + 0.01f) + 128;
+      o[k][i] = (uint8_t)(t < 0 ? 0 : (t > 255 ? 255 : t));
+    }
+  }
 }
 
 /* BPC/BPCEngine.cu:49,55 readCoefficients: (int)c -- truncation toward zero (dead-zone). */
@@ -353,13 +433,20 @@ static int lut_section(const char* path, int32_t* table, int base, int nBp, int 
 /* Greyscale, k==0, cp==2: with LUT_N_FILES==3 the component suffixes are R,G,B and grey uses
  * "R" (Engine.cu:124-139 loads i+1 -> "R","G","B"; CodingEngine.cu:662 passes table 0);
  * with LUT_N_FILES==1 the suffix is empty (IOManager.ipp:433-444).  File suffix `_0` = k==0. */
+int pcso_lut_load_component(const char* folder, int wl, int component, int hdr[8], int32_t* table, int cap);
 int pcso_lut_load(const char* folder, int wl, int hdr[8], int32_t* table, int cap) {
+  return pcso_lut_load_component(folder, wl, 0, hdr, table, cap);
+}
+/* component 0,1,2 -> files "R","G","B" (Engine.cu:124-139: the RGB path codes component i with table i) */
+int pcso_lut_load_component(const char* folder, int wl, int component, int hdr[8], int32_t* table, int cap) {
   if (pcso_lut_header(folder, hdr)) return -1;
   int nBp = hdr[0], nSub = hdr[1], cR = hdr[2], cG = hdr[3], cS = hdr[4];
   int n = pcso_lut_size(hdr, wl);
   if (n > cap) return -2;
   memset(table, 0, (size_t)n * sizeof(int32_t));
-  const char* comp = (hdr[6] == 1) ? "" : "R";
+  static const char* kComp[3] = {"R", "G", "B"};
+  if (component < 0 || component > 2) return -4;
+  const char* comp = (hdr[6] == 1) ? "" : kComp[component];
   int R = nSub * nBp * cR * wl + nBp * cR, S = nSub * nBp * cS * wl + nBp * cS;
   char path[1024];
   /* -LUTFolder is used as a plain string prefix for the table files (must end in '/') */

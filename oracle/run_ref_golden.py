@@ -44,6 +44,15 @@ CASES = [
     ("cfg3_8k_wl6_ll",    "synth", 7680, 4320, 0, 6, 0, 1.0, "n1_lossless", False),
     ("cfg4_4k_f4_wl5_q1", "synth", 3840, 2160, 4, 5, 1, 1.0, "video_lossy", False),
     ("cfg5_band_f2_wl5_ll", "band", 32768, 4096, 2, 5, 0, 1.0, "n1_lossless", False),
+    # RGB path: planar R,G,B planes per frame, `-isRGB 1`, per-component LUT files
+    ("rgb128_wl2_ll", "rgb", 128, 128, 0, 2, 0, 1.0, "n1_lossless", True),
+    ("rgb256x192_wl3_ll", "rgb", 256, 192, 0, 3, 0, 1.0, "n1_lossless", True),
+    ("rgb256x192_wl3_q1", "rgb", 256, 192, 0, 3, 1, 1.0, "n1_lossy", True),
+    ("rgb200x150_wl2_q05", "rgb", 200, 150, 0, 2, 1, 0.5, "n1_lossy", True),
+    ("rgbv128_f3_wl2_ll", "rgb", 128, 128, 3, 2, 0, 1.0, "video_lossless", True),
+    ("rgbv256_f2_wl3_q1", "rgb", 256, 256, 2, 3, 1, 1.0, "video_lossy", True),
+    ("rgb2048_wl5_q1", "rgb", 2048, 2048, 0, 5, 1, 1.0, "n1_lossy", False),
+    ("rgb2048_wl5_ll", "rgb", 2048, 2048, 0, 5, 0, 1.0, "n1_lossless", False),
 ]
 
 
@@ -63,6 +72,8 @@ def make_input(kind, W, H, frames, path):
                 a = synth.synth_frame(W, H, i if frames else 0)
             elif kind == "band":
                 a = synth.synth_frame(W, H, 0, 0, H * i)
+            elif kind == "rgb":
+                a = synth.synth_rgb(W, H, i if frames else 0)  # [3][H][W] planar
             elif kind == "zeros":
                 a = synth.zeros_frame(W, H)
             else:
@@ -102,6 +113,8 @@ def main():
                 "-numberOfStreams", os.environ.get("REF_STREAMS", "1")]
         if frames:
             ecmd += ["-frames", str(frames)]
+        if kind == "rgb":
+            ecmd += ["-isRGB", "1"]
         rc_e, out_e, t_e = run(ecmd)
         dcmd = [REF, "-cd", "1", "-i", enc, "-o", dec, "-LUTFolder", lutdir, "-video", str(video),
                 "-numberOfStreams", os.environ.get("REF_STREAMS", "1")]
@@ -124,10 +137,10 @@ def main():
             # decoded-vs-input comparison (payload only: PGM header is filesize - W*H*n bytes)
             pd = dec if os.path.exists(dec) else os.path.join(OUT, name + ".dec")
             d = np.fromfile(pd, dtype=np.uint8)
-            n = W * H * max(frames, 1)
+            n = W * H * max(frames, 1) * (3 if kind == "rgb" else 1)
             x = np.fromfile(raw, dtype=np.uint8)
             if d.size >= n:
-                d = d[d.size - n:] if not frames else d[:n]
+                d = d[d.size - n:] if not (frames or kind == "rgb") else d[:n]
                 diff = d.astype(np.int32) - x.astype(np.int32)
                 mse = float(np.mean(diff.astype(np.float64) ** 2))
                 ent["dec_equal_input"] = bool(mse == 0.0)

@@ -20,8 +20,10 @@ class Golden:
         k = name + ".dec"
         return self._z[k] if k in self._z.files else None
 
-    def names_with_streams(self):
-        return sorted(k[:-4] for k in self._z.files if k.endswith(".enc"))
+    def names_with_streams(self, rgb=False):
+        """Greyscale cases by default; rgb=True: the RGB-path cases (tests/test_gpu_rgb.py)."""
+        return sorted(k[:-4] for k in self._z.files
+                      if k.endswith(".enc") and (self.manifest[k[:-4]].get("kind") == "rgb") == rgb)
 
     def input(self, name):
         from picsong_b200 import synth

@@ -22,10 +22,13 @@ def materialize(folder: str, dst_root: str) -> str:
     with open(os.path.join(d, "header.txt"), "w") as f:
         f.write("\n".join(f"{n};{int(v)}" for n, v in zip(_HDR_NAMES, z[folder + ".header"])))
     for sec in ("ref", "sig", "sign"):
-        rows = z[f"{folder}.{sec}"]
-        with open(os.path.join(d, f"{sec}R.txt_0"), "w") as f:
-            for r in rows:
-                f.write(f"{r[0]} {r[1]} {r[2]} : " + " ".join(str(int(v)) for v in r[3:]) + " \n")
+        for comp in "RGB":
+            key = f"{folder}.{sec}" + ("" if comp == "R" else comp)
+            if key not in z.files:
+                continue
+            with open(os.path.join(d, f"{sec}{comp}.txt_0"), "w") as f:
+                for r in z[key]:
+                    f.write(f"{r[0]} {r[1]} {r[2]} : " + " ".join(str(int(v)) for v in r[3:]) + " \n")
     return d + "/"
 
 

@@ -1,0 +1,118 @@
+"""GPU parity tests of the RGB path: colour transform + three independently coded component planes,
+through the C ABI, against the CPU oracle and against the outputs of the unmodified reference binary run with
+`-isRGB 1` (tests/golden, made by oracle/run_ref_golden.py).  Bit-exact for codestreams (lossless and lossy) and
+for lossless pixels; lossy pixels within +-1 on <= 1e-4 of the samples (the reference's inverse uses fast-math)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import oracle as O  # noqa: E402  (checker only)
+from picsong_b200 import codec, synth  # noqa: E402
+
+STILLS = ["rgb128_wl2_ll", "rgb256x192_wl3_ll", "rgb256x192_wl3_q1", "rgb200x150_wl2_q05"]
+VIDEOS = ["rgbv128_f3_wl2_ll", "rgbv256_f2_wl3_q1"]
+
+
+def _luts(lut_root, folder, wl):
+    d = f"{lut_root}/{folder}/"
+    return [O.lut_load(d, wl, c) for c in range(3)], codec.load_lut(d, wl, rgb=True)
+
+
+@pytest.mark.parametrize("name", STILLS)
+def test_rgb_stages_against_oracle(name, golden, lut_root):
+    e = golden.manifest[name]
+    W, H, wl, lossy, qs = e["W"], e["H"], e["wl"], bool(e["type"]), e["qs"]
+    oluts, plut = _luts(lut_root, e["lut"], wl)
+    rgb = synth.synth_rgb(W, H)
+    cd = codec.Codec(codec.Params(W, H, wl, lossy, qs, rgb=True), plut)
+    assert cd.planes == 3
+    px = torch.from_numpy(rgb).cuda()[None]
+    # colour transform + DWT: coefficients of the three planes
+    comps = O.rgb_forward(np.stack([O.pad_mirror(rgb[c]) for c in range(3)]), lossy)
+    Wa, Ha = O.adapted_dims(W, H)
+    import ctypes as C
+    oq = []
+    for c in range(3):
+        if lossy:
+            cf = np.empty((Ha, Wa), dtype=np.float32)
+            assert O.lib().pcso_dwt97_forward_plane(O._p(comps[c], C.c_float), Wa, Ha, wl, C.c_float(qs), O._p(cf, C.c_float)) == 0
+            oq.append(O.truncate(cf))
+        else:
+            q = np.empty((Ha, Wa), dtype=np.int32)
+            assert O.lib().pcso_dwt53_forward_plane(O._p(comps[c], C.c_int32), Wa, Ha, wl, O._p(q, C.c_int32)) == 0
+            oq.append(q)
+    gq = cd.dwt_forward(px, trunc_to_int=True)
+    assert gq.shape[0] == 3
+    for c in range(3):
+        assert np.array_equal(gq[c].cpu().numpy(), oq[c]), f"component {c} coefficients differ"
+    # coder + bit-stream builder, per component table
+    cw, sizes = cd.bpc_encode(gq)
+    ref_layout = cd.export_ref_codestream(cw, sizes).cpu().numpy()
+    stream, off = cd.bsb_pack(cw, sizes, 0)
+    off_h = off.cpu().numpy()
+    gs = stream[: off_h[-1]].cpu().numpy().view(np.uint16)
+    ostreams = O.encode_rgb_frame(rgb, wl, lossy, qs, oluts, [True, False, False])
+    for c in range(3):
+        ocs, osz = O.bpc_encode(oq[c], wl, oluts[c])
+        assert np.array_equal(sizes[c].cpu().numpy(), osz)
+        assert np.array_equal(ref_layout[c], ocs)
+        assert np.array_equal(gs[off_h[c]:off_h[c + 1]], ostreams[c]), f"component {c} stream differs"
+    # inverse chain
+    cw_b, sizes_b = cd.bsb_unpack(stream, off)
+    q = cd.bpc_decode(cw_b, sizes_b)
+    for c in range(3):
+        assert np.array_equal(q[c].cpu().numpy(), oq[c])
+    out = cd.dwt_inverse(q)[0].cpu().numpy()
+    expect = O.decode_rgb_frame(ostreams, Wa, Ha, wl, lossy, qs, oluts)[:, :H, :W]
+    assert np.array_equal(out, expect), "decoded RGB differs from the oracle"
+    if not lossy:
+        assert np.array_equal(out, rgb)
+    cd.close()
+
+
+@pytest.mark.parametrize("name", STILLS + VIDEOS)
+def test_rgb_frames_against_reference_golden(name, golden, lut_root):
+    e = golden.manifest[name]
+    W, H, wl, lossy, qs, F = e["W"], e["H"], e["wl"], bool(e["type"]), e["qs"], e["frames"]
+    _, plut = _luts(lut_root, e["lut"], wl)
+    n = max(F, 1)
+    frames = np.stack([synth.synth_rgb(W, H, f if F else 0) for f in range(n)])
+    ref = golden.stream(name)
+    ref_lens = np.array([int(t) for t in e["size_text"].split(",")], dtype=np.int32)
+    for max_batch in sorted({1, n}):
+        cd = codec.Codec(codec.Params(W, H, wl, lossy, qs, frames=F, max_batch=max_batch, rgb=True), plut)
+        stream, lens = cd.encode_frames(frames)
+        assert np.array_equal(lens, ref_lens), (name, max_batch)
+        assert np.array_equal(stream, ref), f"{name}: codestream differs from the reference binary's"
+        dec = cd.decode_frames(ref, ref_lens)
+        if not lossy:
+            assert np.array_equal(dec, frames)
+        elif W % 64 == 0:  # (for other widths the reference's output is its flat-crop quirk, covered for grey)
+            refdec = golden.decoded(name).reshape(dec.shape)
+            d = np.abs(dec.astype(np.int32) - refdec.astype(np.int32))
+            assert d.max() <= 1 and (d != 0).mean() <= 1e-4, (name, int(d.max()), float((d != 0).mean()))
+        cd.close()
+
+
+def test_rgb_full_size_sha(golden, lut_root):
+    """2048x2048 RGB stills: sha256 of the reference binary's stream, and its `_SIZE` text."""
+    import hashlib
+    for name in ("rgb2048_wl5_ll", "rgb2048_wl5_q1"):
+        e = golden.manifest[name]
+        W, H, wl, lossy = e["W"], e["H"], e["wl"], bool(e["type"])
+        _, plut = _luts(lut_root, e["lut"], wl)
+        cd = codec.Codec(codec.Params(W, H, wl, lossy, e["qs"], rgb=True), plut)
+        rgb = synth.synth_rgb(W, H)
+        stream, lens = cd.encode_frames(rgb[None])
+        assert ",".join(str(int(v)) for v in lens) == e["size_text"]
+        assert hashlib.sha256(stream.tobytes()).hexdigest() == e["enc_sha256"], name
+        dec = cd.decode_frames(stream, lens)[0]
+        if lossy:
+            mse = np.mean((dec.astype(np.float64) - rgb) ** 2)
+            assert abs(10 * np.log10(255.0 ** 2 / mse) - e["dec_psnr"]) <= 0.01
+        else:
+            assert np.array_equal(dec, rgb)
+        cd.close()

@@ -182,3 +182,35 @@ def test_lane_classification_pins_block0(golden, lut_root):
     q = O.dwt53_forward(O.pad_mirror(golden.input("s128_wl2_ll")), 2)
     cs, sz = O.bpc_encode(q, 2, lut)
     assert sz[0] == ref[10]
+
+
+RGB_CASES = ["rgb128_wl2_ll", "rgb256x192_wl3_ll", "rgb256x192_wl3_q1", "rgb200x150_wl2_q05", "rgbv128_f3_wl2_ll", "rgbv256_f2_wl3_q1"]
+
+
+@pytest.mark.parametrize("name", RGB_CASES)
+def test_oracle_rgb_matches_reference_binary(name, golden, lut_root):
+    """RGB path of the oracle (colour transform, three component streams with the R/G/B tables, header placement)
+    against the unmodified reference binary run with -isRGB 1: streams and _SIZE values byte for byte."""
+    from picsong_b200 import synth
+    e = golden.manifest[name]
+    W, H, wl, lossy, qs, F = e["W"], e["H"], e["wl"], bool(e["type"]), e["qs"], e["frames"]
+    luts = [O.lut_load(f"{lut_root}/{e['lut']}/", wl, c) for c in range(3)]
+    sizes = [int(t) for t in e["size_text"].split(",")]
+    out = []
+    for f in range(max(F, 1)):
+        rgb = synth.synth_rgb(W, H, f if F else 0)
+        out += O.encode_rgb_frame(rgb, wl, lossy, qs, luts, [True, False, False] if not F else [f == 0] * 3, frames=F)
+    assert [s.size for s in out] == sizes
+    assert np.array_equal(np.concatenate(out), golden.stream(name))
+    Wa, Ha = O.adapted_dims(W, H)
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    ref = golden.stream(name)
+    for f in range(max(F, 1)):
+        d = O.decode_rgb_frame([ref[off[3 * f + c]:off[3 * f + c + 1]] for c in range(3)], Wa, Ha, wl, lossy, qs, luts)[:, :H, :W]
+        src = synth.synth_rgb(W, H, f if F else 0)
+        if not lossy:
+            assert np.array_equal(d, src)
+        elif W % 64 == 0:
+            r = golden.decoded(name).reshape(max(F, 1), 3, H, W)[f]
+            diff = np.abs(d.astype(np.int32) - r.astype(np.int32))
+            assert diff.max() <= 1 and (diff != 0).mean() <= 1e-4
