@@ -51,3 +51,33 @@ def test_cli_still_and_video(tmp_path, golden, lut_root):
     # ---- invalid parameters: the reference's message and exit(-1) ----
     rc, out = run(["-cd", 0, "-wl", 11, "-i", raw, "-o", enc, "-xSize", 256, "-ySize", 256])
     assert rc == 255 and "Incorrect parameters. Please choose valid values." in out
+
+
+def test_cli_rgb(tmp_path, golden, lut_root):
+    """-isRGB 1: planar RGB in, stream + _SIZE identical to the reference binary's, planar RAW out (README.md:105-115)."""
+    from picsong_b200 import synth
+    e = golden.manifest["rgb256x192_wl3_ll"]
+    raw, enc, dec = tmp_path / "c.raw", tmp_path / "c.pcs", tmp_path / "c.out"
+    synth.synth_rgb(256, 192).tofile(raw)
+    rc, out = run(["-cd", 0, "-wl", 3, "-cp", 2, "-type", 0, "-qs", 1, "-i", raw, "-o", enc, "-cbWidth", 64, "-cbHeight", 18,
+                   "-xSize", 256, "-ySize", 192, "-video", 0, "-isRGB", 1, "-LUTFolder", f"{lut_root}/n1_lossless/", "-k", 0])
+    assert rc == 0, out
+    assert np.array_equal(np.fromfile(enc, dtype=np.uint16), golden.stream("rgb256x192_wl3_ll"))
+    assert open(str(enc) + "_SIZE").read() == e["size_text"]
+    rc, out = run(["-cd", 1, "-i", enc, "-o", dec, "-LUTFolder", f"{lut_root}/n1_lossless/", "-video", 0])
+    assert rc == 0, out
+    assert np.array_equal(np.fromfile(dec, dtype=np.uint8), synth.synth_rgb(256, 192).reshape(-1))
+    # RGB video, lossy
+    e = golden.manifest["rgbv256_f2_wl3_q1"]
+    raw, enc, dec = tmp_path / "cv.raw", tmp_path / "cv.pcs", tmp_path / "cv.out"
+    np.stack([synth.synth_rgb(256, 256, f) for f in range(2)]).tofile(raw)
+    rc, out = run(["-cd", 0, "-wl", 3, "-cp", 2, "-type", 1, "-qs", 1.0, "-i", raw, "-o", enc, "-cbWidth", 64, "-cbHeight", 18,
+                   "-xSize", 256, "-ySize", 256, "-video", 1, "-frames", 2, "-isRGB", 1, "-numberOfStreams", 2,
+                   "-LUTFolder", f"{lut_root}/video_lossy/"])
+    assert rc == 0, out
+    assert np.array_equal(np.fromfile(enc, dtype=np.uint16), golden.stream("rgbv256_f2_wl3_q1"))
+    assert open(str(enc) + "_SIZE").read() == e["size_text"]
+    rc, out = run(["-cd", 1, "-i", enc, "-o", dec, "-LUTFolder", f"{lut_root}/video_lossy/", "-video", 1])
+    assert rc == 0, out
+    d = np.abs(np.fromfile(dec, dtype=np.uint8).astype(int) - golden.decoded("rgbv256_f2_wl3_q1").astype(int))
+    assert d.max() <= 1 and (d != 0).mean() <= 1e-4
