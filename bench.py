@@ -37,7 +37,10 @@ WORKLOADS = {
     "cfg2": (4096, 4096, 5, 1, 1.0, "n1_lossy", 8, "configs[1]: 4096x4096 8-bit grey, lossy 9/7 qs=1.0, wl=5, 64x64 codeblocks"),
     "cfg3": (7680, 4320, 6, 0, 1.0, "n1_lossless", 2, "configs[2]: 7680x4320 8-bit grey, lossless 5/3, wl=6, 64x64 codeblocks"),
     "cfg4": (3840, 2160, 5, 1, 1.0, "video_lossy", 8, "configs[3]: 3840x2160 8-bit grey video frames, lossy 9/7 qs=1, wl=5, frame-sharded"),
+    # SURVEY 8f.1 (the widening row): the reference README's own example shape, 2048x2560 RGB still, lossy
+    "rgb": (2048, 2560, 5, 1, 1.0, "n1_lossy", 4, "README example: 2048x2560 8-bit RGB (planar) stills, lossy 9/7 + ICT qs=1, wl=5"),
 }
+RGB_WORKLOADS = {"rgb"}
 
 
 class ClockSampler(threading.Thread):
@@ -114,9 +117,9 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_frames(W, H, n, first=0):
+def make_frames(W, H, n, first=0, rgb=False):
     from picsong_b200 import synth
-    return np.stack([synth.synth_frame(W, H, first + i) for i in range(n)])
+    return np.stack([(synth.synth_rgb if rgb else synth.synth_frame)(W, H, first + i) for i in range(n)])
 
 
 # --------------------------------------------------------------------------------------------------
@@ -134,15 +137,16 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     W, H, wl, lossy, qs, lutname, B, desc = WORKLOADS[args.workload]
     lroot = materialize_luts()
-    lut = codec.load_lut(f"{lroot}/{lutname}/", wl)
+    rgb = args.workload in RGB_WORKLOADS
+    lut = codec.load_lut(f"{lroot}/{lutname}/", wl, rgb=rgb)
     os.environ["PCS_STAGE_TIMING"] = "1"
-    cd = codec.Codec(codec.Params(W, H, wl, bool(lossy), qs, frames=0, max_batch=B), lut)
-    frames_h = make_frames(W, H, B, first=rank * B)
+    cd = codec.Codec(codec.Params(W, H, wl, bool(lossy), qs, frames=0, max_batch=B, rgb=rgb), lut)
+    frames_h = make_frames(W, H, B, first=rank * B, rgb=rgb)
     px = torch.from_numpy(frames_h).to(dev)
     stream = torch.empty(B * cd.max_words, dtype=torch.int16, device=dev)
-    off = torch.empty(B + 1, dtype=torch.int64, device=dev)
+    off = torch.empty(B * cd.planes + 1, dtype=torch.int64, device=dev)
     out = torch.empty_like(px)
-    lens_all = torch.zeros(world * B, dtype=torch.int32, device=dev)
+    lens_all = torch.zeros(world * B * cd.planes, dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > L2 (126 MB): evicts between timed iterations
 
     def step():
@@ -191,7 +195,7 @@ def run_ours(args):
         stage[i, 3:] = cd.last_stage_ms()
 
     # ---- DWT stage alone (roofline): pcs_dwt_forward over the batch, CUDA events on the launch stream ----
-    coeff = torch.empty((B, cd.Ha, cd.Wa), dtype=torch.int32, device=dev)
+    coeff = torch.empty((B * cd.planes, cd.Ha, cd.Wa), dtype=torch.int32, device=dev)
     import ctypes as C
     dw = []
     for i in range(max(args.steps, 5) + 2):
@@ -222,8 +226,8 @@ def run_ours(args):
         t1 = time.perf_counter()
         if i >= args.warmup:
             e2e_t.append(t1 - t0)
-        h2d = hp.nbytes + s.nbytes + 8 * (B + 1)
-        d2h = s.nbytes + ho.nbytes + 8 * (B + 1)
+        h2d = hp.nbytes + s.nbytes + 8 * (B * cd.planes + 1)
+        d2h = s.nbytes + ho.nbytes + 8 * (B * cd.planes + 1)
     e2e_ms = float(np.sum(e2e_t) * 1e3)
 
     # max over ranks
@@ -236,7 +240,7 @@ def run_ours(args):
     mpix_step = W * H * B * world / 1e6
     hbm, hbm_src = peaks()
     A = cd.A
-    dwt_gbs = 5.0 * A * B / (dwt_ms * 1e-3) / 1e9
+    dwt_gbs = 5.0 * A * B * cd.planes / (dwt_ms * 1e-3) / 1e9
     res = {
         "metric": "encode+decode round-trip throughput (Mpix/s, original W*H*frames over encode time + decode time)",
         "value": mpix_step * args.steps / (total_ms * 1e-3), "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
@@ -252,7 +256,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"kernel": "dwt_forward (all levels of the batch; u8 in -> 32-bit Mallat coefficients out)", "bound": "hbm",
                      "achieved": dwt_gbs, "peak": hbm, "peak_source": hbm_src, "unit": "GB/s", "frac": dwt_gbs / hbm,
-                     "algorithmic_bytes_per_launch": 5 * A * B, "ms": dwt_ms, "traffic": None,
+                     "algorithmic_bytes_per_launch": 5 * A * B * cd.planes, "ms": dwt_ms, "traffic": None,
                      "launches_per_call": "one per wavelet level (5)"},
     }
     tr = measured_traffic()
@@ -266,7 +270,7 @@ def run_ours(args):
                       "share_of_step": float((m[1] + m[4]) / m.sum())}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            res["cpu_baseline"] = cpu_baseline(W, H, wl, lossy, qs, f"{lroot}/{lutname}/")
+            res["cpu_baseline"] = cpu_baseline(W, H, wl, lossy, qs, f"{lroot}/{lutname}/") if not rgb else None
         print(json.dumps(res))
     if world > 1:
         dist.destroy_process_group()
@@ -300,6 +304,8 @@ def run_reference(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if lossy else "int32", "data": "synthetic", "impl": "reference",
             "config": {"workload": desc, "frames_per_step_per_gpu": B}}
     lroot = materialize_luts()
+    if args.workload in RGB_WORKLOADS:
+        return run_reference_rgb(args, base, lroot)
     if os.path.exists(harness):
         # the reference's own CUDA stage wrappers on this GPU, one frame per call as its API requires
         tmp = tempfile.mkdtemp(prefix="pcs_ref_")
@@ -329,6 +335,48 @@ def run_reference(args):
         cb = cpu_baseline(W, H, wl, lossy, qs, f"{lroot}/{lutname}/")
         print(json.dumps({**base, "value": cb["value"], "cpu_baseline": cb,
                           "e2e": {"value": cb["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_reference_rgb(args, base, lroot):
+    """RGB stills through the reference's own executable (its stage wrappers have no RGB entry point of their own:
+    the colour transform lives in CodingEngine/DecodingEngine).  Time = what the binary itself reports as "time spent
+    ... without considering allocation periods" for encode and for decode (both include its device<->host copies,
+    the encode figure also its file writes to a tmpfs path); one still per run, median over the runs."""
+    import re
+    W, H, wl, lossy, qs, lutname, B, desc = WORKLOADS[args.workload]
+    exe = os.path.join(ROOT, "oracle", "_ref", "PICSONG_ref")
+    if not os.path.exists(exe):
+        print(json.dumps({**base, "unavailable": "oracle/_ref/PICSONG_ref not built"}))
+        return
+    tmp = tempfile.mkdtemp(prefix="pcs_ref_rgb_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    raw, enc, dec = os.path.join(tmp, "in.raw"), os.path.join(tmp, "o.pcs"), os.path.join(tmp, "o.raw")
+    make_frames(W, H, 1, rgb=True).tofile(raw)
+    lutdir = f"{lroot}/{lutname}/"
+    te, td = [], []
+    sampler = ClockSampler(0); sampler.start()
+    for i in range(args.warmup + args.steps):
+        for p in (enc, enc + "_SIZE", dec):
+            if os.path.exists(p):
+                os.remove(p)
+        oe = subprocess.run([exe, "-cd", "0", "-wl", str(wl), "-cp", "2", "-type", str(lossy), "-qs", repr(qs), "-i", raw, "-o", enc,
+                             "-cbWidth", "64", "-cbHeight", "18", "-xSize", str(W), "-ySize", str(H), "-video", "0", "-isRGB", "1",
+                             "-LUTFolder", lutdir, "-k", "0"], capture_output=True, text=True).stdout
+        od = subprocess.run([exe, "-cd", "1", "-i", enc, "-o", dec, "-LUTFolder", lutdir, "-video", "0"], capture_output=True, text=True).stdout
+        me = re.search(r"without considering allocation periods is: ([0-9.eE+-]+)", oe)
+        md = re.search(r"without considering allocation periods and I/O is: ([0-9.eE+-]+)", od)
+        if not (me and md):
+            print(json.dumps({**base, "unavailable": "could not parse the reference binary's timing lines"}))
+            return
+        if i >= args.warmup:
+            te.append(float(me.group(1))); td.append(float(md.group(1)))
+    clocks = sampler.stop()
+    t = float(np.median(te) + np.median(td))
+    v = W * H / 1e6 / t
+    print(json.dumps({**base, "value": v, "ms_per_step": t * 1e3 * B, "encode_mpix_s": W * H / 1e6 / float(np.median(te)),
+                      "decode_mpix_s": W * H / 1e6 / float(np.median(td)), "clocks": clocks,
+                      "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": 0, "kind": "reference",
+                                       "sample": "the reference's own executable (sm_100 build) on this B200, one RGB still per run, its own reported times"},
+                      "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 def main():
