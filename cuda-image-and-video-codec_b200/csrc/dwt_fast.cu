@@ -27,6 +27,23 @@ constexpr float kA = -1.586134342059924f, kB = -0.052980118572961f, kG = 0.88291
                 kD = 0.443506852043971f, kK = 1.230174104914001f, kIK = 0.812893066f;
 constexpr unsigned kFullMask = 0xffffffffu;
 
+// ---- packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2: two IEEE-rn fp32 operations per issued instruction,
+// bit-identical to the scalar __fadd_rn / __fmul_rn / __fmaf_rn with -ftz) --------------------------------
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk(f2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 d; asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 shfl_down2(f2 v) {
+  float a, b; upk(v, a, b);
+  return pk(__shfl_down_sync(kFullMask, a, 1), __shfl_down_sync(kFullMask, b, 1));
+}
+__device__ __forceinline__ f2 shfl_up2(f2 v) {
+  float a, b; upk(v, a, b);
+  return pk(__shfl_up_sync(kFullMask, a, 1), __shfl_up_sync(kFullMask, b, 1));
+}
+
 struct FastFwdArgs {
   const void* src; long long src_fstride; int src_pitch;    // level input: u8 pixels (level 1) or the 32-bit LL plane of the level above
   int H;                                                    // u8 input: original height (rows >= H are mirror padding); else == Hc
@@ -112,6 +129,45 @@ __device__ __forceinline__ void hfwd97(float (&x)[N], float S, bool left, bool r
   for (int k = 0; k < P; ++k) { x[2 * k] = e[k]; x[2 * k + 1] = __fmul_rn(o[k], kK); }
 }
 
+// The same on BOTH rows of a row pair at once: sample j of the low row (pending scale 1/K) and of the high row
+// (pending scale K) travel as one packed pair, so every lifting operation is issued once for the two rows.
+template <int N, bool FUSED_SUM>
+__device__ __forceinline__ void hfwd97_rows(float (&lo)[N], float (&hi)[N], bool left, bool right) {
+  constexpr int P = N / 2;
+  const f2 S = pk(kIK, kK), A2 = pk(kA, kA), B2 = pk(kB, kB), G2 = pk(kG, kG), D2 = pk(kD, kD), IK2 = pk(kIK, kIK), K2 = pk(kK, kK);
+  f2 x[N], e[P], o[P];
+#pragma unroll
+  for (int j = 0; j < N; ++j) x[j] = pk(lo[j], hi[j]);
+#pragma unroll
+  for (int k = 0; k < P; ++k) e[k] = mul2(x[2 * k], S);
+  f2 n0 = shfl_down2(e[0]);
+  if (right) n0 = e[P - 1];
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    const f2 nxt = k + 1 < P ? e[k + 1] : n0;
+    o[k] = FUSED_SUM ? fma2(x[2 * k], S, nxt) : add2(e[k], nxt);
+  }
+#pragma unroll
+  for (int k = 0; k < P; ++k) o[k] = fma2(x[2 * k + 1], S, mul2(o[k], A2));
+  f2 p1 = shfl_up2(o[P - 1]);
+  if (left) p1 = o[0];
+#pragma unroll
+  for (int k = P - 1; k >= 0; --k) e[k] = fma2(add2(k ? o[k - 1] : p1, o[k]), B2, e[k]);
+  n0 = shfl_down2(e[0]);
+  if (right) n0 = e[P - 1];
+#pragma unroll
+  for (int k = 0; k < P; ++k) o[k] = fma2(add2(e[k], k + 1 < P ? e[k + 1] : n0), G2, o[k]);
+  p1 = shfl_up2(o[P - 1]);
+  if (left) p1 = o[0];
+#pragma unroll
+  for (int k = P - 1; k >= 0; --k) e[k] = mul2(fma2(add2(k ? o[k - 1] : p1, o[k]), D2, e[k]), IK2);
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    upk(e[k], lo[2 * k], hi[2 * k]);
+    upk(mul2(o[k], K2), lo[2 * k + 1], hi[2 * k + 1]);
+  }
+}
+
 // ---- vertical analysis pipelines (state per column) ------------------------------------------------
 // 5/3: step m consumes rows 2m+1, 2m+2 and produces row pair m.  d[n] = x[2n+1] - ((x[2n]+x[2n+2])>>1),
 // s[n] = x[2n] + ((d[n-1]+d[n]+2)>>2)  (DWTGenerator.cu:72-76,137-157).
@@ -163,16 +219,37 @@ struct V97 {
   }
 };
 
+// V97::step without border rules, two columns per instruction
+template <int N>
+__device__ __forceinline__ void v97_step_packed(V97<N>& v, const float (&xo)[N], const float (&x2)[N], float (&lo)[N], float (&hi)[N]) {
+  const f2 A2 = pk(kA, kA), B2 = pk(kB, kB), G2 = pk(kG, kG), D2 = pk(kD, kD);
+#pragma unroll
+  for (int j = 0; j < N; j += 2) {
+    const f2 xe = pk(v.xe[j], v.xe[j + 1]), xn = pk(x2[j], x2[j + 1]), o1p = pk(v.o1p[j], v.o1p[j + 1]);
+    const f2 e1p = pk(v.e1p[j], v.e1p[j + 1]), o2pp = pk(v.o2pp[j], v.o2pp[j + 1]);
+    const f2 o1 = fma2(add2(xe, xn), A2, pk(xo[j], xo[j + 1]));
+    const f2 e1 = fma2(add2(o1p, o1), B2, xe);
+    const f2 o2 = fma2(add2(e1p, e1), G2, o1p);   // o2[m-1]
+    const f2 e2 = fma2(add2(o2pp, o2), D2, e1p);  // e2[m-1]
+    upk(e2, lo[j], lo[j + 1]); upk(o2, hi[j], hi[j + 1]);
+    v.xe[j] = x2[j]; v.xe[j + 1] = x2[j + 1];
+    upk(o1, v.o1p[j], v.o1p[j + 1]); upk(e1, v.e1p[j], v.e1p[j + 1]); upk(o2, v.o2pp[j], v.o2pp[j + 1]);
+  }
+}
+
 template <bool LOSSY, int N> struct VSel { using type = V53<N>; using T = int; };
 template <int N> struct VSel<true, N> { using type = V97<N>; using T = float; };
 
 // 8 pixels of a u8 row -> T (px - 128; for 5/3 the shift is applied to the LL output instead, which is
 // exact because every high-pass step is shift-invariant and the low-pass steps carry the offset through)
 __device__ __forceinline__ void unpack8(uint2 p, float (&v)[8]) {
+  const f2 C2 = pk(-8388736.0f, -8388736.0f);  // 2^23 + b - (2^23 + 128), exact
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    v[j] = __fadd_rn(__uint_as_float(__byte_perm(p.x, 0x4B000000u, 0x7540u + j)), -8388736.0f);      // 2^23 + b - (2^23 + 128)
-    v[4 + j] = __fadd_rn(__uint_as_float(__byte_perm(p.y, 0x4B000000u, 0x7540u + j)), -8388736.0f);
+  for (int j = 0; j < 4; j += 2) {
+    upk(add2(pk(__uint_as_float(__byte_perm(p.x, 0x4B000000u, 0x7540u + j)), __uint_as_float(__byte_perm(p.x, 0x4B000000u, 0x7541u + j))), C2),
+        v[j], v[j + 1]);
+    upk(add2(pk(__uint_as_float(__byte_perm(p.y, 0x4B000000u, 0x7540u + j)), __uint_as_float(__byte_perm(p.y, 0x4B000000u, 0x7541u + j))), C2),
+        v[4 + j], v[5 + j]);
   }
 }
 __device__ __forceinline__ void unpack8(uint2 p, int (&v)[8]) {
@@ -249,8 +326,12 @@ __device__ __forceinline__ void emit_pair(const T (&lo)[NS], const T (&hi)[NS], 
 #pragma unroll
   for (int k = 0; k < P; ++k) {
     if constexpr (LOSSY) {
-      v[0][k] = quant<OT, QS1>(lo[2 * k], q[0], qs); v[1][k] = quant<OT, QS1>(lo[2 * k + 1], q[1], qs);
-      v[2][k] = quant<OT, QS1>(hi[2 * k], q[2], qs); v[3][k] = quant<OT, QS1>(hi[2 * k + 1], q[3], qs);
+      // c * Q * qs, two rounded multiplies left to right (DWTGenerator.cu:403-419), low and high row packed
+      f2 e = mul2(pk(lo[2 * k], hi[2 * k]), pk(q[0], q[2])), o = mul2(pk(lo[2 * k + 1], hi[2 * k + 1]), pk(q[1], q[3]));
+      if (!QS1) { e = mul2(e, pk(qs, qs)); o = mul2(o, pk(qs, qs)); }
+      float t0, t1, t2, t3;
+      upk(e, t0, t2); upk(o, t1, t3);
+      v[0][k] = cvt<OT>(t0); v[1][k] = cvt<OT>(t1); v[2][k] = cvt<OT>(t2); v[3][k] = cvt<OT>(t3);
     } else {
       v[0][k] = lo[2 * k]; v[1][k] = lo[2 * k + 1]; v[2][k] = hi[2 * k]; v[3][k] = hi[2 * k + 1];
     }
@@ -367,13 +448,13 @@ __global__ void __launch_bounds__(128, 3) dwt_forward_fused(const FastFwdArgs a)
       pa = load_row(2 * m + 3); pb = load_row(2 * m + 4);
     }
     // borders of this level come from the folded loads, so no explicit rule here
-    if constexpr (LOSSY) v1.step(xo, x2, false, false, false, lo, hi);
+    if constexpr (LOSSY) v97_step_packed<8>(v1, xo, x2, lo, hi);
     else v1.step(xo, x2, false, lo, hi);
     const int pr = m - VP1::kDelay;  // row pair leaving the vertical pipeline
     if (pr < P0) continue;           // warm-up (warp-uniform)
     if constexpr (LOSSY) {
-      if (pair_variant(pr, a.nW1, a.ls1)) { hfwd97<8, true>(lo, kIK, left, right); hfwd97<8, true>(hi, kK, left, right); }
-      else { hfwd97<8, false>(lo, kIK, left, right); hfwd97<8, false>(hi, kK, left, right); }
+      if (pair_variant(pr, a.nW1, a.ls1)) hfwd97_rows<8, true>(lo, hi, left, right);
+      else hfwd97_rows<8, false>(lo, hi, left, right);
     } else {
       hfwd53<8>(lo, left, right);
       hfwd53<8>(hi, left, right);
