@@ -271,6 +271,15 @@ void pcs_destroy(pcs_ctx* c) {
   delete c;
 }
 
+// Pinned host memory for callers that stream frames from / to disk (the reference allocates its frame buffers
+// with cudaHostAlloc as well: Engines/CodingEngine.cu:129-131,289): copies from pinned buffers are truly
+// asynchronous, which is what lets pcs_encode_frames / pcs_decode_frames overlap PCIe with the kernels.
+void* pcs_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
+}
+void pcs_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 const char* pcs_last_error(const pcs_ctx* c) { return c ? c->err.c_str() : "no context"; }
 size_t pcs_frame_pixels(const pcs_ctx* c) { return c->A; }
 int32_t pcs_frame_codeblocks(const pcs_ctx* c) { return c->ncb; }

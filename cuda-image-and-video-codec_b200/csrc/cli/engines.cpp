@@ -5,11 +5,15 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <deque>
 #include <fstream>
 #include <iostream>
+#include <mutex>
 #include <sstream>
+#include <thread>
 
 namespace picsong {
 
@@ -45,9 +49,44 @@ pcs_ctx* Engine::makeContext(int maxBatch, unsigned flags) {
 static size_t batchFor(const Image* img, int frames) {
   // frames per launch: enough codeblocks to fill a B200 (>= ~9500 resident warps), bounded by memory
   const size_t px = (size_t)img->width * img->height * (img->isRGB ? 3 : 1);
-  size_t b = std::max<size_t>(1, (size_t)(40u << 20) / std::max<size_t>(px, 1));
+  size_t b = std::max<size_t>(1, (size_t)(128u << 20) / std::max<size_t>(px, 1));
   return std::min<size_t>(std::max<size_t>(b, 1), (size_t)std::max(frames, 1));
 }
+
+// ---- host pipeline (replaces readFileParallel / writeFileParallel and their flag-polled double
+// buffers, Engines/CodingEngine.cu:212-262,463-498, Engines/DecodingEngine.cu:241-298,441-520) ----------------
+// A reader thread fills pinned buffers from disk, the caller's thread runs the GPU calls, a writer thread drains
+// pinned output buffers to disk; kRing buffers of one batch each circulate through two bounded queues, so disk
+// reads of batch k+1, the GPU work of batch k and the disk write of batch k-1 overlap.
+namespace {
+
+constexpr int kRing = 3;
+
+template <class T>
+class Channel {  // bounded multi-producer/multi-consumer queue of small tokens
+ public:
+  void push(T v) { { std::lock_guard<std::mutex> l(m_); q_.push_back(v); } cv_.notify_all(); }
+  T pop() { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return !q_.empty(); }); T v = q_.front(); q_.pop_front(); return v; }
+ private:
+  std::mutex m_; std::condition_variable cv_; std::deque<T> q_;
+};
+
+struct Batch { int slot, f0, n; size_t words; };  // n == 0: end of stream; n < 0: the producer failed
+
+struct PinnedRing {
+  std::vector<uint8_t*> in; std::vector<uint16_t*> out; std::vector<std::vector<int32_t>> lens;
+  PinnedRing(size_t inBytes, size_t outWords, size_t nlens) {
+    for (int i = 0; i < kRing; ++i) {
+      in.push_back(static_cast<uint8_t*>(pcs_host_alloc(inBytes)));
+      out.push_back(static_cast<uint16_t*>(pcs_host_alloc(outWords * 2)));
+      lens.emplace_back(nlens);
+    }
+  }
+  bool ok() const { for (int i = 0; i < kRing; ++i) if (!in[i] || !out[i]) return false; return true; }
+  ~PinnedRing() { for (auto p : in) pcs_host_free(p); for (auto p : out) pcs_host_free(p); }
+};
+
+}  // namespace
 
 void CodingEngine::engineManager(int cType) {
   const bool video = cType == 1;
@@ -62,29 +101,54 @@ void CodingEngine::engineManager(int cType) {
   std::remove(_outputFile.c_str());                       // replaceExistingFile, IOManager.ipp:158-170
   std::remove((_outputFile + "_SIZE").c_str());
   std::ofstream out(_outputFile, std::ios::binary | std::ios::trunc);
-  std::vector<uint8_t> px((size_t)batch * fpx);
-  std::vector<uint16_t> stream((size_t)batch * pcs_frame_max_stream_words(ctx));
-  std::vector<int32_t> lens((size_t)batch * planes);
+  const size_t maxWords = (size_t)batch * pcs_frame_max_stream_words(ctx);
+  PinnedRing ring((size_t)batch * fpx, maxWords, (size_t)batch * planes);
+  if (!ring.ok()) die("pinned host allocation failed");
+  Channel<int> freeIn, freeOut;
+  Channel<Batch> filled, coded;
+  for (int i = 0; i < kRing; ++i) { freeIn.push(i); freeOut.push(i); }
+  std::string readErr;
+  std::thread reader([&] {
+    for (int f0 = 0; f0 < frames; f0 += batch) {
+      const int b = std::min(batch, frames - f0), slot = freeIn.pop();
+      in.read(reinterpret_cast<char*>(ring.in[slot]), (std::streamsize)((size_t)b * fpx));
+      if ((size_t)in.gcount() != (size_t)b * fpx) { readErr = "Input file is shorter than xSize*ySize*frames"; filled.push({slot, f0, -1, 0}); return; }
+      filled.push({slot, f0, b, 0});
+    }
+    filled.push({0, 0, 0, 0});
+  });
   std::ostringstream sizes;
+  std::thread writer([&] {
+    for (;;) {
+      const Batch w = coded.pop();
+      if (w.n <= 0) return;
+      out.write(reinterpret_cast<const char*>(ring.out[w.slot]), (std::streamsize)(w.words * 2));
+      for (int i = 0; i < w.n * planes; ++i) sizes << (w.f0 + i ? "," : "") << ring.lens[w.slot][i];
+      freeOut.push(w.slot);
+    }
+  });
   double gpuSeconds = 0;
-  for (int f0 = 0; f0 < frames; f0 += batch) {
-    const int b = std::min(batch, frames - f0);
-    in.read(reinterpret_cast<char*>(px.data()), (std::streamsize)((size_t)b * fpx));
-    if ((size_t)in.gcount() != (size_t)b * fpx) die("Input file is shorter than xSize*ySize*frames");
+  std::string err;
+  for (;;) {
+    const Batch r = filled.pop();
+    if (r.n <= 0) { if (r.n < 0) err = readErr; break; }
+    const int oslot = freeOut.pop();
     size_t total = 0;
     auto t0 = std::chrono::steady_clock::now();
-    const int rc = pcs_encode_frames(ctx, px.data(), b, f0, stream.data(), stream.size(), lens.data(), &total);
+    const int rc = pcs_encode_frames(ctx, ring.in[r.slot], r.n, r.f0, ring.out[oslot], maxWords, ring.lens[oslot].data(), &total);
     gpuSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    if (rc != 0) die(std::string("encode failed: ") + pcs_last_error(ctx) + " (" + std::to_string(rc) + ")");
-    out.write(reinterpret_cast<const char*>(stream.data()), (std::streamsize)(total * 2));
-    for (int i = 0; i < b * planes; ++i) sizes << (f0 + i ? "," : "") << lens[i];
+    freeIn.push(r.slot);
+    if (rc != 0) { err = std::string("encode failed: ") + pcs_last_error(ctx) + " (" + std::to_string(rc) + ")"; break; }
+    coded.push({oslot, r.f0, r.n, total});
   }
+  coded.push({0, 0, 0, 0});
+  writer.join();
+  if (!err.empty()) { reader.detach(); die(err); }
+  reader.join();
   out.close();
   if (video || planes == 3) {  // grey stills write no sidecar (IOManager.ipp:615-620); RGB stills do (CodingEngine.cu:566-577)
     std::ofstream s(_outputFile + "_SIZE", std::ios::binary | std::ios::trunc);
     s << sizes.str();
-  }
-  if (video || planes == 3) {
     std::cout << "The time spent with the app without considering allocation periods is: " << gpuSeconds << std::endl;
   }
   std::cout << "BPC acum time is: " << gpuSeconds << std::endl;  // whole GPU pipeline incl. PCIe (stages are fused)
@@ -126,22 +190,51 @@ void DecodingEngine::engineManager(int cType) {
   std::remove(_outputFile.c_str());
   std::ofstream out(_outputFile, std::ios::binary | std::ios::trunc);
   if (!video && planes == 1) out << "P5\n" << _img->width << " " << _img->height << "\n" << ((2 << (_img->bitDepth - 1)) - 1) << "\n";
-  std::vector<uint16_t> stream;
-  std::vector<uint8_t> px((size_t)batch * fpx);
+  const size_t maxWords = (size_t)batch * pcs_frame_max_stream_words(ctx);
+  // here the ring's "in" side holds pixels (output of the GPU) and its "out" side codestream words (input)
+  PinnedRing ring((size_t)batch * fpx, maxWords, 1);
+  if (!ring.ok()) die("pinned host allocation failed");
+  Channel<int> freeStream, freePx;
+  Channel<Batch> filled, decoded;
+  for (int i = 0; i < kRing; ++i) { freeStream.push(i); freePx.push(i); }
+  std::string readErr;
+  std::thread reader([&] {
+    for (int f0 = 0; f0 < frames; f0 += batch) {
+      const int b = std::min(batch, frames - f0), slot = freeStream.pop();
+      size_t words = 0;
+      for (int i = 0; i < b * planes; ++i) words += (size_t)std::max(lens[(size_t)f0 * planes + i], 0);
+      if (words > maxWords) { readErr = "frame lengths exceed the maximum stream size"; filled.push({slot, f0, -1, 0}); return; }
+      in.read(reinterpret_cast<char*>(ring.out[slot]), (std::streamsize)(words * 2));
+      if ((size_t)in.gcount() != words * 2) { readErr = "Codestream is shorter than its frame lengths"; filled.push({slot, f0, -1, 0}); return; }
+      filled.push({slot, f0, b, words});
+    }
+    filled.push({0, 0, 0, 0});
+  });
+  std::thread writer([&] {
+    for (;;) {
+      const Batch w = decoded.pop();
+      if (w.n <= 0) return;
+      out.write(reinterpret_cast<const char*>(ring.in[w.slot]), (std::streamsize)((size_t)w.n * fpx));
+      freePx.push(w.slot);
+    }
+  });
   double gpuSeconds = 0;
-  for (int f0 = 0; f0 < frames; f0 += batch) {
-    const int b = std::min(batch, frames - f0);
-    size_t words = 0;
-    for (int i = 0; i < b * planes; ++i) words += (size_t)lens[(size_t)f0 * planes + i];
-    stream.resize(words);
-    in.read(reinterpret_cast<char*>(stream.data()), (std::streamsize)(words * 2));
-    if ((size_t)in.gcount() != words * 2) die("Codestream is shorter than its frame lengths");
+  std::string err;
+  for (;;) {
+    const Batch r = filled.pop();
+    if (r.n <= 0) { if (r.n < 0) err = readErr; break; }
+    const int pslot = freePx.pop();
     auto t0 = std::chrono::steady_clock::now();
-    const int rc = pcs_decode_frames(ctx, stream.data(), lens.data() + (size_t)f0 * planes, b, px.data());
+    const int rc = pcs_decode_frames(ctx, ring.out[r.slot], lens.data() + (size_t)r.f0 * planes, r.n, ring.in[pslot]);
     gpuSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    if (rc != 0) die(std::string("decode failed: ") + pcs_last_error(ctx) + " (" + std::to_string(rc) + ")");
-    out.write(reinterpret_cast<const char*>(px.data()), (std::streamsize)((size_t)b * fpx));
+    freeStream.push(r.slot);
+    if (rc != 0) { err = std::string("decode failed: ") + pcs_last_error(ctx) + " (" + std::to_string(rc) + ")"; break; }
+    decoded.push({pslot, r.f0, r.n, 0});
   }
+  decoded.push({0, 0, 0, 0});
+  writer.join();
+  if (!err.empty()) { reader.detach(); die(err); }
+  reader.join();
   std::cout << "BPC acum time is: " << gpuSeconds << std::endl;
   pcs_destroy(ctx);
 }

@@ -354,7 +354,10 @@ __device__ __forceinline__ void emit_pair(const T (&lo)[NS], const T (&hi)[NS], 
 // One launch = one level (LEVELS = 1; LL -> scratch or, if last, -> out) or two fused levels (LEVELS = 2,
 // u8 input only).  SRC_U8: the input is the u8 frame (level 1), else the 32-bit LL plane of the level above.
 template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS, bool QS1>
-__global__ void __launch_bounds__(128, 3) dwt_forward_fused(const FastFwdArgs a) {
+#ifndef PCS_FWD_MINB
+#define PCS_FWD_MINB 3
+#endif
+__global__ void __launch_bounds__(128, PCS_FWD_MINB) dwt_forward_fused(const FastFwdArgs a) {
   using T = typename VSel<LOSSY, 8>::T;
   using VP1 = typename VSel<LOSSY, 8>::type;
   using VP2 = typename VSel<LOSSY, 4>::type;

@@ -46,6 +46,8 @@ SYMBOLS = {
     "pcs_export_ref_codestream": (_I32, [_VP, _VP, _VP, _VP, _I32, _VP]),
     "pcs_encode_frames": (_I32, [_VP, _VP, _I32, _I32, _VP, C.c_size_t, _VP, C.POINTER(C.c_size_t)]),
     "pcs_decode_frames": (_I32, [_VP, _VP, _VP, _I32, _VP]),
+    "pcs_host_alloc": (_VP, [C.c_size_t]),
+    "pcs_host_free": (None, [_VP]),
     "pcs_encode_device": (_I32, [_VP, _VP, _I32, _I32, _VP, _VP, _VP]),
     "pcs_decode_device": (_I32, [_VP, _VP, _VP, _I32, _VP, _VP]),
     "pcs_last_stage_ms": (_I32, [_VP, C.POINTER(C.c_float)]),

@@ -169,6 +169,11 @@ int32_t pcs_encode_frames(pcs_ctx* ctx, const uint8_t* h_pixels, int32_t nframes
 int32_t pcs_decode_frames(pcs_ctx* ctx, const uint16_t* h_stream, const int32_t* h_frame_len, int32_t nframes,
                           uint8_t* h_pixels);
 
+/* Pinned host buffers for the two calls above (the reference's frame buffers are cudaHostAlloc'd too,
+ * Engines/CodingEngine.cu:129-131,289).  NULL on failure. */
+void* pcs_host_alloc(size_t bytes);
+void pcs_host_free(void* p);
+
 /* Same, device-resident in and out (no PCIe), for throughput measurement and for callers that
  * keep frames on the GPU.  d_stream needs max_batch * pcs_frame_max_stream_words() capacity. */
 int32_t pcs_encode_device(pcs_ctx* ctx, const uint8_t* d_pixels, int32_t batch, int32_t first_frame_index,
