@@ -354,9 +354,8 @@ __global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* 
       const unsigned r0b = r0m & b0, r0n = r0m & ~b0, r1b = r1m & b1, r1n = r1m & ~b1;
       unsigned U = __reduce_or_sync(kFull, r0m | r1m);
       while (U) {
-        const int r = __ffs(U) - 1;
-        U &= U - 1;
-        const unsigned bitm = 1u << r;
+        const unsigned bitm = U & (0u - U);  // lowest row in which some lane refines
+        U ^= bitm;
         enc_step(r0b, r0n, bitm, pref, ac, out1, prec);
         enc_step(r1b, r1n, bitm, pref, ac, out1, prec);
       }
@@ -603,11 +602,10 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
       unsigned nb0 = 0, nb1 = 0;
       unsigned U = __reduce_or_sync(kFull, r0m | r1m);
       while (U) {
-        const int r = __ffs(U) - 1;
-        U &= U - 1;
-        const unsigned bitm = 1u << r;
-        nb0 |= dec_step(r0m, bitm, pref, ac, in1, prec) << r;
-        nb1 |= dec_step(r1m, bitm, pref, ac, in1, prec) << r;
+        const unsigned bitm = U & (0u - U);  // lowest row in which some lane refines
+        U ^= bitm;
+        nb0 |= (0u - dec_step(r0m, bitm, pref, ac, in1, prec)) & bitm;
+        nb1 |= (0u - dec_step(r1m, bitm, pref, ac, in1, prec)) & bitm;
       }
       B0 |= (u64)nb0 << sh; B1 |= (u64)nb1 << sh;
     }
