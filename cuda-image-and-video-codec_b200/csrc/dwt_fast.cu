@@ -601,6 +601,38 @@ __device__ __forceinline__ void hinv97(float (&x)[N], float rK, float rIK, bool 
   for (int k = 0; k < P; ++k) { x[2 * k] = e[k]; x[2 * k + 1] = o[k]; }
 }
 
+// The same on both rows of a row pair at once (packed pairs, see hfwd97_rows).
+template <int N>
+__device__ __forceinline__ void hinv97_rows(float (&lo)[N], float (&hi)[N], bool left, bool right) {
+  constexpr int P = N / 2;
+  const float rK = 1.0f / kK, rIK = 1.0f / kIK;
+  // fma(-(a+b), k, x) == fma(a+b, -k, x) bit for bit, so the negation moves into the constants
+  const f2 rK2 = pk(rK, rK), rIK2 = pk(rIK, rIK), nD = pk(-kD, -kD), nG = pk(-kG, -kG), nB = pk(-kB, -kB), nA = pk(-kA, -kA);
+  f2 x[N], e[P], o[P];
+#pragma unroll
+  for (int j = 0; j < N; ++j) x[j] = pk(lo[j], hi[j]);
+#pragma unroll
+  for (int k = 0; k < P; ++k) o[k] = mul2(x[2 * k + 1], rK2);
+  f2 p1 = shfl_up2(o[P - 1]);
+  if (left) p1 = o[0];
+#pragma unroll
+  for (int k = 0; k < P; ++k) e[k] = fma2(add2(k ? o[k - 1] : p1, o[k]), nD, mul2(x[2 * k], rIK2));
+  f2 n0 = shfl_down2(e[0]);
+  if (right) n0 = e[P - 1];
+#pragma unroll
+  for (int k = 0; k < P; ++k) o[k] = fma2(add2(e[k], k + 1 < P ? e[k + 1] : n0), nG, o[k]);
+  p1 = shfl_up2(o[P - 1]);
+  if (left) p1 = o[0];
+#pragma unroll
+  for (int k = P - 1; k >= 0; --k) e[k] = fma2(add2(k ? o[k - 1] : p1, o[k]), nB, e[k]);
+  n0 = shfl_down2(e[0]);
+  if (right) n0 = e[P - 1];
+#pragma unroll
+  for (int k = 0; k < P; ++k) o[k] = fma2(add2(e[k], k + 1 < P ? e[k + 1] : n0), nA, o[k]);
+#pragma unroll
+  for (int k = 0; k < P; ++k) { upk(e[k], lo[2 * k], hi[2 * k]); upk(o[k], lo[2 * k + 1], hi[2 * k + 1]); }
+}
+
 // vertical synthesis pipelines.  step(m) takes row pair m (after the horizontal pass) and releases an even
 // row kEven(m) and an odd row kOdd(m).
 template <int N>
@@ -646,6 +678,24 @@ struct IV97 {  // DWTGenerator.cu:110-122,230-272
     }
   }
 };
+// IV97::step, two columns per instruction
+template <int N>
+__device__ __forceinline__ void iv97_step_packed(IV97<N>& v, const float (&lo)[N], const float (&hi)[N], float (&re)[N], float (&ro)[N]) {
+  const float rK = 1.0f / kK, rIK = 1.0f / kIK;
+  const f2 rK2 = pk(rK, rK), rIK2 = pk(rIK, rIK), nD = pk(-kD, -kD), nG = pk(-kG, -kG), nB = pk(-kB, -kB), nA = pk(-kA, -kA);
+#pragma unroll
+  for (int j = 0; j < N; j += 2) {
+    const f2 opp = pk(v.opp[j], v.opp[j + 1]), e1p = pk(v.e1p[j], v.e1p[j + 1]), o1pp = pk(v.o1pp[j], v.o1pp[j + 1]), e0pp = pk(v.e0pp[j], v.e0pp[j + 1]);
+    const f2 op = mul2(pk(hi[j], hi[j + 1]), rK2);
+    const f2 e1 = fma2(add2(opp, op), nD, mul2(pk(lo[j], lo[j + 1]), rIK2));
+    const f2 o1p = fma2(add2(e1p, e1), nG, opp);     // o1[m-1]
+    const f2 e0p = fma2(add2(o1pp, o1p), nB, e1p);   // x[2(m-1)]
+    const f2 xo = fma2(add2(e0pp, e0p), nA, o1pp);   // x[2(m-2)+1]
+    upk(xo, ro[j], ro[j + 1]); upk(e0p, re[j], re[j + 1]);
+    upk(op, v.opp[j], v.opp[j + 1]); upk(e1, v.e1p[j], v.e1p[j + 1]); upk(o1p, v.o1pp[j], v.o1pp[j + 1]); upk(e0p, v.e0pp[j], v.e0pp[j + 1]);
+  }
+}
+
 template <bool LOSSY, int N> struct IVSel { using type = IV53<N>; };
 template <int N> struct IVSel<true, N> { using type = IV97<N>; };
 
@@ -756,10 +806,16 @@ __global__ void __launch_bounds__(128, 3) dwt_inverse_fast_kernel(const FastInvA
     if constexpr (DST_U8) {
       if (y >= a.H) return;
       unsigned b[8];
+      if constexpr (LOSSY) {  // clamp(rn((v + 128) + 0.01)), DecodingEngine.cu:714
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if constexpr (LOSSY) b[j] = sat_u8(__fadd_rn(__fadd_rn(v[j], 128.0f), 0.01f));  // DecodingEngine.cu:714
-        else b[j] = (unsigned)min(max(v[j] + 128, 0), 255);                                // :728
+        for (int j = 0; j < 8; j += 2) {
+          float t0, t1;
+          upk(add2(add2(pk(v[j], v[j + 1]), pk(128.0f, 128.0f)), pk(0.01f, 0.01f)), t0, t1);
+          b[j] = sat_u8(t0); b[j + 1] = sat_u8(t1);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] = (unsigned)min(max(v[j] + 128, 0), 255);  // :728
       }
       uint2 w;
       w.x = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
@@ -797,9 +853,8 @@ __global__ void __launch_bounds__(128, 3) dwt_inverse_fast_kernel(const FastInvA
       expand(cur, lo, hi);
       cur = load_pair(m + 1);  // prefetch
     }
-    if constexpr (LOSSY) { hinv97<8>(lo, 1.0f / kK, 1.0f / kIK, left, right); hinv97<8>(hi, 1.0f / kK, 1.0f / kIK, left, right); }
-    else { hinv53<8>(lo, left, right); hinv53<8>(hi, left, right); }
-    vp.step(lo, hi, re, ro);
+    if constexpr (LOSSY) { hinv97_rows<8>(lo, hi, left, right); iv97_step_packed<8>(vp, lo, hi, re, ro); }
+    else { hinv53<8>(lo, left, right); hinv53<8>(hi, left, right); vp.step(lo, hi, re, ro); }
     const int yo = VP::odd_row(m), ye = VP::even_row(m);
     if (wlane) {
       if (yo >= 2 * n0 && yo < 2 * n1) store_row(yo, ro);
