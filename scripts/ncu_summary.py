@@ -73,7 +73,7 @@ def full(path, out):
             f.write("\n")
 
 
-def traffic(path, out, workload="cfg2", frames=8, nlaunch=5):
+def traffic(path, out, workload="cfg2", frames=16, nlaunch=5):
     """dram bytes (read + write) of the first `nlaunch` dwt_forward launches of a --set full capture = one
     pcs_dwt_forward call over the bench batch -> profiles/dwt_traffic.json (bench.py's roofline.traffic)."""
     import json
