@@ -317,3 +317,38 @@ def test_batched_dwt_matches_single_frames(lossy, luts):
     if not lossy:
         assert torch.equal(p_all, px)
     cd.close()
+
+
+def test_decoder_survives_malformed_streams(luts):
+    """Hostile / damaged codestreams must not crash, hang or fault the GPU: the decoder clamps every size and slot it
+    reads from the stream (bsb_unpack_kernel, dec_step) and frame lengths are validated on the host.  The decoded
+    pixels are garbage by definition; what is checked is that every call returns and the context stays usable."""
+    W, H, wl = 256, 192, 3
+    _, plut = luts("n1_lossless", wl)
+    cd = codec.Codec(codec.Params(W, H, wl, False, 1.0, max_batch=2), plut)
+    img = synth.synth_frame(W, H)
+    good, lens = cd.encode_frames(img[None])
+    rng = np.random.default_rng(7)
+    for trial in range(12):
+        bad = good.copy()
+        kind = trial % 4
+        if kind == 0:    # random words everywhere behind the header
+            bad[9:] = rng.integers(0, 65536, bad.size - 9, dtype=np.uint16)
+        elif kind == 1:  # corrupt the per-block (MSB, size) table only
+            n = 2 * cd.ncb
+            bad[9:9 + n] = rng.integers(0, 65536, n, dtype=np.uint16)
+        elif kind == 2:  # flip a few bits in the codewords
+            idx = rng.integers(9 + 2 * cd.ncb, bad.size, 64)
+            bad[idx] ^= np.uint16(1) << rng.integers(0, 16, 64).astype(np.uint16)
+        else:            # all-ones sizes
+            bad[10:10 + 2 * cd.ncb:2] = 0xFFFF
+        out = cd.decode_frames(bad, lens)
+        assert out.shape == (1, H, W)
+    # lengths that cannot be right are rejected on the host with an error code, not passed to the GPU
+    with pytest.raises(codec.PcsError):
+        cd.decode_frames(good, np.array([5], dtype=np.int32))
+    with pytest.raises(codec.PcsError):
+        cd.decode_frames(good, np.array([2 ** 30], dtype=np.int32))
+    # the context still works
+    assert np.array_equal(cd.decode_frames(good, lens)[0], img)
+    cd.close()
