@@ -64,6 +64,7 @@ struct pcs_ctx {
   static constexpr int kSlots = 4;
   cudaStream_t sstream[kSlots] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t sev[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t kev[kSlots] = {nullptr, nullptr, nullptr, nullptr};  // "kernels of the slot's chunk are done"
   long long* d_soff = nullptr;     // [kSlots][planes + 1]
   void* d_sstatus = nullptr;       // [kSlots] look-back status areas
   size_t status_bytes = 0;
@@ -249,6 +250,7 @@ int32_t pcs_create(const pcs_params* params, pcs_ctx** out) {
   for (int i = 0; i < pcs_ctx::kSlots && e == cudaSuccess; ++i) {
     e = cudaStreamCreateWithFlags(&c->sstream[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->sev[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->kev[i], cudaEventDisableTiming);
   }
   for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
   if (e != cudaSuccess) { pcs_destroy(c); return (int)e; }
@@ -265,6 +267,7 @@ void pcs_destroy(pcs_ctx* c) {
   cudaFree(c->d_sstatus); cudaFree(c->d_soff);
   for (auto& s2 : c->sstream) if (s2) cudaStreamDestroy(s2);
   for (auto& e2 : c->sev) if (e2) cudaEventDestroy(e2);
+  for (auto& e2 : c->kev) if (e2) cudaEventDestroy(e2);
   dwt_aux_destroy(c->aux);
   if (c->stream) cudaStreamDestroy(c->stream);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -389,11 +392,21 @@ Slot make_slot(pcs_ctx* c, int k, int sb) {
   s.st = c->sstream[k]; s.ev = c->sev[k];
   return s;
 }
+// How many chunks may have kernels on the GPU at once.  The slot streams would otherwise share the SMs evenly, all
+// chunks in flight would finish together and their downloads would queue up behind each other at the end of the
+// call; with a depth of 2 a chunk still fills the partial last waves of its predecessor, but chunks complete in
+// order, one download apart, and uploads run ahead of the kernels (they are enqueued before the wait).
+int kernel_depth(int nslots) {
+  static const int env = [] { const char* e = std::getenv("PCS_PIPE_DEPTH"); return e ? std::atoi(e) : 2; }();
+  return std::max(1, std::min(env, nslots));
+}
 int slots_for(const pcs_ctx* c, int* sb) {
   // chunks of max_batch / (2 * slots) frames: fine enough that the first upload and the last download (the
   // parts of a call that cannot overlap anything) are short, coarse enough that a launch still fills the GPU
   const int n = std::min<int>(pcs_ctx::kSlots, c->p.max_batch);
   *sb = std::max(1, c->p.max_batch / (2 * n));
+  static const int env = [] { const char* e = std::getenv("PCS_PIPE_CHUNK"); return e ? std::atoi(e) : 0; }();
+  if (env > 0) *sb = std::max(1, std::min(env, c->p.max_batch / n));
   return n;
 }
 
@@ -427,18 +440,21 @@ int32_t pcs_encode_frames(pcs_ctx* c, const uint8_t* h_px, int32_t nframes, int3
   // `lag` downloads for the end of the call.
   static const int lag_env = [] { const char* e = std::getenv("PCS_PIPE_LAG"); return e ? std::atoi(e) : 2; }();
   const int lag = std::max(1, std::min(lag_env, nslots));
+  const int depth = kernel_depth(nslots);
   int finished = 0;
   for (int i = 0; i < nchunks; ++i) {
     while (finished <= i - nslots) { int rc = finish(finished++); if (rc) return rc; }  // frees the slot (same stream: ordered)
     Slot s = make_slot(c, i % nslots, sb);
     const int f0 = i * sb, b = std::min(sb, nframes - f0);
     PCS_CUDA_TRY(cudaMemcpyAsync(s.px, h_px + (size_t)f0 * fpx, (size_t)b * fpx, cudaMemcpyHostToDevice, s.st));
+    if (i >= depth && depth < nslots) PCS_CUDA_TRY(cudaStreamWaitEvent(s.st, c->kev[(i - depth) % nslots], 0));
     int rc = run_dwt_forward(c, s.w, s.px, s.w.coeff, true, b, s.st, nullptr);
     if (rc) return rc;
     rc = run_bpc_encode(c, s.w.coeff, false, s.w.cw, s.w.sizes, b, s.st);
     if (rc) return rc;
     rc = bsb_pack(s.w.cw, s.w.sizes, s.stream, s.d_off, s.w.status, bsb_args(c, b * nc, (first + f0) * nc), s.st);
     if (rc) return rc;
+    PCS_CUDA_TRY(cudaEventRecord(c->kev[i % nslots], s.st));
     PCS_CUDA_TRY(cudaMemcpyAsync(s.h_off, s.d_off, (size_t)(b * nc + 1) * sizeof(long long), cudaMemcpyDeviceToHost, s.st));
     PCS_CUDA_TRY(cudaEventRecord(s.ev, s.st));
     while (finished <= i - lag) { int rc2 = finish(finished++); if (rc2) return rc2; }
@@ -457,6 +473,7 @@ int32_t pcs_decode_frames(pcs_ctx* c, const uint16_t* h_stream, const int32_t* h
   const int nslots = slots_for(c, &sb);
   const int nchunks = (nframes + sb - 1) / sb;
   size_t consumed = 0;
+  const int depth = kernel_depth(nslots);
   for (int i = 0; i < nchunks; ++i) {
     Slot s = make_slot(c, i % nslots, sb);
     const int f0 = i * sb, b = std::min(sb, nframes - f0);
@@ -471,12 +488,14 @@ int32_t pcs_decode_frames(pcs_ctx* c, const uint16_t* h_stream, const int32_t* h
     PCS_CUDA_TRY(cudaMemcpyAsync(s.stream, h_stream + consumed, (size_t)off * 2, cudaMemcpyHostToDevice, s.st));
     PCS_CUDA_TRY(cudaMemcpyAsync(s.d_off, s.h_off, (size_t)(b * nc + 1) * sizeof(long long), cudaMemcpyHostToDevice, s.st));
     PCS_CUDA_TRY(cudaEventRecord(s.ev, s.st));
+    if (i >= depth && depth < nslots) PCS_CUDA_TRY(cudaStreamWaitEvent(s.st, c->kev[(i - depth) % nslots], 0));
     int rc = bsb_unpack(s.stream, s.d_off, s.w.cw, s.w.sizes, s.w.status, bsb_args(c, b * nc, 1), s.st);
     if (rc) return rc;
     rc = run_bpc_decode(c, s.w.cw, s.w.sizes, s.w.coeff, b, s.st);
     if (rc) return rc;
     rc = run_dwt_inverse(c, s.w, s.w.coeff, s.px, b, s.st, nullptr);
     if (rc) return rc;
+    PCS_CUDA_TRY(cudaEventRecord(c->kev[i % nslots], s.st));
     PCS_CUDA_TRY(cudaMemcpyAsync(h_px + (size_t)f0 * fpx, s.px, (size_t)b * fpx, cudaMemcpyDeviceToHost, s.st));
     consumed += (size_t)off;
   }
