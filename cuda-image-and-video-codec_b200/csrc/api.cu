@@ -24,8 +24,9 @@ namespace pcs {
 unsigned long long g_launches = 0;
 
 size_t dwt_scratch_elems(int Wa, int Ha, int wl);
-int dwt_forward(const uint8_t*, void*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t, DwtAux*);
-int dwt_forward_planes(const void*, void*, void*, int, int, int, bool, float, bool, int, cudaStream_t);
+int dwt_forward(const uint8_t*, void*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t, DwtAux*, void* qws);
+size_t dwt_queue_ws_bytes(int Wa, int Ha, int wl, int frames);
+int dwt_forward_planes(const void*, void*, void*, int, int, int, bool, float, bool, int, cudaStream_t, void* qws);
 int dwt_inverse_planes(const int32_t*, void*, void*, int, int, int, bool, float, int, cudaStream_t);
 int rgb_forward(const uint8_t*, void*, int, int, int, int, bool, int, cudaStream_t);
 int rgb_inverse(const void*, uint8_t*, int, int, int, int, bool, bool, int, cudaStream_t);
@@ -68,6 +69,8 @@ struct pcs_ctx {
   long long* d_soff = nullptr;     // [kSlots][planes + 1]
   void* d_sstatus = nullptr;       // [kSlots] look-back status areas
   size_t status_bytes = 0;
+  void* d_dwtq = nullptr;          // [1 + kSlots] work-queue counter areas of the forward DWT
+  size_t dwtq_bytes = 0;
   DwtAux* aux = nullptr;           // auxiliary streams of the batched DWT calls (device-buffer entry points)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -150,17 +153,18 @@ int build_prob_tables(pcs_ctx* c) {
 // ---- the stage chain on explicit workspace pointers (used by the device entry points and by the slots) ----
 struct Ws {
   void* scratch; void* status; void* tplanes; int32_t* coeff; uint16_t* cw; int32_t* sizes;
+  void* dwtq;  // counters of the forward DWT's work queue (one area per concurrent call)
 };
 
 int run_dwt_forward(pcs_ctx* c, const Ws& w, const uint8_t* d_px, void* d_coeff, bool out_int, int frames, cudaStream_t st, DwtAux* aux) {
   const pcs_params& p = c->p;
   if (c->ncomp == 1)
     return dwt_forward(d_px, d_coeff, w.scratch, p.width, p.height, c->Wa, c->Ha, p.wavelet_levels, p.lossy != 0, p.quant_size, out_int,
-                       frames, st, aux);
+                       frames, st, aux, w.dwtq);
   int rc = rgb_forward(d_px, w.tplanes, p.width, p.height, c->Wa, c->Ha, p.lossy != 0, frames, st);
   if (rc) return rc;
   return dwt_forward_planes(w.tplanes, d_coeff, w.scratch, c->Wa, c->Ha, p.wavelet_levels, p.lossy != 0, p.quant_size, out_int,
-                            frames * 3, st);
+                            frames * 3, st, w.dwtq);
 }
 
 int run_dwt_inverse(pcs_ctx* c, const Ws& w, const int32_t* d_q, uint8_t* d_px, int frames, cudaStream_t st, DwtAux* aux) {
@@ -243,6 +247,8 @@ int32_t pcs_create(const pcs_params* params, pcs_ctx** out) {
   alloc((void**)&c->d_off, (PL + 1) * sizeof(long long));
   c->status_bytes = (bsb_status_bytes(c->ncb, (int)PL) + 255) / 256 * 256;
   alloc(&c->d_sstatus, pcs_ctx::kSlots * c->status_bytes);
+  c->dwtq_bytes = (dwt_queue_ws_bytes(Wa, Ha, p.wavelet_levels, (int)PL) + 255) / 256 * 256;
+  alloc(&c->d_dwtq, (1 + pcs_ctx::kSlots) * c->dwtq_bytes);
   alloc((void**)&c->d_soff, pcs_ctx::kSlots * (PL + 1) * sizeof(long long));
   if (e == cudaSuccess) e = cudaHostAlloc((void**)&c->h_off, pcs_ctx::kSlots * (PL + 1) * sizeof(long long), cudaHostAllocDefault);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -264,7 +270,7 @@ void pcs_destroy(pcs_ctx* c) {
   cudaFree(c->d_scratch); cudaFree(c->d_status); cudaFree(c->d_px); cudaFree(c->d_tplanes); cudaFree(c->d_coeff); cudaFree(c->d_cw);
   cudaFree(c->d_sizes); cudaFree(c->d_stream); cudaFree(c->d_off);
   if (c->h_off) cudaFreeHost(c->h_off);
-  cudaFree(c->d_sstatus); cudaFree(c->d_soff);
+  cudaFree(c->d_sstatus); cudaFree(c->d_soff); cudaFree(c->d_dwtq);
   for (auto& s2 : c->sstream) if (s2) cudaStreamDestroy(s2);
   for (auto& e2 : c->sev) if (e2) cudaEventDestroy(e2);
   for (auto& e2 : c->kev) if (e2) cudaEventDestroy(e2);
@@ -293,7 +299,7 @@ uint64_t pcs_kernel_launch_count(void) { return g_launches; }
 #define CHECK_BATCH(c, batch) \
   if (!(c)) return PCS_E_ARG; \
   if ((batch) < 1 || (batch) > (c)->p.max_batch) return fail((c), PCS_E_BATCH, "batch exceeds max_batch")
-#define FULL_WS(c) Ws{(c)->d_scratch, (c)->d_status, (c)->d_tplanes, (c)->d_coeff, (c)->d_cw, (c)->d_sizes}
+#define FULL_WS(c) Ws{(c)->d_scratch, (c)->d_status, (c)->d_tplanes, (c)->d_coeff, (c)->d_cw, (c)->d_sizes, (c)->d_dwtq}
 
 int32_t pcs_dwt_forward(pcs_ctx* c, const uint8_t* d_px, void* d_coeff, int32_t trunc, int32_t batch, void* st) {
   CHECK_BATCH(c, batch);
@@ -381,6 +387,7 @@ Slot make_slot(pcs_ctx* c, int k, int sb) {
   Slot s;
   s.w.scratch = static_cast<char*>(c->d_scratch) + p0 * c->scratch_elems * 4;
   s.w.status = static_cast<char*>(c->d_sstatus) + (size_t)k * c->status_bytes;
+  s.w.dwtq = static_cast<char*>(c->d_dwtq) + (size_t)(1 + k) * c->dwtq_bytes;
   s.w.tplanes = c->d_tplanes ? static_cast<char*>(c->d_tplanes) + p0 * c->A * 4 : nullptr;
   s.w.coeff = c->d_coeff + p0 * c->A;
   s.w.cw = c->d_cw + p0 * c->A;

@@ -533,6 +533,7 @@ int dwt_forward_fast(const void*, bool, long long, int, int, int, int, void*, lo
 bool dwt_inverse_fast_ok(const void*, const void*, const void*, bool, int, long long, int, long long, int, int);
 int dwt_inverse_fast(const int32_t*, long long, int, const void*, long long, int, bool, int, int, void*, bool, long long, int, int, int, bool,
                      float, int, cudaStream_t);
+int dwt_forward_queue(const void*, bool, int, int, int, int, void*, void*, int, bool, float, bool, int, void*, cudaStream_t, int*);
 
 // PCS_DWT_FUSE = 0: per-level kernels of this file only; 1: streaming kernel of dwt_fast.cu, one level per launch
 // (default); 2: the same with levels 1+2 fused in one launch
@@ -708,7 +709,13 @@ static int group_frames(int frames, int wl) {  // PCS_DWT_GROUP: frames per grou
 }
 
 int dwt_forward(const uint8_t* d_px, void* d_coeff, void* d_scratch, int W, int H, int Wa, int Ha, int wl, bool lossy, float qs,
-                bool out_int, int frames, cudaStream_t st, DwtAux* aux) {
+                bool out_int, int frames, cudaStream_t st, DwtAux* aux, void* qws) {
+  if (qws) {  // all levels the streaming kernel can take in one persistent launch (dwt_fast.cu), the rest level by level
+    int done = 0;
+    const int rc = dwt_forward_queue(d_px, true, W, H, Wa, Ha, d_coeff, d_scratch, wl, lossy, qs, out_int, frames, qws, st, &done);
+    if (rc || done == wl) return rc;
+    if (done > 0) return dwt_forward_levels(d_px, d_coeff, d_scratch, W, H, Wa, Ha, wl, lossy, qs, out_int, frames, done + 1, wl, st);
+  }
   const int gf = aux ? group_frames(frames, wl) : 0;
   if (!gf) {
     // Levels 1 and 2 go sub-batch by sub-batch so that the LL1 planes level 1 writes (evict-last) are still in
@@ -790,7 +797,13 @@ int dwt_inverse(const int32_t* d_q, uint8_t* d_px, void* d_scratch, int W, int H
 
 // RGB path: the same transforms on colour-transformed 32-bit planes (`planes` = frames x 3 components).
 int dwt_forward_planes(const void* d_tplanes, void* d_coeff, void* d_scratch, int Wa, int Ha, int wl, bool lossy, float qs, bool out_int,
-                       int planes, cudaStream_t st) {
+                       int planes, cudaStream_t st, void* qws) {
+  if (qws) {
+    int done = 0;
+    const int rc = dwt_forward_queue(d_tplanes, false, Wa, Ha, Wa, Ha, d_coeff, d_scratch, wl, lossy, qs, out_int, planes, qws, st, &done);
+    if (rc || done == wl) return rc;
+    if (done > 0) return dwt_forward_levels(nullptr, d_coeff, d_scratch, Wa, Ha, Wa, Ha, wl, lossy, qs, out_int, planes, done + 1, wl, st, d_tplanes);
+  }
   return dwt_forward_levels(nullptr, d_coeff, d_scratch, Wa, Ha, Wa, Ha, wl, lossy, qs, out_int, planes, 1, wl, st, d_tplanes);
 }
 int dwt_inverse_planes(const int32_t* d_q, void* d_tplanes, void* d_scratch, int Wa, int Ha, int wl, bool lossy, float qs, int planes,

@@ -15,7 +15,14 @@
 // written, + LL2 (A/16 samples) for the remaining levels.  Lanes 0,1,30,31 are halo (level 1 needs
 // one neighbour lane, level 2 one more); image borders are handled by explicit mirror rules in the
 // lifting steps, so halo lanes outside the image never influence a result.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <queue>
 #include <type_traits>
+#include <vector>
 
 #include "pcs_common.cuh"
 
@@ -351,22 +358,22 @@ __device__ __forceinline__ void emit_pair(const T (&lo)[NS], const T (&hi)[NS], 
   }
 }
 
-// One launch = one level (LEVELS = 1; LL -> scratch or, if last, -> out) or two fused levels (LEVELS = 2,
-// u8 input only).  SRC_U8: the input is the u8 frame (level 1), else the 32-bit LL plane of the level above.
-template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS, bool QS1>
+// One work item = one 256-column strip x one chunk of row pairs of one frame, one level (LEVELS = 1; LL -> scratch or,
+// if last, -> out) or two fused levels (LEVELS = 2, u8 input only).  SRC_U8: the input is the u8 frame (level 1), else
+// the 32-bit LL plane of the level above.  COH: that plane was written by other SMs during this very launch (queue
+// kernel below), so it is read through L2 (ld.global.cg) instead of the non-coherent path.
+constexpr int kFwdDepth = 6;
+typedef unsigned char FwdRing[kFwdDepth][2][32][8];
 #ifndef PCS_FWD_MINB
 #define PCS_FWD_MINB 3
 #endif
-__global__ void __launch_bounds__(128, PCS_FWD_MINB) dwt_forward_fused(const FastFwdArgs a) {
+template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS, bool QS1, bool COH>
+__device__ __forceinline__ void fwd_item(const FastFwdArgs& a, const int strip, const int chunk, const int frame, FwdRing* const ringp) {
   using T = typename VSel<LOSSY, 8>::T;
   using VP1 = typename VSel<LOSSY, 8>::type;
   using VP2 = typename VSel<LOSSY, 4>::type;
   using RowT = typename std::conditional<SRC_U8, uint2, Row8<T>>::type;
   const int lane = threadIdx.x & 31;
-  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (item >= a.nstrips * a.nchunks) return;
-  const int frame = blockIdx.y;
-  const int strip = item % a.nstrips, chunk = item / a.nstrips;
   constexpr int kHalo = LEVELS;                        // halo lanes per side
   constexpr int kEff = (32 - 2 * kHalo) * 8;           // effective columns per strip
   const int Wc = a.Wc, Hc = a.Hc, hw1 = Wc >> 1, hh1 = Hc >> 1, hw2 = Wc >> 2, hh2 = Hc >> 2;
@@ -394,9 +401,8 @@ __global__ void __launch_bounds__(128, PCS_FWD_MINB) dwt_forward_fused(const Fas
   // bytes of the rows of the next kDepth steps into a per-warp shared-memory ring and reads them back
   // itself (no barrier needed); the deep prefetch hides the DRAM latency at 16 warps per SM.  32-bit
   // input (deeper levels, small): plain register prefetch one step ahead.
-  constexpr int kDepth = 6;
-  __shared__ __align__(16) unsigned char s_ring[SRC_U8 ? 4 : 1][SRC_U8 ? kDepth : 1][2][32][8];
-  auto& ring = s_ring[SRC_U8 ? (threadIdx.x >> 5) : 0];
+  constexpr int kDepth = kFwdDepth;
+  FwdRing& ring = *ringp;
   auto row_index = [&](int y) -> int {  // whole-sample fold at the borders of the level input, then the pad mapping
     int ys = y < 0 ? -y : (y >= Hc ? 2 * (Hc - 1) - y : y);
     if constexpr (SRC_U8) ys = ys < a.H ? ys : 2 * a.H - 1 - ys;
@@ -413,7 +419,8 @@ __global__ void __launch_bounds__(128, PCS_FWD_MINB) dwt_forward_fused(const Fas
     } else {
       RowT r;
       const auto* p4 = reinterpret_cast<const decltype(r.a)*>(srcT + (size_t)row_index(y) * a.src_pitch);
-      r.a = __ldg(p4); r.b = __ldg(p4 + 1);
+      if constexpr (COH) { r.a = __ldcg(p4); r.b = __ldcg(p4 + 1); }
+      else { r.a = __ldg(p4); r.b = __ldg(p4 + 1); }
       return r;
     }
   };
@@ -507,6 +514,14 @@ __global__ void __launch_bounds__(128, PCS_FWD_MINB) dwt_forward_fused(const Fas
   }
 }
 
+template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS, bool QS1>
+__global__ void __launch_bounds__(128, PCS_FWD_MINB) dwt_forward_fused(const FastFwdArgs a) {
+  __shared__ __align__(16) FwdRing s_ring[SRC_U8 ? 4 : 1];
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= a.nstrips * a.nchunks) return;
+  fwd_item<LOSSY, OT, SRC_U8, LEVELS, QS1, false>(a, item % a.nstrips, item / a.nstrips, blockIdx.y, &s_ring[SRC_U8 ? (threadIdx.x >> 5) : 0]);
+}
+
 // quantiser steps, [level-1][LL,HL,LH,HH] (DWT/DWTGenerator.cuh:168-179)
 const float kQ[10][4] = {
     {1.965908f, 1.0112865f, 1.0112865f, 0.52021784f}, {4.1224113f, 1.9968134f, 1.9968134f, 0.96721643f},
@@ -540,6 +555,200 @@ void launch(const FastFwdArgs& a, dim3 grid, cudaStream_t st) {
   else dwt_forward_fused<LOSSY, OT, SRC_U8, LEVELS, false><<<grid, 128, 0, st>>>(a);
 }
 
+
+// ---- all levels in ONE persistent launch: a dependency-ordered work queue ---------------------------------------
+// The per-level launches leave three things on the table: the gaps and partially filled last waves of wl launches,
+// the latency-bound deep levels running alone on an empty GPU, and a trip to HBM and back for every LL plane.  Here
+// the items of ALL levels of ALL frames sit in one list; warps take tickets in list order.  An item of level l >= 2
+// lists the chunks of level l-1 (same frame) whose LL rows it reads and waits until their per-chunk counters say
+// all strips are finished.  The host orders the list so that every item comes after the items it depends on
+// (ticket order == a topological order: a waiting warp only ever waits for warps that already run, so the queue
+// cannot deadlock whatever the residency) and at least `lag` tickets after the last of them (about a wave: by the
+// time a warp picks the item up, its producers have normally finished and their LL rows are still in L2).
+constexpr int kMaxQLevels = 7;  // the codestream header cannot carry more (Annex C.1)
+struct FwdQueueArgs {
+  FastFwdArgs lv[kMaxQLevels];
+  const int4* items;   // {level | frame << 8, strip, chunk, dep_lo | dep_hi << 16}
+  unsigned* ctr;       // [0]: ticket; [1 + (frame * nlevels + level) * maxchunks + chunk]: finished strips
+  int nitems, nlevels, maxchunks;
+};
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+#ifndef PCS_FWDQ_MINB
+#define PCS_FWDQ_MINB 4
+#endif
+template <bool LOSSY, typename OT, bool SRC_U8, bool QS1>
+__global__ void __launch_bounds__(128, PCS_FWDQ_MINB) dwt_forward_queue_kernel(const __grid_constant__ FwdQueueArgs q) {
+  __shared__ __align__(16) FwdRing s_ring[SRC_U8 ? 4 : 1];
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(q.ctr, 1u);
+    t = __shfl_sync(kFullMask, t, 0);
+    if (t >= (unsigned)q.nitems) break;
+    const int4 it = __ldg(q.items + t);
+    const int level = it.x & 0xff, frame = it.x >> 8;
+    unsigned* const cnt = q.ctr + 1 + ((size_t)frame * q.nlevels + level) * q.maxchunks;
+    if (level == 0) {
+      fwd_item<LOSSY, OT, SRC_U8, 1, QS1, false>(q.lv[0], it.y, it.z, frame, &s_ring[SRC_U8 ? (threadIdx.x >> 5) : 0]);
+      if constexpr (SRC_U8) cp_async_wait<0>();  // the ring is reused by this warp's next item
+    } else {
+      if (lane == 0) {
+        const unsigned* const dep = cnt - q.maxchunks;
+        const unsigned need = (unsigned)q.lv[level - 1].nstrips;
+        // (the spin bound only turns a host-side ordering bug into wrong output instead of a hung GPU)
+        unsigned spins = 0;
+        for (int c = it.w & 0xffff; c <= (it.w >> 16); ++c)
+          while (ld_acquire(dep + c) < need && ++spins < (1u << 23)) __nanosleep(64);
+      }
+      __syncwarp();
+      fwd_item<LOSSY, OT, false, 1, QS1, true>(q.lv[level], it.y, it.z, frame, nullptr);
+    }
+    if (level + 1 < q.nlevels) {  // publish: every lane's LL stores, then the count
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicAdd(cnt + it.z, 1u);
+    }
+  }
+}
+
+struct QueueGeo { int nstrips, nchunks, rp, hh; };
+
+// List scheduling with a lag (see above).  Level-1 items in frame / chunk / strip order form the backbone; an item
+// of a deeper level becomes ready when the last chunk it reads has been placed and is placed `lag` tickets later.
+std::vector<int4> build_queue(const QueueGeo* g, int nlevels, int frames, bool lossy, int lag) {
+  const int warm = lossy ? 2 : 1, delay = lossy ? 1 : 0;
+  struct Pending { long long at; int level, frame, chunk; };
+  auto later = [](const Pending& x, const Pending& y) {
+    if (x.at != y.at) return x.at > y.at;
+    if (x.frame != y.frame) return x.frame > y.frame;
+    if (x.level != y.level) return x.level > y.level;
+    return x.chunk > y.chunk;
+  };
+  std::priority_queue<Pending, std::vector<Pending>, decltype(later)> pend(later);
+  // placed[(frame, level, chunk)] = ticket of the chunk's LAST strip, -1 while not placed
+  int maxc = 0;
+  for (int l = 0; l < nlevels; ++l) maxc = std::max(maxc, g[l].nchunks);
+  std::vector<long long> placed((size_t)frames * nlevels * maxc, -1);
+  auto deps = [&](int l, int c, int* lo, int* hi) {  // chunks of level l-1 read by chunk c of level l
+    const int n0 = c * g[l].rp, n1 = std::min(n0 + g[l].rp, g[l].hh);
+    const int Hc = 2 * g[l].hh;  // rows of the level's input == LL rows of the level above
+    const int r0 = std::max(0, 2 * (n0 - warm)), r1 = std::min(Hc - 1, 2 * (n1 - 1 + delay) + 2);
+    *lo = r0 / g[l - 1].rp; *hi = std::min(r1 / g[l - 1].rp, g[l - 1].nchunks - 1);
+  };
+  std::vector<int4> out;
+  auto place = [&](int l, int f, int c) {
+    int lo = 0, hi = 0;
+    if (l) deps(l, c, &lo, &hi);
+    for (int s = 0; s < g[l].nstrips; ++s) out.push_back(make_int4(l | (f << 8), s, c, lo | (hi << 16)));
+    placed[((size_t)f * nlevels + l) * maxc + c] = (long long)out.size() - 1;
+    if (l + 1 < nlevels) {  // which chunks of the next level did this complete?
+      for (int c2 = 0; c2 < g[l + 1].nchunks; ++c2) {
+        int lo2, hi2; deps(l + 1, c2, &lo2, &hi2);
+        if (c < lo2 || c > hi2) continue;
+        long long last = -1; bool all = true;
+        for (int d = lo2; d <= hi2; ++d) {
+          const long long t = placed[((size_t)f * nlevels + l) * maxc + d];
+          if (t < 0) { all = false; break; }
+          last = std::max(last, t);
+        }
+        if (all && last == (long long)out.size() - 1) pend.push({last + lag, l + 1, f, c2});
+      }
+    }
+  };
+  auto flush = [&](bool all) {
+    while (!pend.empty() && (all || pend.top().at <= (long long)out.size())) {
+      const Pending p = pend.top(); pend.pop();
+      place(p.level, p.frame, p.chunk);
+    }
+  };
+  for (int f = 0; f < frames; ++f)
+    for (int c = 0; c < g[0].nchunks; ++c) { flush(false); place(0, f, c); }
+  flush(true);
+  return out;
+}
+
+struct QueueTable { int4* d_items = nullptr; int nitems = 0, maxchunks = 0; QueueGeo geo[kMaxQLevels]; };
+struct QueueKey {
+  int Wa, Ha, nlevels, lossy, frames, rp1, lag, dev;
+  bool operator<(const QueueKey& o) const { return std::memcmp(this, &o, sizeof(*this)) < 0; }
+};
+std::map<QueueKey, QueueTable> g_queue_tables;
+std::mutex g_queue_mutex;
+
+int env_int(const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; }
+
+int queue_resident_warps() {
+  static int n = [] {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms * PCS_FWDQ_MINB * 4;
+  }();
+  return n;
+}
+
+int queue_geo(int Wa, int Ha, int nlevels, int rp1, QueueGeo* geo) {
+  int maxchunks = 0;
+  for (int l = 0; l < nlevels; ++l) {
+    const int Wc = Wa >> l, hh = Ha >> (l + 1);
+    geo[l].nstrips = (Wc + 239) / 240;
+    geo[l].hh = hh;
+    geo[l].rp = std::min(std::max(8, (rp1 >> l) & ~3), (hh + 3) & ~3);
+    geo[l].nchunks = (hh + geo[l].rp - 1) / geo[l].rp;
+    maxchunks = std::max(maxchunks, geo[l].nchunks);
+  }
+  return maxchunks;
+}
+int queue_rp1() {
+  static const int rp1 = std::max(8, env_int("PCS_DWTQ_RP", 64) & ~3);
+  return rp1;
+}
+
+// Levels 1..nlevels of this geometry as one queue (items table cached per geometry and batch size).
+const QueueTable* queue_table(int Wa, int Ha, int nlevels, bool lossy, int frames) {
+  const int rp1 = queue_rp1();
+  static const int lag_pct = env_int("PCS_DWTQ_LAG", 125);  // percent of the resident warps
+  const int lag = (int)((long long)queue_resident_warps() * lag_pct / 100);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  QueueKey key;
+  std::memset(&key, 0, sizeof key);
+  key.Wa = Wa; key.Ha = Ha; key.nlevels = nlevels; key.lossy = lossy; key.frames = frames; key.rp1 = rp1; key.lag = lag; key.dev = dev;
+  std::lock_guard<std::mutex> lk(g_queue_mutex);
+  auto itf = g_queue_tables.find(key);
+  if (itf != g_queue_tables.end()) return &itf->second;
+  QueueTable t;
+  t.maxchunks = queue_geo(Wa, Ha, nlevels, rp1, t.geo);
+  const std::vector<int4> items = build_queue(t.geo, nlevels, frames, lossy, lag);
+  t.nitems = (int)items.size();
+  if (cudaMalloc(&t.d_items, items.size() * sizeof(int4)) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(t.d_items, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  return &g_queue_tables.emplace(key, t).first->second;
+}
+
+template <bool LOSSY, typename OT, bool SRC_U8, bool QS1>
+void launch_queue_k(const FwdQueueArgs& q, cudaStream_t st) {
+  static const int resident = [] {  // CTAs the whole GPU holds at once: a persistent grid needs no more
+    int dev = 0, sms = 148, per_sm = PCS_FWDQ_MINB;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwt_forward_queue_kernel<LOSSY, OT, SRC_U8, QS1>, 128, 0);
+    return sms * std::max(per_sm, 1);
+  }();
+  const int grid = std::min(resident, (q.nitems + 3) / 4);
+  dwt_forward_queue_kernel<LOSSY, OT, SRC_U8, QS1><<<grid, 128, 0, st>>>(q);
+}
+template <bool LOSSY, typename OT, bool SRC_U8>
+void launch_queue(const FwdQueueArgs& q, cudaStream_t st) {
+  if (q.lv[0].qs == 1.0f) launch_queue_k<LOSSY, OT, SRC_U8, true>(q, st);
+  else launch_queue_k<LOSSY, OT, SRC_U8, false>(q, st);
+}
 
 // =================================================================================================
 // inverse
@@ -921,6 +1130,78 @@ int dwt_forward_fast(const void* src, bool src_u8, long long src_fstride, int sr
     else launch<true, float, false, 1>(a, grid, st);
   }
   ++g_launches;
+  return (int)cudaGetLastError();
+}
+
+// ---- queue path: host side --------------------------------------------------------------------------------------
+static size_t queue_scratch_elems(int Wa, int Ha, int wl) {
+  size_t n = 0;
+  for (int l = 1; l < wl; ++l) n += (size_t)(Wa >> l) * (Ha >> l);
+  return n;
+}
+static size_t queue_ll_offset(int Wa, int Ha, int l) {
+  size_t n = 0;
+  for (int k = 1; k < l; ++k) n += (size_t)(Wa >> k) * (Ha >> k);
+  return n;
+}
+
+// Bytes of counter workspace a queue launch over `frames` frames needs (one area per concurrent call).
+size_t dwt_queue_ws_bytes(int Wa, int Ha, int wl, int frames) {
+  QueueGeo geo[kMaxQLevels];
+  const int nl = std::min(wl, kMaxQLevels);
+  const int maxchunks = queue_geo(Wa, Ha, nl, queue_rp1(), geo);
+  return (1 + (size_t)frames * nl * maxchunks) * sizeof(unsigned);
+}
+
+// Levels 1..*done of the forward transform in one persistent launch; *done = 0 (and nothing launched) if the queue
+// does not apply to this geometry / batch, in which case the per-level path takes all levels.  src: the u8 frames
+// (src_u8) or 32-bit colour-transformed planes [frames][Ha][Wa].
+int dwt_forward_queue(const void* src, bool src_u8, int W, int H, int Wa, int Ha, void* d_coeff, void* d_scratch, int wl, bool lossy,
+                      float qs, bool out_int, int frames, void* ws, cudaStream_t st, int* done) {
+  *done = 0;
+  static const int mode = env_int("PCS_DWT_QUEUE", 0);
+  static const int min_mpix = env_int("PCS_DWTQ_MIN_MPIX", 8);
+  const size_t A = (size_t)Wa * Ha, S = queue_scratch_elems(Wa, Ha, wl);
+  if (!mode || !ws || S % 4 || (long long)frames * (long long)A < (long long)min_mpix * 1000000LL || frames >= (1 << 22)) return 0;
+  FwdQueueArgs q{};
+  int nl = 0;
+  for (int l = 1; l <= wl && nl < kMaxQLevels; ++l) {
+    const int Wc = Wa >> (l - 1), Hc = Ha >> (l - 1);
+    const bool u8 = l == 1 && src_u8;
+    const void* lsrc = l == 1 ? src : static_cast<const char*>(d_scratch) + queue_ll_offset(Wa, Ha, l - 1) * 4;
+    const long long sfs = u8 ? (long long)W * H : l == 1 ? (long long)A : (long long)S;
+    const int sp = u8 ? W : Wc;
+    void* ll = l == wl ? nullptr : static_cast<char*>(d_scratch) + queue_ll_offset(Wa, Ha, l) * 4;
+    if (!dwt_forward_fast_ok(lsrc, d_coeff, ll, u8, sp, sfs, H, Wc, Hc, 1)) break;
+    FastFwdArgs& a = q.lv[nl++];
+    a.src = lsrc; a.src_fstride = sfs; a.src_pitch = sp; a.H = u8 ? H : Hc; a.Wc = Wc; a.Hc = Hc;
+    a.out = d_coeff; a.out_fstride = (long long)A; a.pitch = Wa;
+    a.ll = ll; a.ll_fstride = (long long)S; a.ll_pitch = Wa >> l;
+    a.last = l == wl;
+    for (int i = 0; i < 4; ++i) { a.q1[i] = kQ[l - 1][i]; a.q2[i] = kQ[l < 10 ? l : 9][i]; }
+    a.qs = qs;
+    variant_params(Hc, &a.nW1, &a.ls1);
+    variant_params(Hc >> 1, &a.nW2, &a.ls2);
+  }
+  if (nl < 2) return 0;
+  const QueueTable* t = queue_table(Wa, Ha, nl, lossy, frames);
+  if (!t) return (int)cudaErrorMemoryAllocation;
+  for (int i = 0; i < nl; ++i) { q.lv[i].nstrips = t->geo[i].nstrips; q.lv[i].rp = t->geo[i].rp; q.lv[i].nchunks = t->geo[i].nchunks; }
+  q.items = t->d_items; q.nitems = t->nitems; q.nlevels = nl; q.maxchunks = t->maxchunks;
+  q.ctr = static_cast<unsigned*>(ws);
+  cudaError_t e = cudaMemsetAsync(ws, 0, (1 + (size_t)frames * nl * t->maxchunks) * sizeof(unsigned), st);
+  if (e != cudaSuccess) return (int)e;
+  if (src_u8) {
+    if (!lossy) launch_queue<false, int, true>(q, st);
+    else if (out_int) launch_queue<true, int, true>(q, st);
+    else launch_queue<true, float, true>(q, st);
+  } else {
+    if (!lossy) launch_queue<false, int, false>(q, st);
+    else if (out_int) launch_queue<true, int, false>(q, st);
+    else launch_queue<true, float, false>(q, st);
+  }
+  ++g_launches;
+  *done = nl;
   return (int)cudaGetLastError();
 }
 

@@ -352,3 +352,40 @@ def test_decoder_survives_malformed_streams(luts):
     # the context still works
     assert np.array_equal(cd.decode_frames(good, lens)[0], img)
     cd.close()
+
+
+_QUEUE_SNIPPET = r"""
+import hashlib, sys
+sys.path[:0] = [{root!r}, {pkg!r}]
+import torch
+from picsong_b200 import codec, synth
+out = []
+for (W, H, wl, lossy, B) in [(512, 384, 3, 0, 3), (1024, 512, 4, 1, 2), (256, 192, 2, 1, 1), (768, 320, 5, 0, 2)]:
+    folder = "video_lossy" if lossy else "video_lossless"
+    cd = codec.Codec(codec.Params(W, H, wl, bool(lossy), 1.0, max_batch=B), codec.load_lut({lut_root!r} + "/" + folder + "/", wl))
+    import numpy as np
+    px = torch.from_numpy(np.stack([synth.synth_frame(W, H, f) for f in range(B)])).cuda()
+    for trunc in (True, False):
+        c = cd.dwt_forward(px, trunc_to_int=trunc)
+        out.append(hashlib.sha256(c.cpu().numpy().tobytes()).hexdigest())
+    s, lens = cd.encode_frames(px.cpu().numpy(), 0)
+    out.append(hashlib.sha256(np.asarray(s).tobytes()).hexdigest())
+print("HASHES " + " ".join(out))
+"""
+
+
+def test_forward_dwt_work_queue_matches_per_level_launches(lut_root):
+    """PCS_DWT_QUEUE=1 (all levels in one persistent launch, dwt_fast.cu) is off by default; it must stay
+    bit-identical to the per-level launches.  The switch is read once per process, hence the subprocesses."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = _QUEUE_SNIPPET.format(root=root, pkg=os.path.join(root, "cuda-image-and-video-codec_b200"), lut_root=str(lut_root))
+    res = {}
+    for mode in ("0", "1"):
+        env = dict(os.environ, PCS_DWT_QUEUE=mode, PCS_DWTQ_MIN_MPIX="0")
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[mode] = [ln for ln in r.stdout.splitlines() if ln.startswith("HASHES ")][0]
+    assert res["0"] == res["1"]
