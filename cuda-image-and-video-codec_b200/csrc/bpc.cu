@@ -194,7 +194,7 @@ __device__ __forceinline__ void enc_step(unsigned abw, unsigned anbw, unsigned b
 constexpr int kSppUnroll = PCS_SPP_UNROLL;
 
 #ifndef PCS_ENC_MINB
-#define PCS_ENC_MINB 4
+#define PCS_ENC_MINB 5
 #endif
 template <typename T>
 __global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* __restrict__ coeff, unsigned short* __restrict__ cw,
@@ -448,7 +448,7 @@ __device__ __forceinline__ unsigned dec_step(unsigned actw, unsigned bitm, unsig
 constexpr int kMaxProbRows = (3 * kMaxLevels + 1) * 15 + 32;  // shipped tables: nSub = 3, nBp = 15
 
 #ifndef PCS_DEC_MINB
-#define PCS_DEC_MINB 4
+#define PCS_DEC_MINB 5
 #endif
 __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const unsigned short* __restrict__ cw, const int* __restrict__ sizes,
                                                                       int* __restrict__ q, const BpcArgs p) {

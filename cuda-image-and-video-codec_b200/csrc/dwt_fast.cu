@@ -538,8 +538,8 @@ void variant_params(int Hc, int* nW, int* ls) {
 // Row pairs per chunk.  A chunk costs (rp + warm-up) serial steps and the grid runs in ceil(CTAs / resident CTAs)
 // waves, so pick the rp that minimises waves * steps: long chunks amortise the warm-up rows, but a grid that
 // spills a few CTAs into a second wave doubles the time of the small, latency-bound levels.
-int choose_rp(int nstrips, int hh, int frames, int warm, int step) {
-  const long long slots = 148LL * 4;  // CTAs of 128 threads resident at <= 128 registers per thread
+int choose_rp(int nstrips, int hh, int frames, int warm, int step, long long slots = 148LL * 4) {
+  // slots: CTAs of 128 threads the GPU holds at once (148 SMs x 4 at <= 128 registers per thread)
   int best = step; long long best_cost = -1;
   for (int rp = step; rp <= 128; rp += step) {
     const long long ctas = (long long)((nstrips * ((hh + rp - 1) / rp) + 3) / 4) * frames;
@@ -911,14 +911,19 @@ template <int N> struct IVSel<true, N> { using type = IV97<N>; };
 // De-quantiser on subband read (DWTGenerator.cu:513-553): 0 -> 0, else (|q|+0.5)*sgn / Q / qs, the two
 // divisions as multiplications by rounded reciprocals.  |q| -> float through the 2^23 mantissa trick
 // (exact for |q| < 2^23, which the decoder guarantees) instead of an I2F on the quarter-rate pipe.
+// Two quantisation indices -> reconstruction values (|q| + 0.5) * sgn(q) / Q [/ qs], 0 for q == 0
+// (DWTGenerator.cu:513-553 with the divisions restated as the oracle's reciprocal multiplies).  s = 2q + sgn(q) is
+// twice the reconstruction point as an integer (0 stays 0, the sign comes for free); the 1.5 * 2^23 magic number turns
+// it into a float with one integer add and one exact fp32 add (|s| < 2^22: indices of 8-bit frames stay below 2^18
+// at any depth), and s * (0.5 / Q) rounds exactly like (|q| + 0.5) * (1 / Q) because the factors 2 and 0.5 are exact.
+// hrq = 0.5 / Q for the two samples.  5 instructions per sample instead of 8, two of them packed.
 template <bool QS1>
-__device__ __forceinline__ float dequant(int q, float rq, float rqs) {
-  const unsigned aq = (unsigned)abs(q);
-  const float mag = __fadd_rn(__fadd_rn(__uint_as_float(0x4B000000u | aq), -8388608.0f), 0.5f);
-  float t = __fmul_rn(mag, rq);
-  if (!QS1) t = __fmul_rn(t, rqs);
-  t = __uint_as_float(__float_as_uint(t) | ((unsigned)q & 0x80000000u));
-  return q == 0 ? 0.0f : t;
+__device__ __forceinline__ f2 dequant2(int q0, int q1, f2 hrq, f2 rqs2) {
+  const int s0 = 2 * q0 + max(min(q0, 1), -1), s1 = 2 * q1 + max(min(q1, 1), -1);
+  f2 v = add2(pk(__int_as_float(0x4B400000 + s0), __int_as_float(0x4B400000 + s1)), pk(-12582912.0f, -12582912.0f));
+  v = mul2(v, hrq);
+  if (!QS1) v = mul2(v, rqs2);
+  return v;
 }
 
 __device__ __forceinline__ unsigned sat_u8(float v) {  // clamp(rn(v), 0, 255)
@@ -928,7 +933,10 @@ __device__ __forceinline__ unsigned sat_u8(float v) {  // clamp(rn(v), 0, 255)
 }
 
 template <bool LOSSY, bool DST_U8, bool FIRST, bool QS1>
-__global__ void __launch_bounds__(128, 3) dwt_inverse_fast_kernel(const FastInvArgs a) {
+#ifndef PCS_INV_MINB
+#define PCS_INV_MINB 4
+#endif
+__global__ void __launch_bounds__(128, PCS_INV_MINB) dwt_inverse_fast_kernel(const FastInvArgs a) {
   using T = typename VSel<LOSSY, 8>::T;
   using VP = typename IVSel<LOSSY, 8>::type;
   using T4 = typename std::conditional<LOSSY, float4, int4>::type;
@@ -954,8 +962,13 @@ __global__ void __launch_bounds__(128, 3) dwt_inverse_fast_kernel(const FastInvA
     else { rl = n; rh = n; }
   };
   auto ll_from_q = [&](int4 t) -> T4 {
-    if constexpr (LOSSY) return make_float4(dequant<QS1>(t.x, a.r[0], a.rqs), dequant<QS1>(t.y, a.r[0], a.rqs), dequant<QS1>(t.z, a.r[0], a.rqs), dequant<QS1>(t.w, a.r[0], a.rqs));
-    else return t;
+    if constexpr (LOSSY) {
+      const f2 h0 = pk(0.5f * a.r[0], 0.5f * a.r[0]), rqs2 = pk(a.rqs, a.rqs);
+      float4 v;
+      upk(dequant2<QS1>(t.x, t.y, h0, rqs2), v.x, v.y);
+      upk(dequant2<QS1>(t.z, t.w, h0, rqs2), v.z, v.w);
+      return v;
+    } else return t;
   };
   auto load_pair = [&](int n) -> Raw {
     int rl, rh;
@@ -999,12 +1012,14 @@ __global__ void __launch_bounds__(128, 3) dwt_inverse_fast_kernel(const FastInvA
   auto expand = [&](const Raw& r, T (&lo)[8], T (&hi)[8]) {
     lo[0] = r.ll.x; lo[2] = r.ll.y; lo[4] = r.ll.z; lo[6] = r.ll.w;
     if constexpr (LOSSY) {
-      lo[1] = dequant<QS1>(r.hl.x, a.r[1], a.rqs); lo[3] = dequant<QS1>(r.hl.y, a.r[1], a.rqs);
-      lo[5] = dequant<QS1>(r.hl.z, a.r[1], a.rqs); lo[7] = dequant<QS1>(r.hl.w, a.r[1], a.rqs);
-      hi[0] = dequant<QS1>(r.lh.x, a.r[2], a.rqs); hi[2] = dequant<QS1>(r.lh.y, a.r[2], a.rqs);
-      hi[4] = dequant<QS1>(r.lh.z, a.r[2], a.rqs); hi[6] = dequant<QS1>(r.lh.w, a.r[2], a.rqs);
-      hi[1] = dequant<QS1>(r.hh.x, a.r[3], a.rqs); hi[3] = dequant<QS1>(r.hh.y, a.r[3], a.rqs);
-      hi[5] = dequant<QS1>(r.hh.z, a.r[3], a.rqs); hi[7] = dequant<QS1>(r.hh.w, a.r[3], a.rqs);
+      // odd columns: HL (low row) and HH (high row) of a column form the pair the horizontal pass works on
+      const f2 h13 = pk(0.5f * a.r[1], 0.5f * a.r[3]), h22 = pk(0.5f * a.r[2], 0.5f * a.r[2]), rqs2 = pk(a.rqs, a.rqs);
+      upk(dequant2<QS1>(r.hl.x, r.hh.x, h13, rqs2), lo[1], hi[1]);
+      upk(dequant2<QS1>(r.hl.y, r.hh.y, h13, rqs2), lo[3], hi[3]);
+      upk(dequant2<QS1>(r.hl.z, r.hh.z, h13, rqs2), lo[5], hi[5]);
+      upk(dequant2<QS1>(r.hl.w, r.hh.w, h13, rqs2), lo[7], hi[7]);
+      upk(dequant2<QS1>(r.lh.x, r.lh.y, h22, rqs2), hi[0], hi[2]);
+      upk(dequant2<QS1>(r.lh.z, r.lh.w, h22, rqs2), hi[4], hi[6]);
     } else {
       lo[1] = r.hl.x; lo[3] = r.hl.y; lo[5] = r.hl.z; lo[7] = r.hl.w;
       hi[0] = r.lh.x; hi[2] = r.lh.y; hi[4] = r.lh.z; hi[6] = r.lh.w;
@@ -1072,10 +1087,31 @@ __global__ void __launch_bounds__(128, 3) dwt_inverse_fast_kernel(const FastInvA
   }
 }
 
+// CTAs of kernel K the whole GPU holds at once (its register count decides: 3 or 4 per SM)
+template <typename K>
+long long resident_ctas(K kernel) {
+  int dev = 0, sms = 148, per_sm = 3;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0);
+  return (long long)sms * std::max(per_sm, 1);
+}
+
+// The chunk length is chosen per kernel variant: a grid sized for 4 CTAs per SM runs 1.3 waves on a variant that
+// only fits 3 (the 9/7 inverse needs 130-138 registers), i.e. a second wave that is 30 % full.
+template <bool LOSSY, bool DST_U8, bool FIRST, bool QS1>
+void launch_inv_k(FastInvArgs a, int frames, cudaStream_t st) {
+  static const long long slots = resident_ctas(dwt_inverse_fast_kernel<LOSSY, DST_U8, FIRST, QS1>);
+  const int hh = a.Hc >> 1;
+  a.rp = choose_rp(a.nstrips, hh, frames, 4, 2, slots);
+  a.nchunks = (hh + a.rp - 1) / a.rp;
+  dim3 grid((a.nstrips * a.nchunks + 3) / 4, frames);
+  dwt_inverse_fast_kernel<LOSSY, DST_U8, FIRST, QS1><<<grid, 128, 0, st>>>(a);
+}
 template <bool LOSSY, bool DST_U8, bool FIRST>
-void launch_inv(const FastInvArgs& a, dim3 grid, bool qs1, cudaStream_t st) {
-  if (qs1) dwt_inverse_fast_kernel<LOSSY, DST_U8, FIRST, true><<<grid, 128, 0, st>>>(a);
-  else dwt_inverse_fast_kernel<LOSSY, DST_U8, FIRST, false><<<grid, 128, 0, st>>>(a);
+void launch_inv(const FastInvArgs& a, int frames, bool qs1, cudaStream_t st) {
+  if (qs1) launch_inv_k<LOSSY, DST_U8, FIRST, true>(a, frames, st);
+  else launch_inv_k<LOSSY, DST_U8, FIRST, false>(a, frames, st);
 }
 
 }  // namespace
@@ -1225,17 +1261,13 @@ int dwt_inverse_fast(const int32_t* d_q, long long q_fstride, int pitch, const v
   for (int i = 0; i < 4; ++i) a.r[i] = 1.0f / kQ[level - 1][i];
   a.rqs = 1.0f / qs;
   a.nstrips = (Wc + 239) / 240;
-  const int hh = Hc >> 1;
-  a.rp = choose_rp(a.nstrips, hh, frames, 4, 2);
-  a.nchunks = (hh + a.rp - 1) / a.rp;
-  dim3 grid((a.nstrips * a.nchunks + 3) / 4, frames);
   const bool qs1 = a.rqs == 1.0f;
   if (!lossy) {
-    if (dst_u8) { if (first) launch_inv<false, true, true>(a, grid, qs1, st); else launch_inv<false, true, false>(a, grid, qs1, st); }
-    else { if (first) launch_inv<false, false, true>(a, grid, qs1, st); else launch_inv<false, false, false>(a, grid, qs1, st); }
+    if (dst_u8) { if (first) launch_inv<false, true, true>(a, frames, qs1, st); else launch_inv<false, true, false>(a, frames, qs1, st); }
+    else { if (first) launch_inv<false, false, true>(a, frames, qs1, st); else launch_inv<false, false, false>(a, frames, qs1, st); }
   } else {
-    if (dst_u8) { if (first) launch_inv<true, true, true>(a, grid, qs1, st); else launch_inv<true, true, false>(a, grid, qs1, st); }
-    else { if (first) launch_inv<true, false, true>(a, grid, qs1, st); else launch_inv<true, false, false>(a, grid, qs1, st); }
+    if (dst_u8) { if (first) launch_inv<true, true, true>(a, frames, qs1, st); else launch_inv<true, true, false>(a, frames, qs1, st); }
+    else { if (first) launch_inv<true, false, true>(a, frames, qs1, st); else launch_inv<true, false, false>(a, frames, qs1, st); }
   }
   ++g_launches;
   return (int)cudaGetLastError();
