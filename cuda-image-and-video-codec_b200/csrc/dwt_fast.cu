@@ -362,6 +362,10 @@ __device__ __forceinline__ void emit_pair(const T (&lo)[NS], const T (&hi)[NS], 
 // if last, -> out) or two fused levels (LEVELS = 2, u8 input only).  SRC_U8: the input is the u8 frame (level 1), else
 // the 32-bit LL plane of the level above.  COH: that plane was written by other SMs during this very launch (queue
 // kernel below), so it is read through L2 (ld.global.cg) instead of the non-coherent path.
+#ifndef PCS_FWD_PF2
+#define PCS_FWD_PF2 0
+#endif
+constexpr bool kPf2 = PCS_FWD_PF2 != 0;  // 32-bit input rows prefetched two steps ahead instead of one
 constexpr int kFwdDepth = 6;
 typedef unsigned char FwdRing[kFwdDepth][2][32][8];
 #ifndef PCS_FWD_MINB
@@ -430,12 +434,13 @@ __device__ __forceinline__ void fwd_item(const FastFwdArgs& a, const int strip, 
   T ll_odd[4] = {};  // buffered odd LL row for the second level
   const int ms = P0 - VP1::kWarm;          // first step: pair P0 is the first valid one
   const int mend = Plast + VP1::kDelay;    // last step
-  RowT pa, pb;
+  RowT pa, pb, pc, pd;  // 32-bit input: rows of step m and (PCS_FWD_PF2) of step m + 1, loaded ahead
   if constexpr (SRC_U8) {
 #pragma unroll
     for (int d = 0; d < kDepth; ++d) issue_step(ms + d, d);
   } else {
     pa = load_row(2 * ms + 1); pb = load_row(2 * ms + 2);
+    if constexpr (kPf2) { pc = load_row(2 * ms + 3); pd = load_row(2 * ms + 4); }
   }
   {
     T r[8];
@@ -455,7 +460,8 @@ __device__ __forceinline__ void fwd_item(const FastFwdArgs& a, const int strip, 
       slot = slot + 1 == kDepth ? 0 : slot + 1;
     } else {
       unpack8(pa, xo); unpack8(pb, x2);
-      pa = load_row(2 * m + 3); pb = load_row(2 * m + 4);
+      if constexpr (kPf2) { pa = pc; pb = pd; pc = load_row(2 * m + 5); pd = load_row(2 * m + 6); }
+      else { pa = load_row(2 * m + 3); pb = load_row(2 * m + 4); }
     }
     // borders of this level come from the folded loads, so no explicit rule here
     if constexpr (LOSSY) v97_step_packed<8>(v1, xo, x2, lo, hi);
@@ -514,8 +520,11 @@ __device__ __forceinline__ void fwd_item(const FastFwdArgs& a, const int strip, 
   }
 }
 
+#ifndef PCS_FWD_MINB_U8
+#define PCS_FWD_MINB_U8 4
+#endif
 template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS, bool QS1>
-__global__ void __launch_bounds__(128, PCS_FWD_MINB) dwt_forward_fused(const FastFwdArgs a) {
+__global__ void __launch_bounds__(128, (SRC_U8 && LEVELS == 1) ? PCS_FWD_MINB_U8 : PCS_FWD_MINB) dwt_forward_fused(const FastFwdArgs a) {
   __shared__ __align__(16) FwdRing s_ring[SRC_U8 ? 4 : 1];
   const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (item >= a.nstrips * a.nchunks) return;
@@ -549,10 +558,30 @@ int choose_rp(int nstrips, int hh, int frames, int warm, int step, long long slo
   return best;
 }
 
+// CTAs of kernel K the whole GPU holds at once (its register count decides how many per SM)
+template <typename K>
+long long resident_ctas(K kernel) {
+  int dev = 0, sms = 148, per_sm = 3;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0);
+  return (long long)sms * std::max(per_sm, 1);
+}
+
+// The chunk length is chosen per kernel variant, for the number of CTAs that variant really keeps resident.
+template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS, bool QS1>
+void launch_k(FastFwdArgs a, int frames, cudaStream_t st) {
+  static const long long slots = resident_ctas(dwt_forward_fused<LOSSY, OT, SRC_U8, LEVELS, QS1>);
+  const int hh1 = a.Hc >> 1;
+  a.rp = choose_rp(a.nstrips, hh1, frames, LEVELS == 2 ? 12 : 3, 4, slots);
+  a.nchunks = (hh1 + a.rp - 1) / a.rp;
+  dim3 grid((a.nstrips * a.nchunks + 3) / 4, frames);
+  dwt_forward_fused<LOSSY, OT, SRC_U8, LEVELS, QS1><<<grid, 128, 0, st>>>(a);
+}
 template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS>
-void launch(const FastFwdArgs& a, dim3 grid, cudaStream_t st) {
-  if (a.qs == 1.0f) dwt_forward_fused<LOSSY, OT, SRC_U8, LEVELS, true><<<grid, 128, 0, st>>>(a);
-  else dwt_forward_fused<LOSSY, OT, SRC_U8, LEVELS, false><<<grid, 128, 0, st>>>(a);
+void launch(const FastFwdArgs& a, int frames, cudaStream_t st) {
+  if (a.qs == 1.0f) launch_k<LOSSY, OT, SRC_U8, LEVELS, true>(a, frames, st);
+  else launch_k<LOSSY, OT, SRC_U8, LEVELS, false>(a, frames, st);
 }
 
 
@@ -1087,16 +1116,6 @@ __global__ void __launch_bounds__(128, PCS_INV_MINB) dwt_inverse_fast_kernel(con
   }
 }
 
-// CTAs of kernel K the whole GPU holds at once (its register count decides: 3 or 4 per SM)
-template <typename K>
-long long resident_ctas(K kernel) {
-  int dev = 0, sms = 148, per_sm = 3;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0);
-  return (long long)sms * std::max(per_sm, 1);
-}
-
 // The chunk length is chosen per kernel variant: a grid sized for 4 CTAs per SM runs 1.3 waves on a variant that
 // only fits 3 (the 9/7 inverse needs 130-138 registers), i.e. a second wave that is 30 % full.
 template <bool LOSSY, bool DST_U8, bool FIRST, bool QS1>
@@ -1146,24 +1165,20 @@ int dwt_forward_fast(const void* src, bool src_u8, long long src_fstride, int sr
   variant_params(Hc >> 1, &a.nW2, &a.ls2);
   const int eff = (32 - 2 * levels) * 8;
   a.nstrips = (Wc + eff - 1) / eff;
-  const int hh1 = Hc >> 1;
-  a.rp = choose_rp(a.nstrips, hh1, frames, levels == 2 ? 12 : 3, 4);
-  a.nchunks = (hh1 + a.rp - 1) / a.rp;
-  dim3 grid((a.nstrips * a.nchunks + 3) / 4, frames);
   if (src_u8) {
     if (levels == 2) {
-      if (!lossy) launch<false, int, true, 2>(a, grid, st);
-      else if (out_int) launch<true, int, true, 2>(a, grid, st);
-      else launch<true, float, true, 2>(a, grid, st);
+      if (!lossy) launch<false, int, true, 2>(a, frames, st);
+      else if (out_int) launch<true, int, true, 2>(a, frames, st);
+      else launch<true, float, true, 2>(a, frames, st);
     } else {
-      if (!lossy) launch<false, int, true, 1>(a, grid, st);
-      else if (out_int) launch<true, int, true, 1>(a, grid, st);
-      else launch<true, float, true, 1>(a, grid, st);
+      if (!lossy) launch<false, int, true, 1>(a, frames, st);
+      else if (out_int) launch<true, int, true, 1>(a, frames, st);
+      else launch<true, float, true, 1>(a, frames, st);
     }
   } else {
-    if (!lossy) launch<false, int, false, 1>(a, grid, st);
-    else if (out_int) launch<true, int, false, 1>(a, grid, st);
-    else launch<true, float, false, 1>(a, grid, st);
+    if (!lossy) launch<false, int, false, 1>(a, frames, st);
+    else if (out_int) launch<true, int, false, 1>(a, frames, st);
+    else launch<true, float, false, 1>(a, frames, st);
   }
   ++g_launches;
   return (int)cudaGetLastError();
