@@ -417,6 +417,27 @@ int slots_for(const pcs_ctx* c, int* sb) {
   return n;
 }
 
+// The chunks of a call: `sb` frames each, except that the first two and the last two are halved -- the upload of the
+// first chunk and the download of the last one are the parts of a call nothing else can overlap.
+struct Chunk { int f0, b; };
+std::vector<Chunk> chunk_plan(int nframes, int sb) {
+  static const int taper = [] { const char* e = std::getenv("PCS_PIPE_TAPER"); return e ? std::atoi(e) : 1; }();
+  std::vector<Chunk> plan;
+  const int small = std::max(1, sb / 2);
+  const bool tap = taper && sb >= 2 && nframes >= 4 * sb;
+  int f = 0;
+  while (f < nframes) {
+    const int left = nframes - f;
+    const bool edge = tap && (f < 2 * small || left <= 2 * small);
+    const int b = std::min(edge ? small : sb, left);
+    // never let a full-size chunk eat into the tapered tail
+    const int bb = (tap && !edge && left - b < 2 * small && left - b > 0) ? left - 2 * small : b;
+    plan.push_back({f, std::max(1, bb)});
+    f += plan.back().b;
+  }
+  return plan;
+}
+
 }  // namespace
 
 // h_frame_len receives one length per PLANE (nframes entries for grey, 3 * nframes for RGB: the values the
@@ -428,12 +449,13 @@ int32_t pcs_encode_frames(pcs_ctx* c, const uint8_t* h_px, int32_t nframes, int3
   const int nc = c->ncomp;
   int sb;
   const int nslots = slots_for(c, &sb);
-  const int nchunks = (nframes + sb - 1) / sb;
+  const std::vector<Chunk> plan = chunk_plan(nframes, sb);
+  const int nchunks = (int)plan.size();
   size_t written = 0;
   // second half of a chunk's work: its plane offsets are on the host -> copy its packed planes out
   auto finish = [&](int j) -> int {
     Slot s = make_slot(c, j % nslots, sb);
-    const int f0 = j * sb, b = std::min(sb, nframes - f0);
+    const int f0 = plan[j].f0, b = plan[j].b;
     PCS_CUDA_TRY(cudaEventSynchronize(s.ev));
     const size_t words = (size_t)s.h_off[b * nc];
     if (written + words > cap) return fail(c, PCS_E_NOMEM, "output capacity too small");
@@ -452,7 +474,7 @@ int32_t pcs_encode_frames(pcs_ctx* c, const uint8_t* h_px, int32_t nframes, int3
   for (int i = 0; i < nchunks; ++i) {
     while (finished <= i - nslots) { int rc = finish(finished++); if (rc) return rc; }  // frees the slot (same stream: ordered)
     Slot s = make_slot(c, i % nslots, sb);
-    const int f0 = i * sb, b = std::min(sb, nframes - f0);
+    const int f0 = plan[i].f0, b = plan[i].b;
     PCS_CUDA_TRY(cudaMemcpyAsync(s.px, h_px + (size_t)f0 * fpx, (size_t)b * fpx, cudaMemcpyHostToDevice, s.st));
     if (i >= depth && depth < nslots) PCS_CUDA_TRY(cudaStreamWaitEvent(s.st, c->kev[(i - depth) % nslots], 0));
     int rc = run_dwt_forward(c, s.w, s.px, s.w.coeff, true, b, s.st, nullptr);
@@ -478,12 +500,13 @@ int32_t pcs_decode_frames(pcs_ctx* c, const uint16_t* h_stream, const int32_t* h
   const int nc = c->ncomp;
   int sb;
   const int nslots = slots_for(c, &sb);
-  const int nchunks = (nframes + sb - 1) / sb;
+  const std::vector<Chunk> plan = chunk_plan(nframes, sb);
+  const int nchunks = (int)plan.size();
   size_t consumed = 0;
   const int depth = kernel_depth(nslots);
   for (int i = 0; i < nchunks; ++i) {
     Slot s = make_slot(c, i % nslots, sb);
-    const int f0 = i * sb, b = std::min(sb, nframes - f0);
+    const int f0 = plan[i].f0, b = plan[i].b;
     if (i >= nslots) PCS_CUDA_TRY(cudaEventSynchronize(s.ev));  // the slot's pinned offsets have been uploaded
     long long off = 0;
     for (int f = 0; f < b * nc; ++f) {

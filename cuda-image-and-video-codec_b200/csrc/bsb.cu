@@ -57,6 +57,30 @@ __device__ __forceinline__ long long lookback(unsigned long long* status, int ti
   return excl;
 }
 
+// Warp-cooperative copy of n uint16 between two arrays of arbitrary (2-byte) alignment.  The destination is written
+// in 16-byte vectors (512 B per warp instruction instead of 64 B); the source is read as aligned 32-bit words and, when
+// source and destination disagree in their alignment modulo 4, re-aligned with one PRMT per output word.  Reads stay
+// inside [src, src + n) rounded outwards to 32-bit words only where the extra half word belongs to the same array:
+// the caller guarantees src[n] is readable when it passes tail_ok (it is another element of the same buffer).
+__device__ __forceinline__ void warp_copy_u16(unsigned short* __restrict__ dst, const unsigned short* __restrict__ src, int n, bool tail_ok,
+                                              int lane) {
+  const int head = min(n, (int)(((16u - (unsigned)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u) >> 1));
+  for (int j = lane; j < head; j += 32) dst[j] = src[j];
+  const unsigned short* const s = src + head;
+  const int odd = (int)((reinterpret_cast<uintptr_t>(s) >> 1) & 1u);
+  // an odd source reads one half word past the last element of a vector
+  const int nvec = max(0, n - head - ((odd && !tail_ok) ? 1 : 0)) >> 3;
+  const unsigned sel = odd ? 0x5432u : 0x3210u;
+  const unsigned* const s32 = reinterpret_cast<const unsigned*>(s - odd);
+  uint4* const d4 = reinterpret_cast<uint4*>(dst + head);
+  for (int v = lane; v < nvec; v += 32) {
+    const unsigned* const p = s32 + 4 * v;
+    const unsigned w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3], w4 = odd ? p[4] : 0u;
+    d4[v] = make_uint4(__byte_perm(w0, w1, sel), __byte_perm(w1, w2, sel), __byte_perm(w2, w3, sel), __byte_perm(w3, w4, sel));
+  }
+  for (int j = head + 8 * nvec + lane; j < n; j += 32) dst[j] = src[j];
+}
+
 // sparse uint16 [batch][ncb][4096] + sizes  ->  frames back to back (Annex C.2 layout per frame)
 __global__ void __launch_bounds__(256) bsb_pack_kernel(const unsigned short* __restrict__ cw, const int* __restrict__ sizes,
                                                       unsigned short* __restrict__ out, long long* __restrict__ frame_off,
@@ -88,7 +112,8 @@ __global__ void __launch_bounds__(256) bsb_pack_kernel(const unsigned short* __r
     const int sz = sizes[g];
     const long long data = s_excl[k] + (long long)f * (n + 10) + 9 + 2LL * n - cb;
     const unsigned short* src = cw + (size_t)g * kCBWords;
-    for (int j = 1 + lane; j < sz; j += 32) out[data + j - 1] = src[j];
+    // src[sz] is readable: sz <= 4095 leaves it inside the block, and a block of 4096 words ends on a 32-bit boundary
+    warp_copy_u16(out + data, src + 1, sz - 1, sz < kCBWords, lane);
   }
   // The tile holding block 0 of frame f knows S_f: it writes that frame's 9-word header, all n
   // (MSB, size) pairs (BitStreamBuilder.cu:122-127) and the previous frame's trailing 0xFFFF.
@@ -149,7 +174,10 @@ __global__ void __launch_bounds__(256) bsb_unpack_kernel(const unsigned short* _
     const long long data = 9 + 2LL * n + s_excl[k] - cb;
     unsigned short* dst = cw + (size_t)g * kCBWords;
     if (lane == 0) { dst[0] = fin[9 + 2 * cb]; sizes[g] = sz; }
-    for (int j = 1 + lane; j < sz; j += 32) dst[j] = (S + data + j - 1 < E) ? fin[data + j - 1] : (unsigned short)0xFFFFu;
+    // words the (possibly malformed) frame really holds; the rest of the block reads as 0xFFFF
+    const int have = (int)min((long long)(sz - 1), max(0LL, E - S - data));
+    warp_copy_u16(dst + 1, fin + data, have, false, lane);
+    for (int j = 1 + have + lane; j < sz; j += 32) dst[j] = (unsigned short)0xFFFFu;
   }
 }
 
