@@ -34,7 +34,7 @@ import numpy as np  # noqa: E402
 WORKLOADS = {
     # name: (W, H, wl, lossy, qs, lut folder, frames per step, description)
     "cfg1": (512, 512, 5, 0, 1.0, "n1_lossless", 16, "configs[0]: 512x512 8-bit grey, lossless 5/3, wl=5, 64x64 codeblocks"),
-    "cfg2": (4096, 4096, 5, 1, 1.0, "n1_lossy", 16, "configs[1]: 4096x4096 8-bit grey, lossy 9/7 qs=1.0, wl=5, 64x64 codeblocks"),
+    "cfg2": (4096, 4096, 5, 1, 1.0, "n1_lossy", 32, "configs[1]: 4096x4096 8-bit grey, lossy 9/7 qs=1.0, wl=5, 64x64 codeblocks"),
     "cfg3": (7680, 4320, 6, 0, 1.0, "n1_lossless", 2, "configs[2]: 7680x4320 8-bit grey, lossless 5/3, wl=6, 64x64 codeblocks"),
     "cfg4": (3840, 2160, 5, 1, 1.0, "video_lossy", 8, "configs[3]: 3840x2160 8-bit grey video frames, lossy 9/7 qs=1, wl=5, frame-sharded"),
     # SURVEY 8f.1 (the widening row): the reference README's own example shape, 2048x2560 RGB still, lossy

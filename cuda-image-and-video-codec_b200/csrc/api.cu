@@ -403,17 +403,25 @@ Slot make_slot(pcs_ctx* c, int k, int sb) {
 // chunks in flight would finish together and their downloads would queue up behind each other at the end of the
 // call; with a depth of 2 a chunk still fills the partial last waves of its predecessor, but chunks complete in
 // order, one download apart, and uploads run ahead of the kernels (they are enqueued before the wait).
-int kernel_depth(int nslots) {
-  static const int env = [] { const char* e = std::getenv("PCS_PIPE_DEPTH"); return e ? std::atoi(e) : 2; }();
-  return std::max(1, std::min(env, nslots));
+// A call of no more chunks than slots has no such tail to speak of and runs them all at once (measured: RGB stills,
+// 4 chunks: +5 %).
+int kernel_depth(int nslots, int nchunks) {
+  static const int env = [] { const char* e = std::getenv("PCS_PIPE_DEPTH"); return e ? std::atoi(e) : 0; }();
+  const int d = env > 0 ? env : (nchunks <= nslots ? nslots : 2);
+  return std::max(1, std::min(d, nslots));
 }
 int slots_for(const pcs_ctx* c, int* sb) {
   // chunks of max_batch / (2 * slots) frames: fine enough that the first upload and the last download (the
-  // parts of a call that cannot overlap anything) are short, coarse enough that a launch still fills the GPU
-  const int n = std::min<int>(pcs_ctx::kSlots, c->p.max_batch);
-  *sb = std::max(1, c->p.max_batch / (2 * n));
+  // parts of a call that cannot overlap anything) are short, coarse enough that a launch still fills the GPU.
+  // Small frames: a chunk carries at least 8 MB of pixels (a 512x512 batch goes through as one chunk -- ten
+  // launches and two copies per chunk cost more than overlapping a 4 MB upload could ever gain).
+  const size_t min_chunk = 8u << 20;
+  const int B = c->p.max_batch;
+  const int sb_min = (int)std::min<size_t>((size_t)B, (min_chunk + c->frame_px - 1) / c->frame_px);
+  int n = std::max(1, std::min<int>(pcs_ctx::kSlots, B / sb_min));
+  *sb = std::min(std::max(sb_min, std::max(1, B / (2 * n))), B / n);
   static const int env = [] { const char* e = std::getenv("PCS_PIPE_CHUNK"); return e ? std::atoi(e) : 0; }();
-  if (env > 0) *sb = std::max(1, std::min(env, c->p.max_batch / n));
+  if (env > 0) { n = std::min<int>(pcs_ctx::kSlots, B); *sb = std::max(1, std::min(env, B / n)); }
   return n;
 }
 
@@ -469,7 +477,7 @@ int32_t pcs_encode_frames(pcs_ctx* c, const uint8_t* h_px, int32_t nframes, int3
   // `lag` downloads for the end of the call.
   static const int lag_env = [] { const char* e = std::getenv("PCS_PIPE_LAG"); return e ? std::atoi(e) : 2; }();
   const int lag = std::max(1, std::min(lag_env, nslots));
-  const int depth = kernel_depth(nslots);
+  const int depth = kernel_depth(nslots, nchunks);
   int finished = 0;
   for (int i = 0; i < nchunks; ++i) {
     while (finished <= i - nslots) { int rc = finish(finished++); if (rc) return rc; }  // frees the slot (same stream: ordered)
@@ -503,7 +511,7 @@ int32_t pcs_decode_frames(pcs_ctx* c, const uint16_t* h_stream, const int32_t* h
   const std::vector<Chunk> plan = chunk_plan(nframes, sb);
   const int nchunks = (int)plan.size();
   size_t consumed = 0;
-  const int depth = kernel_depth(nslots);
+  const int depth = kernel_depth(nslots, nchunks);
   for (int i = 0; i < nchunks; ++i) {
     Slot s = make_slot(c, i % nslots, sb);
     const int f0 = plan[i].f0, b = plan[i].b;

@@ -95,4 +95,7 @@ def traffic(path, out, workload="cfg2", frames=16, nlaunch=5):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "traffic" and len(sys.argv) > 4:  # ... traffic <report> <out.json> <frames>
+        traffic(sys.argv[2], sys.argv[3], frames=int(sys.argv[4]))
+    else:
+        {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
