@@ -250,8 +250,8 @@ def run_ours(args):
                    "parallelism": f"frame-sharded x{world}" if world > 1 else "single GPU",
                    **({"rank0_numa_node": numa} if numa is not None else {})},
         "encode_mpix_s": mpix_step * args.steps / (enc_ms * 1e-3), "decode_mpix_s": mpix_step * args.steps / (dec_ms * 1e-3),
-        "e2e": {"value": mpix_step * args.steps / (e2e_ms * 1e-3), "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h)},
+        "e2e": {"value": mpix_step * args.steps / (e2e_ms * 1e-3), "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d) * world,
+                "d2h_bytes_per_step": int(d2h) * world},  # whole job, like `value` (every rank moves the same amount)
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks,
         "roofline": {"kernel": "dwt_forward (all levels of the batch; u8 in -> 32-bit Mallat coefficients out)", "bound": "hbm",
