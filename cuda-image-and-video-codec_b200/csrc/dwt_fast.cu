@@ -363,13 +363,16 @@ __device__ __forceinline__ void emit_pair(const T (&lo)[NS], const T (&hi)[NS], 
 // the 32-bit LL plane of the level above.  COH: that plane was written by other SMs during this very launch (queue
 // kernel below), so it is read through L2 (ld.global.cg) instead of the non-coherent path.
 #ifndef PCS_FWD_PF2
-#define PCS_FWD_PF2 0
+#define PCS_FWD_PF2 1
 #endif
-constexpr bool kPf2 = PCS_FWD_PF2 != 0;  // 32-bit input rows prefetched two steps ahead instead of one
+// 9/7 levels >= 2 (32-bit input): rows prefetched two steps ahead instead of one.  These launches are a single wave of
+// long streams and were bound by the bytes in flight (2 KB per warp); with 4 KB per warp at 128 registers (still 4 CTAs
+// per SM) the 16 x 4096^2 call goes from 0.433 to 0.41 ms.  The 5/3 variants gain nothing and keep one step.
+constexpr bool kPf2On = PCS_FWD_PF2 != 0;
 constexpr int kFwdDepth = 6;
 typedef unsigned char FwdRing[kFwdDepth][2][32][8];
 #ifndef PCS_FWD_MINB
-#define PCS_FWD_MINB 3
+#define PCS_FWD_MINB 4
 #endif
 template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS, bool QS1, bool COH>
 __device__ __forceinline__ void fwd_item(const FastFwdArgs& a, const int strip, const int chunk, const int frame, FwdRing* const ringp) {
@@ -377,6 +380,7 @@ __device__ __forceinline__ void fwd_item(const FastFwdArgs& a, const int strip, 
   using VP1 = typename VSel<LOSSY, 8>::type;
   using VP2 = typename VSel<LOSSY, 4>::type;
   using RowT = typename std::conditional<SRC_U8, uint2, Row8<T>>::type;
+  constexpr bool kPf2 = kPf2On && LOSSY;
   const int lane = threadIdx.x & 31;
   constexpr int kHalo = LEVELS;                        // halo lanes per side
   constexpr int kEff = (32 - 2 * kHalo) * 8;           // effective columns per strip
@@ -524,7 +528,7 @@ __device__ __forceinline__ void fwd_item(const FastFwdArgs& a, const int strip, 
 #define PCS_FWD_MINB_U8 4
 #endif
 template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS, bool QS1>
-__global__ void __launch_bounds__(128, (SRC_U8 && LEVELS == 1) ? PCS_FWD_MINB_U8 : PCS_FWD_MINB) dwt_forward_fused(const FastFwdArgs a) {
+__global__ void __launch_bounds__(128, LEVELS == 2 ? 3 : SRC_U8 ? PCS_FWD_MINB_U8 : PCS_FWD_MINB) dwt_forward_fused(const FastFwdArgs a) {
   __shared__ __align__(16) FwdRing s_ring[SRC_U8 ? 4 : 1];
   const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (item >= a.nstrips * a.nchunks) return;
@@ -965,6 +969,9 @@ template <bool LOSSY, bool DST_U8, bool FIRST, bool QS1>
 #ifndef PCS_INV_MINB
 #define PCS_INV_MINB 4
 #endif
+#ifndef PCS_INV_RING_ALL   // 1: the cp.async ring also stages the inputs of the 9/7 levels >= 2 (32-bit output)
+#define PCS_INV_RING_ALL 0
+#endif
 __global__ void __launch_bounds__(128, PCS_INV_MINB) dwt_inverse_fast_kernel(const FastInvArgs a) {
   using T = typename VSel<LOSSY, 8>::T;
   using VP = typename IVSel<LOSSY, 8>::type;
@@ -1015,8 +1022,9 @@ __global__ void __launch_bounds__(128, PCS_INV_MINB) dwt_inverse_fast_kernel(con
   // The finest level (u8 output) moves 4 of the 5 bytes per pixel on its READ side: stage its subband rows
   // through a per-warp cp.async ring kDepth steps deep, as the forward level-1 kernel does.
   constexpr int kDepth = 4;
-  __shared__ __align__(16) unsigned char s_ring[DST_U8 ? 4 : 1][DST_U8 ? kDepth : 1][4][32][16];
-  auto& ring = s_ring[DST_U8 ? (threadIdx.x >> 5) : 0];
+  constexpr bool kRing = DST_U8 || (PCS_INV_RING_ALL && LOSSY);  // deeper 9/7 levels too: see PCS_INV_RING_ALL
+  __shared__ __align__(16) unsigned char s_ring[kRing ? 4 : 1][kRing ? kDepth : 1][4][32][16];
+  auto& ring = s_ring[kRing ? (threadIdx.x >> 5) : 0];
   auto issue_pair = [&](int n, int slot) {
     int rl, rh;
     pair_rows(n, rl, rh);
@@ -1087,7 +1095,7 @@ __global__ void __launch_bounds__(128, PCS_INV_MINB) dwt_inverse_fast_kernel(con
   const int ms = n0 - VP::kLead, mend = n1 + VP::kTail;
   Raw cur;
   int slot = 0;
-  if constexpr (DST_U8) {
+  if constexpr (kRing) {
 #pragma unroll
     for (int d = 0; d < kDepth; ++d) issue_pair(ms + d, d);
   } else {
@@ -1096,7 +1104,7 @@ __global__ void __launch_bounds__(128, PCS_INV_MINB) dwt_inverse_fast_kernel(con
 #pragma unroll 2
   for (int m = ms; m <= mend; ++m) {
     T lo[8], hi[8], re[8], ro[8];
-    if constexpr (DST_U8) {
+    if constexpr (kRing) {
       cp_async_wait<kDepth - 1>();  // pair m has landed
       cur = read_pair(slot);
       issue_pair(m + kDepth, slot);  // pairs past the chunk fold to valid rows and are not used
