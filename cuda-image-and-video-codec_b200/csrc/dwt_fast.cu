@@ -369,7 +369,10 @@ __device__ __forceinline__ void emit_pair(const T (&lo)[NS], const T (&hi)[NS], 
 // long streams and were bound by the bytes in flight (2 KB per warp); with 4 KB per warp at 128 registers (still 4 CTAs
 // per SM) the 16 x 4096^2 call goes from 0.433 to 0.41 ms.  The 5/3 variants gain nothing and keep one step.
 constexpr bool kPf2On = PCS_FWD_PF2 != 0;
-constexpr int kFwdDepth = 6;
+#ifndef PCS_FWD_DEPTH
+#define PCS_FWD_DEPTH 6
+#endif
+constexpr int kFwdDepth = PCS_FWD_DEPTH;
 typedef unsigned char FwdRing[kFwdDepth][2][32][8];
 #ifndef PCS_FWD_MINB
 #define PCS_FWD_MINB 4

@@ -389,3 +389,40 @@ def test_forward_dwt_work_queue_matches_per_level_launches(lut_root):
         assert r.returncode == 0, r.stderr[-2000:]
         res[mode] = [ln for ln in r.stdout.splitlines() if ln.startswith("HASHES ")][0]
     assert res["0"] == res["1"]
+
+
+_PIPE_SNIPPET = r"""
+import hashlib, sys
+sys.path[:0] = [{root!r}, {pkg!r}]
+import numpy as np
+from picsong_b200 import codec, synth
+out = []
+for (W, H, wl, lossy, B, n) in [(256, 192, 3, 0, 16, 16), (320, 256, 2, 1, 16, 13), (256, 256, 2, 0, 8, 5)]:
+    folder = "video_lossy" if lossy else "video_lossless"
+    cd = codec.Codec(codec.Params(W, H, wl, bool(lossy), 1.0, frames=n, max_batch=B), codec.load_lut({lut_root!r} + "/" + folder + "/", wl))
+    px = np.stack([synth.synth_frame(W, H, f) for f in range(n)])
+    s, lens = cd.encode_frames(px, 0)
+    back = cd.decode_frames(s, lens)
+    if not lossy:
+        assert np.array_equal(back, px)
+    out += [hashlib.sha256(np.asarray(s).tobytes()).hexdigest(), hashlib.sha256(lens.tobytes()).hexdigest(), hashlib.sha256(back.tobytes()).hexdigest()]
+print("HASHES " + " ".join(out))
+"""
+
+
+def test_host_buffer_pipeline_chunking_is_transparent(lut_root):
+    """pcs_encode_frames / pcs_decode_frames cut a call into chunks on four slot streams (tapered first / last chunks,
+    at most two chunks' kernels in flight).  Small test frames normally travel as ONE chunk, so the chunked schedule
+    is forced here (PCS_PIPE_CHUNK, read once per process -> subprocesses) and must not change a single byte."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = _PIPE_SNIPPET.format(root=root, pkg=os.path.join(root, "cuda-image-and-video-codec_b200"), lut_root=str(lut_root))
+    res = {}
+    for name, extra in (("one_chunk", {}), ("chunk2", {"PCS_PIPE_CHUNK": "2"}), ("chunk1_depth3", {"PCS_PIPE_CHUNK": "1", "PCS_PIPE_DEPTH": "3"}),
+                        ("chunk2_notaper_lag1", {"PCS_PIPE_CHUNK": "2", "PCS_PIPE_TAPER": "0", "PCS_PIPE_LAG": "1"})):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **extra), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[name] = [ln for ln in r.stdout.splitlines() if ln.startswith("HASHES ")][0]
+    assert len(set(res.values())) == 1, res
