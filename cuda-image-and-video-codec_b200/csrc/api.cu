@@ -428,6 +428,12 @@ int slots_for(const pcs_ctx* c, int* sb) {
   return n;
 }
 
+// Early error returns must not leave work queued on the slot streams (the next call would reuse the slots under it).
+struct SlotDrain {
+  pcs_ctx* c; int n; bool armed = true;
+  ~SlotDrain() { if (armed) for (int k = 0; k < n; ++k) cudaStreamSynchronize(c->sstream[k]); }
+};
+
 // The chunks of a call: `sb` frames each, except that the first two and the last two are halved -- the upload of the
 // first chunk and the download of the last one are the parts of a call nothing else can overlap.
 struct Chunk { int f0, b; };
@@ -462,6 +468,7 @@ int32_t pcs_encode_frames(pcs_ctx* c, const uint8_t* h_px, int32_t nframes, int3
   const int nslots = slots_for(c, &sb);
   const std::vector<Chunk> plan = chunk_plan(nframes, sb);
   const int nchunks = (int)plan.size();
+  SlotDrain drain{c, nslots};
   size_t written = 0;
   // second half of a chunk's work: its plane offsets are on the host -> copy its packed planes out
   auto finish = [&](int j) -> int {
@@ -501,6 +508,7 @@ int32_t pcs_encode_frames(pcs_ctx* c, const uint8_t* h_px, int32_t nframes, int3
   }
   while (finished < nchunks) { int rc = finish(finished++); if (rc) return rc; }
   for (int k = 0; k < nslots; ++k) PCS_CUDA_TRY(cudaStreamSynchronize(c->sstream[k]));
+  drain.armed = false;
   if (total_words) *total_words = written;
   return PCS_OK;
 }
@@ -513,6 +521,7 @@ int32_t pcs_decode_frames(pcs_ctx* c, const uint16_t* h_stream, const int32_t* h
   const int nslots = slots_for(c, &sb);
   const std::vector<Chunk> plan = chunk_plan(nframes, sb);
   const int nchunks = (int)plan.size();
+  SlotDrain drain{c, nslots};
   size_t consumed = 0;
   const int depth = kernel_depth(nslots, nchunks);
   for (int i = 0; i < nchunks; ++i) {
@@ -541,6 +550,7 @@ int32_t pcs_decode_frames(pcs_ctx* c, const uint16_t* h_stream, const int32_t* h
     consumed += (size_t)off;
   }
   for (int k = 0; k < nslots; ++k) PCS_CUDA_TRY(cudaStreamSynchronize(c->sstream[k]));
+  drain.armed = false;
   return PCS_OK;
 }
 
