@@ -407,41 +407,51 @@ __device__ __forceinline__ unsigned sign_entry1(unsigned i) {
 struct DecState { unsigned lower, size, slot, count, code, lt; };
 // One call site of the interval decoder for the whole warp (BPCEngine.cu:405-442); returns the decoded
 // bit (0 for idle lanes).  `actw` bit `bitm`: this lane decodes a symbol here.  Predicated PTX, see enc_step.
+// PREC = 7 (every shipped LUT): the shift is an immediate; PREC = 0: taken from `prec` at run time.
+#define PCS_DEC_STEP_ASM(SHR)                                   \
+      "{\n\t"                                                   \
+      ".reg .pred pact, pneed, pb, pnb;\n\t"                     \
+      ".reg .b32 t, m, x, pre, pm, r, q, sl, lim;\n\t"           \
+      ".reg .b64 ad;\n\t"                                        \
+      "and.b32 t, %6, %7;\n\t"                                   \
+      "setp.ne.u32 pact, t, 0;\n\t"                              \
+      "setp.eq.and.u32 pneed, %1, 0, pact;\n\t"                  \
+      "vote.sync.ballot.b32 m, pneed, 0xffffffff;\n\t"           \
+      "and.b32 x, m, %8;\n\t"                                    \
+      "popc.b32 pre, x;\n\t"                                     \
+      "popc.b32 pm, m;\n\t"                                      \
+      "@pneed add.u32 %2, %3, pre;\n\t"                          \
+      "add.u32 %3, %3, pm;\n\t"                                  \
+      "min.u32 sl, %2, 4094;\n\t"                                \
+      "mad.wide.u32 ad, sl, 2, %11;\n\t"                         \
+      "@pneed ld.global.nc.u16 %4, [ad];\n\t"                    \
+      "@pneed mov.u32 %1, 0xFFFF;\n\t"                           \
+      "@pneed mov.u32 %0, 0;\n\t"                                \
+      "mul.lo.u32 r, %1, %9;\n\t"                                \
+      SHR                                                        \
+      "add.u32 t, q, 1;\n\t"                                     \
+      "add.u32 lim, %0, t;\n\t"                                  \
+      "setp.ge.and.u32 pb|pnb, %4, lim, pact;\n\t"               \
+      "@pb sub.u32 %1, %1, t;\n\t"                               \
+      "@pb mov.u32 %0, lim;\n\t"                                 \
+      "@pnb mov.u32 %1, q;\n\t"                                  \
+      "selp.u32 %5, 1, 0, pb;\n\t"                               \
+      "}"
+template <int PREC>
 __device__ __forceinline__ unsigned dec_step(unsigned actw, unsigned bitm, unsigned p, DecState& c,
                                              const unsigned short* in1, unsigned prec) {
   unsigned b;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred pact, pneed, pb, pnb;\n\t"
-      ".reg .b32 t, m, x, pre, pm, r, q, sl, lim;\n\t"
-      ".reg .b64 ad;\n\t"
-      "and.b32 t, %6, %7;\n\t"
-      "setp.ne.u32 pact, t, 0;\n\t"
-      "setp.eq.and.u32 pneed, %1, 0, pact;\n\t"
-      "vote.sync.ballot.b32 m, pneed, 0xffffffff;\n\t"
-      "and.b32 x, m, %8;\n\t"
-      "popc.b32 pre, x;\n\t"
-      "popc.b32 pm, m;\n\t"
-      "@pneed add.u32 %2, %3, pre;\n\t"
-      "add.u32 %3, %3, pm;\n\t"
-      "min.u32 sl, %2, 4094;\n\t"
-      "mad.wide.u32 ad, sl, 2, %11;\n\t"
-      "@pneed ld.global.nc.u16 %4, [ad];\n\t"
-      "@pneed mov.u32 %1, 0xFFFF;\n\t"
-      "@pneed mov.u32 %0, 0;\n\t"
-      "mul.lo.u32 r, %1, %9;\n\t"
-      "shr.u32 q, r, %10;\n\t"
-      "add.u32 t, q, 1;\n\t"
-      "add.u32 lim, %0, t;\n\t"
-      "setp.ge.and.u32 pb|pnb, %4, lim, pact;\n\t"
-      "@pb sub.u32 %1, %1, t;\n\t"
-      "@pb mov.u32 %0, lim;\n\t"
-      "@pnb mov.u32 %1, q;\n\t"
-      "selp.u32 %5, 1, 0, pb;\n\t"
-      "}"
-      : "+r"(c.lower), "+r"(c.size), "+r"(c.slot), "+r"(c.count), "+r"(c.code), "=r"(b)
-      : "r"(actw), "r"(bitm), "r"(c.lt), "r"(p), "r"(prec), "l"(in1)
-      : "memory");
+  if constexpr (PREC == 7) {
+    asm volatile(PCS_DEC_STEP_ASM("shr.u32 q, r, 7;\n\t")
+                 : "+r"(c.lower), "+r"(c.size), "+r"(c.slot), "+r"(c.count), "+r"(c.code), "=r"(b)
+                 : "r"(actw), "r"(bitm), "r"(c.lt), "r"(p), "r"(prec), "l"(in1)
+                 : "memory");
+    return b;
+  }
+  asm volatile(PCS_DEC_STEP_ASM("shr.u32 q, r, %10;\n\t")
+               : "+r"(c.lower), "+r"(c.size), "+r"(c.slot), "+r"(c.count), "+r"(c.code), "=r"(b)
+               : "r"(actw), "r"(bitm), "r"(c.lt), "r"(p), "r"(prec), "l"(in1)
+               : "memory");
   return b;
 }
 
@@ -450,12 +460,21 @@ constexpr int kMaxProbRows = (3 * kMaxLevels + 1) * 15 + 32;  // shipped tables:
 #ifndef PCS_DEC_MINB
 #define PCS_DEC_MINB 5
 #endif
+__device__ __forceinline__ unsigned lds_u8(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+template <int PREC>
 __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const unsigned short* __restrict__ cw, const int* __restrict__ sizes,
                                                                       int* __restrict__ q, const BpcArgs p) {
   // decoded magnitude bit planes, same layout as the encoder's: word [32*half + k][lane], k < 16: plane k of
   // column 0, k >= 16: plane k-16 of column 1
   __shared__ unsigned s_pl[4][64][32];
-  __shared__ unsigned char s_sign0[64], s_sign1[256];
+  __shared__ unsigned char s_sign[64 + 256];  // sign-context tables: column 0 at [0, 64), column 1 at [64, 320)
+  unsigned char* const s_sign0 = s_sign;
+  unsigned char* const s_sign1 = s_sign + 64;
   // probability bytes per table row: [0..8] significance contexts, [9] refinement, [12..15] sign contexts
   __shared__ uint4 s_tab[kMaxProbRows + 1];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
@@ -466,6 +485,10 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
   for (int i = threadIdx.x; i <= zero_row; i += blockDim.x) s_tab[i] = i < zero_row ? __ldg(p.tab4 + i) : make_uint4(0, 0, 0, 0);
   __syncthreads();
   const unsigned char* const s_prob = reinterpret_cast<const unsigned char*>(s_tab);
+  // 32-bit shared address of the sign tables, made opaque so that it stays in a register instead of being rebuilt
+  // from the CTA's shared window at every use (4 uniform-datapath instructions per sign call site)
+  unsigned sgn0 = (unsigned)__cvta_generic_to_shared(s_sign);
+  asm volatile("mov.u32 %0, %0;" : "+r"(sgn0));
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int w = blockIdx.x * (blockDim.x >> 5) + wib;
   if (w >= p.total_cb) return;
@@ -554,12 +577,12 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
             const unsigned bitm = 1u << qq;
             // ---- column 0 ----
             unsigned ctx = (n0[qq] >> r0) + pnl + pns;  // bits above the nibble are masked at the look-up
-            const unsigned cn0 = dec_step(a40, bitm, prob[ctx & 15u], ac, in1, prec);
+            const unsigned cn0 = dec_step<PREC>(a40, bitm, prob[ctx & 15u], ac, in1, prec);
             unsigned neg0 = (g40 >> qq) & 1u;
             if (__any_sync(kFull, cn0)) {
               // horizontal: static (sign of the static sum), up: row i-1 now, down: static
-              const unsigned sc = s_sign0[((c0[qq] >> r0) & 15u) | u0];
-              const unsigned sym = dec_step(cn0, 1u, prob[12u + (sc >> 1)], ac, in1, prec);
+              const unsigned sc = lds_u8(sgn0 + (((c0[qq] >> r0) & 15u) | u0));
+              const unsigned sym = dec_step<PREC>(cn0, 1u, prob[12u + (sc >> 1)], ac, in1, prec);
               if (cn0) neg0 = (sym ^ sc) & 1u;  // BPCEngine.cu:583-589
             }
             nb0 = __funnelshift_r(nb0, cn0, 1); ng0 = __funnelshift_r(ng0, cn0 & neg0, 1);
@@ -570,11 +593,11 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
             const unsigned cnr = rv >> 2;
             // ---- column 1 ----
             ctx = (n1[qq] >> r0) + pns + pnr + cn0 + cnr;
-            const unsigned cn1 = dec_step(a41, bitm, prob[ctx & 15u], ac, in1, prec);
+            const unsigned cn1 = dec_step<PREC>(a41, bitm, prob[ctx & 15u], ac, in1, prec);
             unsigned neg1 = (g41 >> qq) & 1u;
             if (__any_sync(kFull, cn1)) {
-              const unsigned sc = s_sign1[((c1[qq] >> r0) & 3u) | (cur0 << 2) | ((rv & 3u) << 4) | u1];
-              const unsigned sym = dec_step(cn1, 1u, prob[12u + (sc >> 1)], ac, in1, prec);
+              const unsigned sc = lds_u8(sgn0 + 64u + (((c1[qq] >> r0) & 3u) | (cur0 << 2) | ((rv & 3u) << 4) | u1));
+              const unsigned sym = dec_step<PREC>(cn1, 1u, prob[12u + (sc >> 1)], ac, in1, prec);
               if (cn1) neg1 = (sym ^ sc) & 1u;
             }
             nb1 = __funnelshift_r(nb1, cn1, 1); ng1 = __funnelshift_r(ng1, cn1 & neg1, 1);
@@ -604,8 +627,8 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
       while (U) {
         const unsigned bitm = U & (0u - U);  // lowest row in which some lane refines
         U ^= bitm;
-        nb0 |= (0u - dec_step(r0m, bitm, pref, ac, in1, prec)) & bitm;
-        nb1 |= (0u - dec_step(r1m, bitm, pref, ac, in1, prec)) & bitm;
+        nb0 |= (0u - dec_step<PREC>(r0m, bitm, pref, ac, in1, prec)) & bitm;
+        nb1 |= (0u - dec_step<PREC>(r1m, bitm, pref, ac, in1, prec)) & bitm;
       }
       B0 |= (u64)nb0 << sh; B1 |= (u64)nb1 << sh;
     }
@@ -662,7 +685,8 @@ int bpc_encode(const void* d_coeff, bool is_float, uint16_t* d_cw, int32_t* d_si
 
 int bpc_decode(const uint16_t* d_cw, const int32_t* d_sizes, int32_t* d_q, const BpcArgs& a, cudaStream_t st) {
   const int blocks = (a.total_cb + 3) / 4;
-  bpc_decode_kernel<<<blocks, 128, 0, st>>>(d_cw, d_sizes, d_q, a);
+  if (a.prec == 7) bpc_decode_kernel<7><<<blocks, 128, 0, st>>>(d_cw, d_sizes, d_q, a);
+  else bpc_decode_kernel<0><<<blocks, 128, 0, st>>>(d_cw, d_sizes, d_q, a);
   ++g_launches;
   return (int)cudaGetLastError();
 }
