@@ -27,6 +27,8 @@ size_t dwt_scratch_elems(int Wa, int Ha, int wl);
 int dwt_forward(const uint8_t*, void*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t, DwtAux*, void* qws);
 size_t dwt_queue_ws_bytes(int Wa, int Ha, int wl, int frames);
 int dwt_forward_planes(const void*, void*, void*, int, int, int, bool, float, bool, int, cudaStream_t, void* qws);
+bool dwt_forward_rgb_ok(const uint8_t*, const void*, const void*, int, int, int, int, int);
+int dwt_forward_rgb(const uint8_t*, void*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t);
 int dwt_inverse_planes(const int32_t*, void*, void*, int, int, int, bool, float, int, cudaStream_t);
 int rgb_forward(const uint8_t*, void*, int, int, int, int, bool, int, cudaStream_t);
 int rgb_inverse(const void*, uint8_t*, int, int, int, int, bool, bool, int, cudaStream_t);
@@ -161,6 +163,12 @@ int run_dwt_forward(pcs_ctx* c, const Ws& w, const uint8_t* d_px, void* d_coeff,
   if (c->ncomp == 1)
     return dwt_forward(d_px, d_coeff, w.scratch, p.width, p.height, c->Wa, c->Ha, p.wavelet_levels, p.lossy != 0, p.quant_size, out_int,
                        frames, st, aux, w.dwtq);
+  // colour transform fused into the level-1 load where the streaming kernel applies ...
+  static const bool fuse_rgb = [] { const char* e = std::getenv("PCS_RGB_FUSE"); return !e || std::atoi(e) != 0; }();
+  if (fuse_rgb && dwt_forward_rgb_ok(d_px, d_coeff, w.scratch, p.width, p.height, c->Wa, c->Ha, p.wavelet_levels))
+    return dwt_forward_rgb(d_px, d_coeff, w.scratch, p.width, p.height, c->Wa, c->Ha, p.wavelet_levels, p.lossy != 0, p.quant_size,
+                           out_int, frames * 3, st);
+  // ... else as a pass of its own into 32-bit planes
   int rc = rgb_forward(d_px, w.tplanes, p.width, p.height, c->Wa, c->Ha, p.lossy != 0, frames, st);
   if (rc) return rc;
   return dwt_forward_planes(w.tplanes, d_coeff, w.scratch, c->Wa, c->Ha, p.wavelet_levels, p.lossy != 0, p.quant_size, out_int,

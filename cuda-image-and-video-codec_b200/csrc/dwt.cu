@@ -528,7 +528,7 @@ static size_t ll_offset(int Wa, int Ha, int l) {
 
 bool dwt_forward_fast_ok(const void*, const void*, const void*, bool, int, long long, int, int, int, int);
 int dwt_forward_fast(const void*, bool, long long, int, int, int, int, void*, long long, int, void*, long long, int, int, int, int, bool, float,
-                     bool, int, cudaStream_t);
+                     bool, int, cudaStream_t, bool rgb, long long comp_stride);
 
 bool dwt_inverse_fast_ok(const void*, const void*, const void*, bool, int, long long, int, long long, int, int);
 int dwt_inverse_fast(const int32_t*, long long, int, const void*, long long, int, bool, int, int, void*, bool, long long, int, int, int, bool,
@@ -550,9 +550,11 @@ static int fuse_mode() {
 // Host loop over levels (replaces DWTEngine::DWTForward, DWT/DWTGenerator.cu:1268-1342; no host
 // synchronisation between levels).  out_int: 9/7 only, write (int)c instead of c.
 // tplane != nullptr (RGB path): level 1 reads colour-transformed 32-bit planes [frames][Ha][Wa] instead of u8 pixels.
+// rgb_px (RGB path, fused): d_px holds planar u8 RGB frames, `frames` counts component planes, level 1 applies the
+// colour transform in its load (streaming kernel only: the caller checks dwt_forward_rgb_ok first).
 static int dwt_forward_levels(const uint8_t* d_px, void* d_coeff, void* d_scratch, int W, int H, int Wa, int Ha, int wl,
                               bool lossy, float qs, bool out_int, int frames, int lfirst, int llast, cudaStream_t st,
-                              const void* tplane = nullptr) {
+                              const void* tplane = nullptr, bool rgb_px = false) {
   const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl);
   int first = lfirst;
   // leading levels through the streaming kernel of dwt_fast.cu while the geometry allows it
@@ -560,9 +562,9 @@ static int dwt_forward_levels(const uint8_t* d_px, void* d_coeff, void* d_scratc
     const int l = first, Wc = Wa >> (l - 1), Hc = Ha >> (l - 1);
     const bool u8 = l == 1 && !tplane;
     const void* src = u8 ? static_cast<const void*>(d_px) : l == 1 ? tplane : static_cast<const char*>(d_scratch) + ll_offset(Wa, Ha, l - 1) * 4;
-    const long long sfs = u8 ? (long long)W * H : l == 1 ? (long long)A : (long long)S;
+    const long long sfs = u8 ? (long long)W * H * (rgb_px ? 3 : 1) : l == 1 ? (long long)A : (long long)S;
     const int sp = u8 ? W : Wc;
-    int lv = (u8 && fuse_mode() == 2 && llast >= 2) ? 2 : 1;
+    int lv = (u8 && !rgb_px && fuse_mode() == 2 && llast >= 2) ? 2 : 1;
     void* ll = (l + lv - 1 == wl) ? nullptr : static_cast<char*>(d_scratch) + ll_offset(Wa, Ha, l + lv - 1) * 4;
     if (!dwt_forward_fast_ok(src, d_coeff, ll, u8, sp, sfs, H, Wc, Hc, lv)) {
       if (lv == 2) { lv = 1; ll = (l == wl) ? nullptr : static_cast<char*>(d_scratch) + ll_offset(Wa, Ha, l) * 4; }
@@ -570,7 +572,7 @@ static int dwt_forward_levels(const uint8_t* d_px, void* d_coeff, void* d_scratc
     }
     if (S % 4) break;
     int rc = dwt_forward_fast(src, u8, sfs, sp, H, Wc, Hc, d_coeff, (long long)A, Wa, ll, (long long)S, Wa >> (l + lv - 1), l, lv, wl, lossy,
-                              qs, out_int, frames, st);
+                              qs, out_int, frames, st, u8 && rgb_px, (long long)W * H);
     if (rc) return rc;
     first = l + lv;
   }
@@ -793,6 +795,19 @@ int dwt_inverse(const int32_t* d_q, uint8_t* d_px, void* d_scratch, int W, int H
   PCS_CUDA_TRY(cudaStreamWaitEvent(st, aux->ev[1], 0));
   PCS_CUDA_TRY(cudaStreamWaitEvent(st, aux->ev[2], 0));
   return (int)cudaGetLastError();
+}
+
+// RGB path, forward, colour transform fused into the level-1 load: possible when the streaming kernel takes level 1
+// of this geometry (no horizontal padding, 8-byte aligned colour planes).
+bool dwt_forward_rgb_ok(const uint8_t* d_px, const void* d_coeff, const void* d_scratch, int W, int H, int Wa, int Ha, int wl) {
+  const size_t S = dwt_scratch_elems(Wa, Ha, wl);
+  const void* ll = wl == 1 ? nullptr : static_cast<const char*>(d_scratch) + ll_offset(Wa, Ha, 1) * 4;
+  return fuse_mode() > 0 && S % 4 == 0 && ((long long)W * H) % 8 == 0 &&
+         dwt_forward_fast_ok(d_px, d_coeff, ll, true, W, (long long)W * H * 3, H, Wa, Ha, 1);
+}
+int dwt_forward_rgb(const uint8_t* d_px, void* d_coeff, void* d_scratch, int W, int H, int Wa, int Ha, int wl, bool lossy, float qs,
+                    bool out_int, int planes, cudaStream_t st) {
+  return dwt_forward_levels(d_px, d_coeff, d_scratch, W, H, Wa, Ha, wl, lossy, qs, out_int, planes, 1, wl, st, nullptr, true);
 }
 
 // RGB path: the same transforms on colour-transformed 32-bit planes (`planes` = frames x 3 components).

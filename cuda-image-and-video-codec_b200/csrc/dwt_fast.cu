@@ -61,6 +61,7 @@ struct FastFwdArgs {
   float q1[4], q2[4], qs;                                   // quantiser steps of the first / second level of this launch: LL, HL, LH, HH
   int nW1, ls1, nW2, ls2;                                   // row-variant tiling of the reference, per level (9/7 only)
   int nstrips, nchunks, rp;                                 // rp: row pairs per chunk (multiple of 4)
+  long long comp_stride;                                    // RGB input: bytes between the R, G and B planes of a frame
 };
 
 // Which row PAIR the reference computes with the fused neighbour sum (dwt.cu fwd97_row_variant restated
@@ -358,6 +359,24 @@ __device__ __forceinline__ void emit_pair(const T (&lo)[NS], const T (&hi)[NS], 
   }
 }
 
+// ---- colour transform fused into the level-1 load (RGB path) -----------------------------------------------------
+// Component `comp` (0 = Y, 1 = Cb = B-G, 2 = Cr = R-G) of 8 level-shifted RGB pixels: the reversible transform for 5/3
+// (Engines/CodingEngine.cu:357-380), the irreversible one for 9/7 in the operation order of the reference binary
+// (t = G*m1; t = fma(R, m0, t); t = fma(B, m2, t), see color.cu), two pixels per packed instruction.
+__device__ __forceinline__ void rgb_component(int comp, const int (&r)[8], const int (&g)[8], const int (&b)[8], int (&v)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = comp == 0 ? (r[j] + 2 * g[j] + b[j]) >> 2 : comp == 1 ? b[j] - g[j] : r[j] - g[j];
+}
+__device__ __forceinline__ void rgb_component(int comp, const float (&r)[8], const float (&g)[8], const float (&b)[8], float (&v)[8]) {
+  const float m0 = comp == 0 ? 0.299f : comp == 1 ? -0.168736f : 0.5f;
+  const float m1 = comp == 0 ? 0.587f : comp == 1 ? -0.331264f : -0.418688f;
+  const float m2 = comp == 0 ? 0.114f : comp == 1 ? 0.5f : -0.081312f;
+  const f2 M0 = pk(m0, m0), M1 = pk(m1, m1), M2 = pk(m2, m2);
+#pragma unroll
+  for (int j = 0; j < 8; j += 2)
+    upk(fma2(pk(b[j], b[j + 1]), M2, fma2(pk(r[j], r[j + 1]), M0, mul2(pk(g[j], g[j + 1]), M1))), v[j], v[j + 1]);
+}
+
 // One work item = one 256-column strip x one chunk of row pairs of one frame, one level (LEVELS = 1; LL -> scratch or,
 // if last, -> out) or two fused levels (LEVELS = 2, u8 input only).  SRC_U8: the input is the u8 frame (level 1), else
 // the 32-bit LL plane of the level above.  COH: that plane was written by other SMs during this very launch (queue
@@ -377,8 +396,11 @@ typedef unsigned char FwdRing[kFwdDepth][2][32][8];
 #ifndef PCS_FWD_MINB
 #define PCS_FWD_MINB 4
 #endif
-template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS, bool QS1, bool COH>
+// RGB (u8 input, one level): `frame` is a component PLANE 3f + c of planar RGB frames; the three colour planes of
+// frame f are staged side by side (ringp[0..2]) and the colour transform runs in the load.
+template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS, bool QS1, bool COH, bool RGB = false>
 __device__ __forceinline__ void fwd_item(const FastFwdArgs& a, const int strip, const int chunk, const int frame, FwdRing* const ringp) {
+  static_assert(!RGB || (SRC_U8 && LEVELS == 1), "the fused colour transform reads u8 pixels and feeds one level");
   using T = typename VSel<LOSSY, 8>::T;
   using VP1 = typename VSel<LOSSY, 8>::type;
   using VP2 = typename VSel<LOSSY, 4>::type;
@@ -394,7 +416,8 @@ __device__ __forceinline__ void fwd_item(const FastFwdArgs& a, const int strip, 
   const bool left = c0 == 0, right = c0 + 8 == Wc;
   // lanes outside the image read inside it; their values are never used (explicit border rules)
   const int cl = min(max(c0, 0), Wc - 8);
-  const unsigned char* const src8 = static_cast<const unsigned char*>(a.src) + (size_t)frame * a.src_fstride + cl;
+  const int sframe = RGB ? frame / 3 : frame, comp = RGB ? frame - 3 * sframe : 0;  // source frame, colour component
+  const unsigned char* const src8 = static_cast<const unsigned char*>(a.src) + (size_t)sframe * a.src_fstride + cl;
   const T* const srcT = static_cast<const T*>(a.src) + (size_t)frame * a.src_fstride + cl;
   OT* const out = static_cast<OT*>(a.out) + (size_t)frame * a.out_fstride;
   T* const llbase = a.last ? nullptr : static_cast<T*>(a.ll) + (size_t)frame * a.ll_fstride;
@@ -420,9 +443,26 @@ __device__ __forceinline__ void fwd_item(const FastFwdArgs& a, const int strip, 
     return ys;
   };
   auto issue_step = [&](int m, int slot) {  // rows 2m+1, 2m+2 (rows past the chunk fold to valid rows and are not used)
-    cp_async8(&ring[slot][0][lane][0], src8 + (size_t)row_index(2 * m + 1) * a.src_pitch);
-    cp_async8(&ring[slot][1][lane][0], src8 + (size_t)row_index(2 * m + 2) * a.src_pitch);
+    const unsigned char* const r1 = src8 + (size_t)row_index(2 * m + 1) * a.src_pitch;
+    const unsigned char* const r2 = src8 + (size_t)row_index(2 * m + 2) * a.src_pitch;
+#pragma unroll
+    for (int k = 0; k < (RGB ? 3 : 1); ++k) {
+      cp_async8(&ringp[k][slot][0][lane][0], r1 + (size_t)k * a.comp_stride);
+      cp_async8(&ringp[k][slot][1][lane][0], r2 + (size_t)k * a.comp_stride);
+    }
     cp_async_commit();
+  };
+  // level-1 samples of a staged row (r = 0 / 1: the odd / even row of the step in ring slot `slot`)
+  auto ring_row = [&](int slot, int r, T (&v)[8]) {
+    if constexpr (RGB) {
+      T cr[8], cg[8], cb[8];
+      unpack8(*reinterpret_cast<const uint2*>(&ringp[0][slot][r][lane][0]), cr);
+      unpack8(*reinterpret_cast<const uint2*>(&ringp[1][slot][r][lane][0]), cg);
+      unpack8(*reinterpret_cast<const uint2*>(&ringp[2][slot][r][lane][0]), cb);
+      rgb_component(comp, cr, cg, cb, v);
+    } else {
+      unpack8(*reinterpret_cast<const uint2*>(&ring[slot][r][lane][0]), v);
+    }
   };
   auto load_row = [&](int y) -> RowT {
     if constexpr (SRC_U8) {
@@ -451,7 +491,16 @@ __device__ __forceinline__ void fwd_item(const FastFwdArgs& a, const int strip, 
   }
   {
     T r[8];
-    unpack8(load_row(2 * ms), r);
+    if constexpr (RGB) {
+      const unsigned char* const p = src8 + (size_t)row_index(2 * ms) * a.src_pitch;
+      T cr[8], cg[8], cb[8];
+      unpack8(__ldg(reinterpret_cast<const uint2*>(p)), cr);
+      unpack8(__ldg(reinterpret_cast<const uint2*>(p + a.comp_stride)), cg);
+      unpack8(__ldg(reinterpret_cast<const uint2*>(p + 2 * a.comp_stride)), cb);
+      rgb_component(comp, cr, cg, cb, r);
+    } else {
+      unpack8(load_row(2 * ms), r);
+    }
     v1.init(r);
   }
   int slot = 0;
@@ -461,8 +510,8 @@ __device__ __forceinline__ void fwd_item(const FastFwdArgs& a, const int strip, 
     T xo[8], x2[8], lo[8], hi[8];
     if constexpr (SRC_U8) {
       cp_async_wait<kDepth - 1>();  // the group of step m has landed
-      unpack8(*reinterpret_cast<const uint2*>(&ring[slot][0][lane][0]), xo);
-      unpack8(*reinterpret_cast<const uint2*>(&ring[slot][1][lane][0]), x2);
+      ring_row(slot, 0, xo);
+      ring_row(slot, 1, x2);
       issue_step(m + kDepth, slot);
       slot = slot + 1 == kDepth ? 0 : slot + 1;
     } else {
@@ -530,12 +579,13 @@ __device__ __forceinline__ void fwd_item(const FastFwdArgs& a, const int strip, 
 #ifndef PCS_FWD_MINB_U8
 #define PCS_FWD_MINB_U8 4
 #endif
-template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS, bool QS1>
+template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS, bool QS1, bool RGB = false>
 __global__ void __launch_bounds__(128, LEVELS == 2 ? 3 : SRC_U8 ? PCS_FWD_MINB_U8 : PCS_FWD_MINB) dwt_forward_fused(const FastFwdArgs a) {
-  __shared__ __align__(16) FwdRing s_ring[SRC_U8 ? 4 : 1];
+  __shared__ __align__(16) FwdRing s_ring[SRC_U8 ? 4 : 1][RGB ? 3 : 1];
   const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (item >= a.nstrips * a.nchunks) return;
-  fwd_item<LOSSY, OT, SRC_U8, LEVELS, QS1, false>(a, item % a.nstrips, item / a.nstrips, blockIdx.y, &s_ring[SRC_U8 ? (threadIdx.x >> 5) : 0]);
+  fwd_item<LOSSY, OT, SRC_U8, LEVELS, QS1, false, RGB>(a, item % a.nstrips, item / a.nstrips, blockIdx.y,
+                                                       &s_ring[SRC_U8 ? (threadIdx.x >> 5) : 0][0]);
 }
 
 // quantiser steps, [level-1][LL,HL,LH,HH] (DWT/DWTGenerator.cuh:168-179)
@@ -576,19 +626,19 @@ long long resident_ctas(K kernel) {
 }
 
 // The chunk length is chosen per kernel variant, for the number of CTAs that variant really keeps resident.
-template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS, bool QS1>
+template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS, bool QS1, bool RGB = false>
 void launch_k(FastFwdArgs a, int frames, cudaStream_t st) {
-  static const long long slots = resident_ctas(dwt_forward_fused<LOSSY, OT, SRC_U8, LEVELS, QS1>);
+  static const long long slots = resident_ctas(dwt_forward_fused<LOSSY, OT, SRC_U8, LEVELS, QS1, RGB>);
   const int hh1 = a.Hc >> 1;
   a.rp = choose_rp(a.nstrips, hh1, frames, LEVELS == 2 ? 12 : 3, 4, slots);
   a.nchunks = (hh1 + a.rp - 1) / a.rp;
   dim3 grid((a.nstrips * a.nchunks + 3) / 4, frames);
-  dwt_forward_fused<LOSSY, OT, SRC_U8, LEVELS, QS1><<<grid, 128, 0, st>>>(a);
+  dwt_forward_fused<LOSSY, OT, SRC_U8, LEVELS, QS1, RGB><<<grid, 128, 0, st>>>(a);
 }
-template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS>
+template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS, bool RGB = false>
 void launch(const FastFwdArgs& a, int frames, cudaStream_t st) {
-  if (a.qs == 1.0f) launch_k<LOSSY, OT, SRC_U8, LEVELS, true>(a, frames, st);
-  else launch_k<LOSSY, OT, SRC_U8, LEVELS, false>(a, frames, st);
+  if (a.qs == 1.0f) launch_k<LOSSY, OT, SRC_U8, LEVELS, true, RGB>(a, frames, st);
+  else launch_k<LOSSY, OT, SRC_U8, LEVELS, false, RGB>(a, frames, st);
 }
 
 
@@ -1164,8 +1214,11 @@ bool dwt_forward_fast_ok(const void* src, const void* d_coeff, const void* ll, b
 // `levels` (1 or 2) levels of the forward transform, starting at 1-based level `level`, in one launch.
 int dwt_forward_fast(const void* src, bool src_u8, long long src_fstride, int src_pitch, int H, int Wc, int Hc, void* d_coeff,
                      long long out_fstride, int pitch, void* d_ll, long long ll_fstride, int ll_pitch, int level, int levels, int wl,
-                     bool lossy, float qs, bool out_int, int frames, cudaStream_t st) {
+                     bool lossy, float qs, bool out_int, int frames, cudaStream_t st, bool rgb, long long comp_stride) {
+  // rgb: src = planar u8 RGB frames (src_fstride per FRAME, comp_stride between colour planes), `frames` counts
+  // component planes (3 per frame) and the colour transform is fused into the load (one level only)
   FastFwdArgs a{};
+  a.comp_stride = comp_stride;
   a.src = src; a.src_fstride = src_fstride; a.src_pitch = src_pitch; a.H = src_u8 ? H : Hc; a.Wc = Wc; a.Hc = Hc;
   a.out = d_coeff; a.out_fstride = out_fstride; a.pitch = pitch;
   a.ll = d_ll; a.ll_fstride = ll_fstride; a.ll_pitch = ll_pitch;
@@ -1181,6 +1234,10 @@ int dwt_forward_fast(const void* src, bool src_u8, long long src_fstride, int sr
       if (!lossy) launch<false, int, true, 2>(a, frames, st);
       else if (out_int) launch<true, int, true, 2>(a, frames, st);
       else launch<true, float, true, 2>(a, frames, st);
+    } else if (rgb) {
+      if (!lossy) launch<false, int, true, 1, true>(a, frames, st);
+      else if (out_int) launch<true, int, true, 1, true>(a, frames, st);
+      else launch<true, float, true, 1, true>(a, frames, st);
     } else {
       if (!lossy) launch<false, int, true, 1>(a, frames, st);
       else if (out_int) launch<true, int, true, 1>(a, frames, st);
