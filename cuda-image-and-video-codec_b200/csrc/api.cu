@@ -32,6 +32,8 @@ int dwt_forward_rgb(const uint8_t*, void*, void*, int, int, int, int, int, bool,
 int dwt_inverse_planes(const int32_t*, void*, void*, int, int, int, bool, float, int, cudaStream_t);
 int rgb_forward(const uint8_t*, void*, int, int, int, int, bool, int, cudaStream_t);
 int rgb_inverse(const void*, uint8_t*, int, int, int, int, bool, bool, int, cudaStream_t);
+bool dwt_inverse_rgb_ok(const int32_t*, const uint8_t*, const void*, int, int, int, int, int);
+int dwt_inverse_rgb(const int32_t*, uint8_t*, void*, int, int, int, int, int, bool, float, int, cudaStream_t);
 int dwt_inverse(const int32_t*, uint8_t*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t, DwtAux*);
 int bpc_encode(const void*, bool, uint16_t*, int32_t*, const BpcArgs&, cudaStream_t);
 int bpc_decode(const uint16_t*, const int32_t*, int32_t*, const BpcArgs&, cudaStream_t);
@@ -181,6 +183,10 @@ int run_dwt_inverse(pcs_ctx* c, const Ws& w, const int32_t* d_q, uint8_t* d_px, 
   if (c->ncomp == 1)
     return dwt_inverse(d_q, d_px, w.scratch, p.width, p.height, c->Wa, c->Ha, p.wavelet_levels, p.lossy != 0, p.quant_size, flat, frames,
                        st, aux);
+  static const bool fuse_rgb = [] { const char* e = std::getenv("PCS_RGB_FUSE"); return !e || std::atoi(e) != 0; }();
+  if (fuse_rgb && dwt_inverse_rgb_ok(d_q, d_px, w.scratch, p.width, p.height, c->Wa, c->Ha, p.wavelet_levels))
+    return dwt_inverse_rgb(d_q, d_px, w.scratch, p.width, p.height, c->Wa, c->Ha, p.wavelet_levels, p.lossy != 0, p.quant_size, frames * 3,
+                           st);
   int rc = dwt_inverse_planes(d_q, w.tplanes, w.scratch, c->Wa, c->Ha, p.wavelet_levels, p.lossy != 0, p.quant_size, frames * 3, st);
   if (rc) return rc;
   return rgb_inverse(w.tplanes, d_px, p.width, p.height, c->Wa, c->Ha, p.lossy != 0, flat, frames, st);

@@ -532,7 +532,7 @@ int dwt_forward_fast(const void*, bool, long long, int, int, int, int, void*, lo
 
 bool dwt_inverse_fast_ok(const void*, const void*, const void*, bool, int, long long, int, long long, int, int);
 int dwt_inverse_fast(const int32_t*, long long, int, const void*, long long, int, bool, int, int, void*, bool, long long, int, int, int, bool,
-                     float, int, cudaStream_t);
+                     float, int, cudaStream_t, bool rgb, long long comp_stride);
 int dwt_forward_queue(const void*, bool, int, int, int, int, void*, void*, int, bool, float, bool, int, void*, cudaStream_t, int*);
 
 // PCS_DWT_FUSE = 0: per-level kernels of this file only; 1: streaming kernel of dwt_fast.cu, one level per launch
@@ -620,8 +620,11 @@ static int dwt_forward_levels(const uint8_t* d_px, void* d_coeff, void* d_scratc
 // Replaces DWTEngine::DWTReverse (DWT/DWTGenerator.cu:1349-1424) + removeOffsetAndApplyMaxMin[Lossy].
 // tplane != nullptr (RGB path): level 1 writes 32-bit planes [frames][Ha][Wa] for the inverse colour transform
 // instead of clamped u8 pixels.
+// rgb_px (RGB path, fused): `frames` counts component planes, level 1 writes planar u8 RGB frames to d_px with the
+// inverse colour transform in its store (streaming kernel only: the caller checks dwt_inverse_rgb_ok first).
 static int dwt_inverse_levels(const int32_t* d_q, uint8_t* d_px, void* d_scratch, int W, int H, int Wa, int Ha, int wl, bool lossy,
-                              float qs, bool flat_crop, int frames, int lhigh, int llow, cudaStream_t st, void* tplane = nullptr) {
+                              float qs, bool flat_crop, int frames, int lhigh, int llow, cudaStream_t st, void* tplane = nullptr,
+                              bool rgb_px = false) {
   const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl);
   for (int l = lhigh; l >= llow; --l) {
     InvArgs a{};
@@ -635,7 +638,7 @@ static int dwt_inverse_levels(const int32_t* d_q, uint8_t* d_px, void* d_scratch
     a.W = W; a.H = H; a.flat_crop = flat_crop ? 1 : 0;
     const bool px_out = l == 1 && !tplane;
     if (px_out) {
-      a.dst = d_px; a.dst_fstride = (long long)W * H; a.dst_pitch = W;
+      a.dst = d_px; a.dst_fstride = (long long)W * H * (rgb_px ? 3 : 1); a.dst_pitch = W;
       a.dst_vec = (W == Wa) && ((reinterpret_cast<uintptr_t>(d_px) & 3) == 0) && (((long long)W * H) % 4 == 0);
     } else if (l == 1) {
       a.dst = tplane; a.dst_fstride = (long long)A; a.dst_pitch = Wa;
@@ -649,8 +652,9 @@ static int dwt_inverse_levels(const int32_t* d_q, uint8_t* d_px, void* d_scratch
     a.rqs = 1.0f / qs;
     if (fuse_mode() > 0 && S % 4 == 0 && !(px_out && flat_crop && W != Wa) &&
         dwt_inverse_fast_ok(d_q, a.first ? nullptr : a.ll, a.dst, px_out, a.dst_pitch, a.dst_fstride, a.ll_pitch, a.ll_fstride, a.Wc, a.Hc)) {
+      const bool rgb = px_out && rgb_px;
       int rc = dwt_inverse_fast(d_q, (long long)A, Wa, a.first ? nullptr : a.ll, a.ll_fstride, a.ll_pitch, a.first != 0, a.Wc, a.Hc, a.dst, px_out,
-                                a.dst_fstride, a.dst_pitch, H, l, lossy, qs, frames, st);
+                                a.dst_fstride, a.dst_pitch, H, l, lossy, qs, rgb ? frames / 3 : frames, st, rgb, (long long)W * H);
       if (rc) return rc;
       continue;
     }
@@ -820,6 +824,18 @@ int dwt_forward_planes(const void* d_tplanes, void* d_coeff, void* d_scratch, in
     if (done > 0) return dwt_forward_levels(nullptr, d_coeff, d_scratch, Wa, Ha, Wa, Ha, wl, lossy, qs, out_int, planes, done + 1, wl, st, d_tplanes);
   }
   return dwt_forward_levels(nullptr, d_coeff, d_scratch, Wa, Ha, Wa, Ha, wl, lossy, qs, out_int, planes, 1, wl, st, d_tplanes);
+}
+// RGB path, inverse, colour transform fused into the level-1 store: possible when the streaming kernel produces level 1
+// of this geometry (no horizontal crop, 8-byte aligned colour planes).
+bool dwt_inverse_rgb_ok(const int32_t* d_q, const uint8_t* d_px, const void* d_scratch, int W, int H, int Wa, int Ha, int wl) {
+  const size_t S = dwt_scratch_elems(Wa, Ha, wl);
+  const void* ll = wl == 1 ? nullptr : static_cast<const char*>(d_scratch) + ll_offset(Wa, Ha, 1) * 4;
+  return fuse_mode() > 0 && S % 4 == 0 && W == Wa && ((long long)W * H) % 8 == 0 &&
+         dwt_inverse_fast_ok(d_q, ll, d_px, true, W, (long long)W * H * 3, Wa >> 1, (long long)S, Wa, Ha);
+}
+int dwt_inverse_rgb(const int32_t* d_q, uint8_t* d_px, void* d_scratch, int W, int H, int Wa, int Ha, int wl, bool lossy, float qs,
+                    int planes, cudaStream_t st) {
+  return dwt_inverse_levels(d_q, d_px, d_scratch, W, H, Wa, Ha, wl, lossy, qs, false, planes, wl, 1, st, nullptr, true);
 }
 int dwt_inverse_planes(const int32_t* d_q, void* d_tplanes, void* d_scratch, int Wa, int Ha, int wl, bool lossy, float qs, int planes,
                        cudaStream_t st) {

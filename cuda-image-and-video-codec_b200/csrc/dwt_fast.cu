@@ -840,6 +840,7 @@ void launch_queue(const FwdQueueArgs& q, cudaStream_t st) {
 // inverse
 // =================================================================================================
 struct FastInvArgs {
+  long long comp_stride;   // RGB output: bytes between the R, G and B planes of a frame
   const int32_t* q; long long q_fstride; int pitch;        // quantised Mallat plane, row pitch = adapted frame width
   const void* ll; long long ll_fstride; int ll_pitch;      // LL source (scratch, type T) unless `first`
   int first;                                               // coarsest level: LL comes from q (de-quantised)
@@ -1018,7 +1019,10 @@ __device__ __forceinline__ unsigned sat_u8(float v) {  // clamp(rn(v), 0, 255)
   return r;
 }
 
-template <bool LOSSY, bool DST_U8, bool FIRST, bool QS1>
+// RGB (u8 output only): a CTA is three warps, warp w reconstructs component w (Y, Cb, Cr) of the SAME strip and chunk of
+// frame blockIdx.y; the rows of a step are exchanged through shared memory, warp w then forms colour plane w (R, G, B) --
+// the inverse colour transform (Engines/DecodingEngine.cu:599-650) fused into the final store.
+template <bool LOSSY, bool DST_U8, bool FIRST, bool QS1, bool RGB = false>
 #ifndef PCS_INV_MINB
 #define PCS_INV_MINB 4
 #endif
@@ -1029,10 +1033,11 @@ __global__ void __launch_bounds__(128, PCS_INV_MINB) dwt_inverse_fast_kernel(con
   using T = typename VSel<LOSSY, 8>::T;
   using VP = typename IVSel<LOSSY, 8>::type;
   using T4 = typename std::conditional<LOSSY, float4, int4>::type;
-  const int lane = threadIdx.x & 31;
-  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (item >= a.nstrips * a.nchunks) return;
-  const int frame = blockIdx.y;
+  static_assert(!RGB || DST_U8, "the fused inverse colour transform writes u8 pixels");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int item = RGB ? blockIdx.x : blockIdx.x * (blockDim.x >> 5) + warp;
+  if (item >= a.nstrips * a.nchunks) return;  // RGB: the same for the three warps of the CTA
+  const int frame = RGB ? 3 * blockIdx.y + warp : blockIdx.y;  // component plane this warp reconstructs
   const int strip = item % a.nstrips, chunk = item / a.nstrips;
   const int Wc = a.Wc, Hc = a.Hc, hw = Wc >> 1, hh = Hc >> 1;
   const int c0 = strip * 240 - 8 + 8 * lane;
@@ -1076,8 +1081,8 @@ __global__ void __launch_bounds__(128, PCS_INV_MINB) dwt_inverse_fast_kernel(con
   // through a per-warp cp.async ring kDepth steps deep, as the forward level-1 kernel does.
   constexpr int kDepth = 4;
   constexpr bool kRing = DST_U8 || (PCS_INV_RING_ALL && LOSSY);  // deeper 9/7 levels too: see PCS_INV_RING_ALL
-  __shared__ __align__(16) unsigned char s_ring[kRing ? 4 : 1][kRing ? kDepth : 1][4][32][16];
-  auto& ring = s_ring[kRing ? (threadIdx.x >> 5) : 0];
+  __shared__ __align__(16) unsigned char s_ring[kRing ? (RGB ? 3 : 4) : 1][kRing ? kDepth : 1][4][32][16];
+  auto& ring = s_ring[kRing ? warp : 0];
   auto issue_pair = [&](int n, int slot) {
     int rl, rh;
     pair_rows(n, rl, rh);
@@ -1143,6 +1148,32 @@ __global__ void __launch_bounds__(128, PCS_INV_MINB) dwt_inverse_fast_kernel(con
     }
   };
 
+  // RGB: exchange of a step's two rows between the three component warps (double buffered: one barrier per step)
+  __shared__ __align__(16) T s_x[RGB ? 2 : 1][RGB ? 2 : 1][RGB ? 3 : 1][32][8];
+  auto colour_row = [&](int y, const T (&cy)[8], const T (&cb)[8], const T (&cr)[8]) {  // colour plane `warp` of row y
+    if (y >= a.H) return;
+    unsigned b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int v;
+      if constexpr (LOSSY) {  // DecodingEngine.cu:620-640 in the operation order of color.cu
+        const float t = warp == 0 ? __fmaf_rn(cr[j], 1.402f, cy[j])
+                      : warp == 1 ? __fmaf_rn(cr[j], -0.714136f, __fmaf_rn(cb[j], -0.344136f, cy[j]))
+                                  : __fmaf_rn(cb[j], 1.772f, cy[j]);
+        v = __float2int_rn(__fadd_rn(t, 0.01f));
+      } else {
+        const int g = cy[j] - ((cb[j] + cr[j]) >> 2);
+        v = warp == 0 ? cr[j] + g : warp == 1 ? g : cb[j] + g;
+      }
+      b[j] = (unsigned)min(max(v + 128, 0), 255);
+    }
+    uint2 w;
+    w.x = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+    w.y = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+    __stcs(reinterpret_cast<uint2*>(static_cast<unsigned char*>(a.dst) + (size_t)blockIdx.y * a.dst_fstride + (size_t)warp * a.comp_stride +
+                                    (size_t)y * a.dst_pitch + c0), w);
+  };
+
   const int n0 = chunk * a.rp, n1 = min(n0 + a.rp, hh);
   VP vp; vp.init();
   const int ms = n0 - VP::kLead, mend = n1 + VP::kTail;
@@ -1170,7 +1201,28 @@ __global__ void __launch_bounds__(128, PCS_INV_MINB) dwt_inverse_fast_kernel(con
     if constexpr (LOSSY) { hinv97_rows<8>(lo, hi, left, right); iv97_step_packed<8>(vp, lo, hi, re, ro); }
     else { hinv53<8>(lo, left, right); hinv53<8>(hi, left, right); vp.step(lo, hi, re, ro); }
     const int yo = VP::odd_row(m), ye = VP::even_row(m);
-    if (wlane) {
+    if constexpr (RGB) {
+      const int buf = m & 1;
+      T4* const mine_o = reinterpret_cast<T4*>(&s_x[buf][0][warp][lane][0]);
+      T4* const mine_e = reinterpret_cast<T4*>(&s_x[buf][1][warp][lane][0]);
+      T4 t;
+      t.x = ro[0]; t.y = ro[1]; t.z = ro[2]; t.w = ro[3]; mine_o[0] = t;
+      t.x = ro[4]; t.y = ro[5]; t.z = ro[6]; t.w = ro[7]; mine_o[1] = t;
+      t.x = re[0]; t.y = re[1]; t.z = re[2]; t.w = re[3]; mine_e[0] = t;
+      t.x = re[4]; t.y = re[5]; t.z = re[6]; t.w = re[7]; mine_e[1] = t;
+      __syncthreads();  // every warp of the CTA runs the same steps (same strip and chunk), so this is uniform
+      if (wlane) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int y = r ? ye : yo;
+          if (y < 2 * n0 || y >= 2 * n1) continue;
+          T cy[8], cb[8], cr[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { cy[j] = s_x[buf][r][0][lane][j]; cb[j] = s_x[buf][r][1][lane][j]; cr[j] = s_x[buf][r][2][lane][j]; }
+          colour_row(y, cy, cb, cr);
+        }
+      }
+    } else if (wlane) {
       if (yo >= 2 * n0 && yo < 2 * n1) store_row(yo, ro);
       if (ye >= 2 * n0 && ye < 2 * n1) store_row(ye, re);
     }
@@ -1188,6 +1240,24 @@ void launch_inv_k(FastInvArgs a, int frames, cudaStream_t st) {
   dim3 grid((a.nstrips * a.nchunks + 3) / 4, frames);
   dwt_inverse_fast_kernel<LOSSY, DST_U8, FIRST, QS1><<<grid, 128, 0, st>>>(a);
 }
+// RGB: one item (three component warps) per CTA of 96 threads, grid.y counts frames
+template <bool LOSSY, bool FIRST, bool QS1>
+void launch_inv_rgb_k(FastInvArgs a, int frames, cudaStream_t st) {
+  static const long long slots = [] {
+    int dev = 0, sms = 148, per_sm = 4;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwt_inverse_fast_kernel<LOSSY, true, FIRST, QS1, true>, 96, 0);
+    return (long long)sms * std::max(per_sm, 1);
+  }();
+  const int hh = a.Hc >> 1;
+  // choose_rp counts CTAs of four items: present a CTA of one item as four times as many slots
+  a.rp = choose_rp(a.nstrips, hh, frames, 4, 2, slots / 4 > 0 ? slots / 4 : 1);
+  a.nchunks = (hh + a.rp - 1) / a.rp;
+  dim3 grid(a.nstrips * a.nchunks, frames);
+  dwt_inverse_fast_kernel<LOSSY, true, FIRST, QS1, true><<<grid, 96, 0, st>>>(a);
+}
+
 template <bool LOSSY, bool DST_U8, bool FIRST>
 void launch_inv(const FastInvArgs& a, int frames, bool qs1, cudaStream_t st) {
   if (qs1) launch_inv_k<LOSSY, DST_U8, FIRST, true>(a, frames, st);
@@ -1336,8 +1406,11 @@ bool dwt_inverse_fast_ok(const void* q, const void* ll, const void* dst, bool ds
 
 int dwt_inverse_fast(const int32_t* d_q, long long q_fstride, int pitch, const void* ll, long long ll_fstride, int ll_pitch, bool first,
                      int Wc, int Hc, void* dst, bool dst_u8, long long dst_fstride, int dst_pitch, int H, int level, bool lossy, float qs,
-                     int frames, cudaStream_t st) {
+                     int frames, cudaStream_t st, bool rgb, long long comp_stride) {
+  // rgb (dst_u8 only): dst = planar u8 RGB frames (dst_fstride per FRAME, comp_stride between colour planes), `frames`
+  // counts frames, d_q / ll hold three component planes per frame
   FastInvArgs a{};
+  a.comp_stride = comp_stride;
   a.q = d_q; a.q_fstride = q_fstride; a.pitch = pitch;
   a.ll = ll; a.ll_fstride = ll_fstride; a.ll_pitch = ll_pitch; a.first = first;
   a.Wc = Wc; a.Hc = Hc; a.dst = dst; a.dst_fstride = dst_fstride; a.dst_pitch = dst_pitch; a.H = dst_u8 ? H : Hc;
@@ -1345,6 +1418,13 @@ int dwt_inverse_fast(const int32_t* d_q, long long q_fstride, int pitch, const v
   a.rqs = 1.0f / qs;
   a.nstrips = (Wc + 239) / 240;
   const bool qs1 = a.rqs == 1.0f;
+  if (rgb && dst_u8) {
+    if (!lossy) { if (first) launch_inv_rgb_k<false, true, true>(a, frames, st); else launch_inv_rgb_k<false, false, true>(a, frames, st); }
+    else if (qs1) { if (first) launch_inv_rgb_k<true, true, true>(a, frames, st); else launch_inv_rgb_k<true, false, true>(a, frames, st); }
+    else { if (first) launch_inv_rgb_k<true, true, false>(a, frames, st); else launch_inv_rgb_k<true, false, false>(a, frames, st); }
+    ++g_launches;
+    return (int)cudaGetLastError();
+  }
   if (!lossy) {
     if (dst_u8) { if (first) launch_inv<false, true, true>(a, frames, qs1, st); else launch_inv<false, true, false>(a, frames, qs1, st); }
     else { if (first) launch_inv<false, false, true>(a, frames, qs1, st); else launch_inv<false, false, false>(a, frames, qs1, st); }
