@@ -116,3 +116,39 @@ def test_rgb_full_size_sha(golden, lut_root):
         else:
             assert np.array_equal(dec, rgb)
         cd.close()
+
+
+_FUSE_SNIPPET = r"""
+import hashlib, sys
+sys.path[:0] = [{root!r}, {pkg!r}]
+import numpy as np
+from picsong_b200 import codec, synth
+out = []
+for (W, H, wl, lossy, qs, n) in [(256, 200, 3, 0, 1.0, 2), (320, 192, 2, 1, 0.6, 3), (512, 328, 4, 1, 1.0, 1), (192, 64, 1, 0, 1.0, 1)]:
+    folder = "n1_lossy" if lossy else "n1_lossless"
+    cd = codec.Codec(codec.Params(W, H, wl, bool(lossy), qs, max_batch=n, rgb=True), codec.load_lut({lut_root!r} + "/" + folder + "/", wl, rgb=True))
+    px = np.stack([synth.synth_rgb(W, H, f) for f in range(n)])
+    s, lens = cd.encode_frames(px, 0)
+    back = cd.decode_frames(s, lens)
+    if not lossy:
+        assert np.array_equal(back, px)
+    out += [hashlib.sha256(np.asarray(s).tobytes()).hexdigest(), hashlib.sha256(back.tobytes()).hexdigest()]
+print("HASHES " + " ".join(out))
+"""
+
+
+def test_fused_colour_transforms_match_the_separate_pass(lut_root):
+    """Widths that are multiples of 64 take the colour transforms fused into the level-1 DWT load / inverse store
+    (DESIGN 4.5); PCS_RGB_FUSE=0 forces the separate colour pass.  Same bytes either way, including heights that need
+    mirror padding.  The switch is read once per process, hence the subprocesses."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = _FUSE_SNIPPET.format(root=root, pkg=os.path.join(root, "cuda-image-and-video-codec_b200"), lut_root=str(lut_root))
+    res = {}
+    for mode in ("1", "0"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PCS_RGB_FUSE=mode), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[mode] = [ln for ln in r.stdout.splitlines() if ln.startswith("HASHES ")][0]
+    assert res["0"] == res["1"]
