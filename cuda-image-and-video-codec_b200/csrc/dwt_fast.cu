@@ -1,20 +1,21 @@
-// dwt_fast.cu -- fused two-level forward lifting DWT for sm_100a (the bandwidth-critical front of the
-// forward transform): u8 pixels -> level-1 HL/LH/HH and level-2 HL/LH/HH (+ LL2) in ONE pass.
+// dwt_fast.cu -- streaming lifting DWT kernels for sm_100a: the forward and inverse transforms of every level whose
+// geometry allows it (width a multiple of 8, no horizontal padding on the u8 side), including the level shift, the
+// mirror padding in y, the quantiser / de-quantiser, the u8 narrowing and -- for RGB frames -- the colour transforms.
 //
-// Replaces, for frames whose width needs no padding (W == W_a), the first two iterations of the
-// reference's host loop DWTEngine::DWTForward (DWT/DWTGenerator.cu:1268-1342: one kernel + one
-// cudaStreamSynchronize per level, int32/f32 LL ping-pong through global memory) together with
-// offsetImage (Engines/CodingEngine.cu:581-588).  Arithmetic, boundary rules and the quantiser are the
-// ones of dwt.cu / oracle/picsong_oracle.c, bit for bit.
+// Replaces the per-level kernels of the reference's host loops DWTEngine::DWTForward / DWTReverse
+// (DWT/DWTGenerator.cu:753-1124,1268-1424: one kernel + one cudaStreamSynchronize per level, 64x18 register tiles with
+// 1.4x / 2.1x read amplification) together with offsetImage (Engines/CodingEngine.cu:581-588),
+// removeOffsetAndApplyMaxMin[Lossy] (Engines/DecodingEngine.cu:706-729) and RGBTransform* (CodingEngine.cu:357-405,
+// DecodingEngine.cu:599-650).  Arithmetic, boundary rules and the quantiser are the ones of dwt.cu /
+// oracle/picsong_oracle.c, bit for bit.
 //
-// Design: a warp owns a 256-pixel-wide strip (8 pixels per lane, 16-byte subband stores) and streams
-// down a chunk of rows.  Level 1 runs as a register pipeline (vertical lifting state per column,
-// horizontal lifting with 4 shuffles per row); the LL samples it produces -- 4 per lane, exactly the
-// operand layout of a 4-sample-per-lane transform -- feed a second register pipeline for level 2 in
-// the same warp, so LL1 never exists in memory.  HBM traffic per frame: 1 B/px read, 4 B/px
-// written, + LL2 (A/16 samples) for the remaining levels.  Lanes 0,1,30,31 are halo (level 1 needs
-// one neighbour lane, level 2 one more); image borders are handled by explicit mirror rules in the
-// lifting steps, so halo lanes outside the image never influence a result.
+// Design: a warp owns a 256-sample-wide strip (8 samples per lane, 16-byte subband accesses; lanes 0 and 31 are halo)
+// and streams down a chunk of row pairs.  The vertical lifting state lives in registers per column, the horizontal
+// lifting of a finished row pair needs four shuffles; image borders are explicit mirror rules in the lifting steps, so
+// halo lanes outside the image never influence a result.  Bandwidth-critical inputs (u8 pixels forward, subband rows
+// of the finest inverse level) are staged through a per-warp cp.async ring; 9/7 arithmetic is issued as packed
+// f32x2 instructions.  Also in this file, both off by default and kept as measured experiments: levels
+// 1+2 fused in one warp (LEVELS = 2) and all levels as one dependency-ordered persistent work queue.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
