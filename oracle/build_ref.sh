@@ -50,5 +50,8 @@ for o in "${objs[@]}"; do case "$o" in *Launcher_cu.o) ;; *) hobjs+=("$o");; esa
 for d in n1_lossless n1_lossy video_lossless video_lossy; do
   mkdir -p "$OUT/LUT/$d"
   cp -f "$SRC/LUT/$d/header.txt" "$SRC/LUT/$d/"*.txt_0 "$OUT/LUT/$d/"
+  # all bit-plane files (the k-factor mode of SURVEY 8f.2 reads `*_0 .. *_15`), for oracle/run_ref_golden.py --k
+  mkdir -p "$OUT/LUT_all/$d"
+  cp -f "$SRC/LUT/$d/"* "$OUT/LUT_all/$d/"
 done
 echo "build_ref: built $OUT/PICSONG_ref${REF_SUFFIX:-}"

@@ -56,6 +56,21 @@ CASES = [
 ]
 
 
+# k-factor ("bulk") mode, SURVEY 8f.2: not implemented by the new code yet; these runs pin the reference's behaviour
+# for the oracle restatement that has to come first.  Run with `--k`; needs oracle/_ref/LUT_all (build_ref.sh).
+# name, kind, W, H, frames, wl, type, qs, lut, keep_files, k
+K_CASES = [
+    ("k05_s128_wl2_ll", "synth", 128, 128, 0, 2, 0, 1.0, "n1_lossless", True, 0.5),
+    ("k1_s128_wl2_ll", "synth", 128, 128, 0, 2, 0, 1.0, "n1_lossless", True, 1.0),
+    ("k3_s128_wl2_ll", "synth", 128, 128, 0, 2, 0, 1.0, "n1_lossless", True, 3.0),
+    ("k2_noise128_wl2_ll", "noise", 128, 128, 0, 2, 0, 1.0, "n1_lossless", True, 2.0),
+    ("k1_s256_wl3_q1", "synth", 256, 256, 0, 3, 1, 1.0, "n1_lossy", True, 1.0),
+    ("k07_s256x192_wl3_ll", "synth", 256, 192, 0, 3, 0, 1.0, "n1_lossless", True, 0.7),
+    ("k1_v128_f3_wl2_q1", "synth", 128, 128, 3, 2, 1, 1.0, "video_lossy", True, 1.0),
+    ("k65_s128_wl2_ll", "synth", 128, 128, 0, 2, 0, 1.0, "n1_lossless", True, 65.0),
+]
+
+
 def sha(path):
     h = hashlib.sha256()
     with open(path, "rb") as f:
@@ -91,11 +106,16 @@ def run(cmd, timeout=600):
 
 
 def main():
-    only = set(sys.argv[1:])
-    os.makedirs(OUT, exist_ok=True)
+    kmode = "--k" in sys.argv[1:]
+    only = set(a for a in sys.argv[1:] if a != "--k")
+    out_dir = OUT + ("_k" if kmode else "")
+    lut_root = os.path.join(ROOT, "oracle", "_ref", "LUT_all") if kmode else LUT
+    os.makedirs(out_dir, exist_ok=True)
     os.makedirs(TMP, exist_ok=True)
     manifest = {}
-    for name, kind, W, H, frames, wl, typ, qs, lut, keep in CASES:
+    for case in (K_CASES if kmode else CASES):
+        name, kind, W, H, frames, wl, typ, qs, lut, keep = case[:10]
+        kfac = case[10] if len(case) > 10 else 0
         if only and name not in only:
             continue
         raw = os.path.join(TMP, name + ".raw")
@@ -106,10 +126,10 @@ def main():
                 os.remove(p)
         make_input(kind, W, H, frames, raw)
         video = 1 if frames else 0
-        lutdir = os.path.join(LUT, lut) + "/"
+        lutdir = os.path.join(lut_root, lut) + "/"
         ecmd = [REF, "-cd", "0", "-wl", str(wl), "-cp", "2", "-type", str(typ), "-qs", repr(qs),
                 "-i", raw, "-o", enc, "-cbWidth", "64", "-cbHeight", "18", "-xSize", str(W),
-                "-ySize", str(H), "-video", str(video), "-LUTFolder", lutdir, "-k", "0",
+                "-ySize", str(H), "-video", str(video), "-LUTFolder", lutdir, "-k", repr(kfac) if kfac else "0",
                 "-numberOfStreams", os.environ.get("REF_STREAMS", "1")]
         if frames:
             ecmd += ["-frames", str(frames)]
@@ -122,7 +142,7 @@ def main():
         if os.path.exists(enc):
             rc_d, out_d, t_d = run(dcmd)
         ent = {"kind": kind, "W": W, "H": H, "frames": frames, "wl": wl, "type": typ, "qs": qs,
-               "lut": lut, "rc_enc": rc_e, "rc_dec": rc_d, "t_enc_s": round(t_e, 3),
+               "lut": lut, "k": kfac, "rc_enc": rc_e, "rc_dec": rc_d, "t_enc_s": round(t_e, 3),
                "t_dec_s": round(t_d, 3), "stdout_enc": out_e[-3000:], "stdout_dec": out_d[-3000:],
                "input_sha256": sha(raw)}
         for tag, p in (("enc", enc), ("size", enc + "_SIZE"), ("dec", dec)):
@@ -132,10 +152,10 @@ def main():
                 if tag == "size":
                     ent["size_text"] = open(p).read()
                 if keep or os.environ.get("KEEP_ALL"):
-                    os.replace(p, os.path.join(OUT, name + "." + tag))
-        if os.path.exists(dec) or (keep and os.path.exists(os.path.join(OUT, name + ".dec"))):
+                    os.replace(p, os.path.join(out_dir, name + "." + tag))
+        if os.path.exists(dec) or (keep and os.path.exists(os.path.join(out_dir, name + ".dec"))):
             # decoded-vs-input comparison (payload only: PGM header is filesize - W*H*n bytes)
-            pd = dec if os.path.exists(dec) else os.path.join(OUT, name + ".dec")
+            pd = dec if os.path.exists(dec) else os.path.join(out_dir, name + ".dec")
             d = np.fromfile(pd, dtype=np.uint8)
             n = W * H * max(frames, 1) * (3 if kind == "rgb" else 1)
             x = np.fromfile(raw, dtype=np.uint8)
@@ -153,7 +173,7 @@ def main():
         for p in (raw, enc, enc + "_SIZE", dec):
             if os.path.exists(p):
                 os.remove(p)
-    with open(os.path.join(OUT, "manifest.json"), "w") as f:
+    with open(os.path.join(out_dir, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1)
 
 
