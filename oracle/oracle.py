@@ -109,12 +109,28 @@ def lut_load(folder: str, wl: int, component: int = 0) -> Lut:
     return Lut(hdr, table[:n].copy())
 
 
-def bpc_encode(q: np.ndarray, wl: int, lut: Lut, cb0: int = 0, cb1: int = 0):
+def lut_load_k(folder: str, wl: int, component: int = 0) -> Lut:
+    """k > 0 (Engines/Engine.cu:12-100): the tables of all AMOUNT_OF_BITPLANE_FILES bit-plane files back to back."""
+    hdr = np.zeros(8, dtype=np.int32)
+    cap = 1 << 20
+    table = np.zeros(cap, dtype=np.int32)
+    n = lib().pcso_lut_load_component_k(folder.encode(), wl, component, _p(hdr, C.c_int), _p(table, C.c_int32), cap)
+    if n < 0:
+        raise RuntimeError(f"oracle lut_load_k({folder!r}, wl={wl}) failed: {n}")
+    return Lut(hdr, table[:n].copy())
+
+
+def bpc_encode(q: np.ndarray, wl: int, lut: Lut, cb0: int = 0, cb1: int = 0, k: float = 0.0):
+    """k > 0: complexity-scalable mode (ENCODER only, lut from lut_load_k); exact for blocks inside one subband."""
     Ha, Wa = q.shape
     q = np.ascontiguousarray(q, dtype=np.int32)
     ncb = (Wa // 64) * (Ha // 64)
     cs = np.full(ncb * CBSZ, -1, dtype=np.int32)
     sizes = np.zeros(ncb, dtype=np.int32)
+    if k > 0:
+        lib().pcso_bpc_encode_k(_p(q, C.c_int32), Wa, Ha, wl, _p(lut.hdr, C.c_int), _p(lut.table, C.c_int32),
+                                int(lut.table.size), C.c_float(k), _p(cs, C.c_int32), _p(sizes, C.c_int32), cb0, cb1)
+        return cs, sizes
     lib().pcso_bpc_encode(_p(q, C.c_int32), Wa, Ha, wl, _p(lut.hdr, C.c_int), _p(lut.table, C.c_int32),
                           int(lut.table.size), _p(cs, C.c_int32), _p(sizes, C.c_int32), cb0, cb1)
     return cs, sizes
@@ -167,7 +183,7 @@ def bsb_unpack(stream: np.ndarray, ncb: int):
 
 # ---- whole-frame convenience (the reference's runImage call order) -------------------------
 def encode_frame(img: np.ndarray, wl: int, lossy: bool, qs: float, lut: Lut, first: bool = True,
-                 frames: int = 0) -> np.ndarray:
+                 frames: int = 0, k: float = 0.0) -> np.ndarray:
     """Engines/CodingEngine.cu:593-753 (grey): pad -> offset -> DWT -> BPC -> bit stream."""
     H, W = img.shape
     px = pad_mirror(img)
@@ -175,8 +191,8 @@ def encode_frame(img: np.ndarray, wl: int, lossy: bool, qs: float, lut: Lut, fir
         q = truncate(dwt97_forward(px, wl, qs))
     else:
         q = dwt53_forward(px, wl)
-    cs, sizes = bpc_encode(q, wl, lut)
-    hdr = header_pack(W, H, wl, lossy, qs, frames) if first else None
+    cs, sizes = bpc_encode(q, wl, lut, k=k)
+    hdr = header_pack(W, H, wl, lossy, qs, frames, k=k) if first else None
     return bsb_pack(cs, sizes, hdr)
 
 

@@ -438,7 +438,24 @@ int pcso_lut_load(const char* folder, int wl, int hdr[8], int32_t* table, int ca
   return pcso_lut_load_component(folder, wl, 0, hdr, table, cap);
 }
 /* component 0,1,2 -> files "R","G","B" (Engine.cu:124-139: the RGB path codes component i with table i) */
+int pcso_lut_load_component_file(const char* folder, int wl, int component, int file, int hdr[8], int32_t* table, int cap);
 int pcso_lut_load_component(const char* folder, int wl, int component, int hdr[8], int32_t* table, int cap) {
+  return pcso_lut_load_component_file(folder, wl, component, 0, hdr, table, cap);
+}
+/* k > 0 (Engine.cu:12-100): the tables of the bit-plane files `_0 .. _(AMOUNT_OF_BITPLANE_FILES-1)` back to back,
+ * each pcso_lut_size() ints long (the file index only enters the file name, IOManager.ipp:445-447);
+ * initializeLUTPointers then adds s * size for LUT set s (BPCEngine.cu:333). */
+int pcso_lut_load_component_k(const char* folder, int wl, int component, int hdr[8], int32_t* table, int cap) {
+  if (pcso_lut_header(folder, hdr)) return -1;
+  int n = pcso_lut_size(hdr, wl), files = hdr[7];
+  if (files < 1 || (long long)n * files > cap) return -2;
+  for (int j = 0; j < files; j++) {
+    int r = pcso_lut_load_component_file(folder, wl, component, j, hdr, table + (size_t)j * n, n);
+    if (r < 0) return r;
+  }
+  return n * files;
+}
+int pcso_lut_load_component_file(const char* folder, int wl, int component, int file, int hdr[8], int32_t* table, int cap) {
   if (pcso_lut_header(folder, hdr)) return -1;
   int nBp = hdr[0], nSub = hdr[1], cR = hdr[2], cG = hdr[3], cS = hdr[4];
   int n = pcso_lut_size(hdr, wl);
@@ -450,11 +467,11 @@ int pcso_lut_load_component(const char* folder, int wl, int component, int hdr[8
   int R = nSub * nBp * cR * wl + nBp * cR, S = nSub * nBp * cS * wl + nBp * cS;
   char path[1024];
   /* -LUTFolder is used as a plain string prefix for the table files (must end in '/') */
-  snprintf(path, sizeof path, "%sref%s.txt_0", folder, comp);
+  snprintf(path, sizeof path, "%sref%s.txt_%d", folder, comp, file);
   if (lut_section(path, table, 0, nBp, cR, wl, n)) return -3;
-  snprintf(path, sizeof path, "%ssig%s.txt_0", folder, comp);
+  snprintf(path, sizeof path, "%ssig%s.txt_%d", folder, comp, file);
   if (lut_section(path, table, R, nBp, cS, wl, n)) return -3;
-  snprintf(path, sizeof path, "%ssign%s.txt_0", folder, comp);
+  snprintf(path, sizeof path, "%ssign%s.txt_%d", folder, comp, file);
   if (lut_section(path, table, R + S, nBp, cG, wl, n)) return -3;
   return n;
 }
@@ -468,6 +485,7 @@ typedef struct {
   int wl;
   const int32_t* lut;
   int lutN;
+  float k;     /* complexity-scalability factor (-k); 0 = every plane by the two coding passes */
 } bpc_cfg;
 
 /* BPCEngine.cu:143-170 findSubband.  NOTE: the kernel calls it with the THREAD's coordinates
@@ -585,6 +603,26 @@ static inline int sig_ctx(const uint32_t n[8]) { /* BPCEngine.cu:222-230 */
   return c;
 }
 
+/* ---- k > 0: the lowest planes of a block are coded coefficient by coefficient ("bulk" mode, BPCEngine.cu:1285-1662) ---- */
+/* Planes [0, c) go to the bulk pass, c = max(floor(MSB * (k / L2Norm)), 0) (:1683-1692); L2Norm is the quantiser table
+ * (BPCEngine.cuh:158-169 == QSTEP), row = the lane's level (LL: level - 1), column 3 - subband as the reference indexes it. */
+static int bulk_planes(const bpc_cfg* cfg, int lvl, int sb, int MSB) {
+  float norm = (cfg->wl == lvl) ? QSTEP[lvl - 1 > 0 ? lvl - 1 : 0][0] : QSTEP[lvl][3 - sb];
+  int c = (int)floorf((float)MSB * (cfg->k / norm));
+  return c > 0 ? c : 0;
+}
+/* computeContextBulk :236-246: neighbours that became significant at plane >= B (bits 28:24 of the state word) */
+static inline int sig_ctx_bulk(const uint32_t n[8], int B) {
+  int c = 0;
+  for (int k = 0; k < 8; k++) c += (int)(((n[k] >> 24) & 31) >= (uint32_t)B);
+  return c;
+}
+/* computeSignContextBulk :310-322: only neighbours significant since plane >= cur contribute their sign */
+static int sgn_of_bulk(uint32_t s, int cur) { return ((s >> 31) && ((s >> 24) & 31) >= (uint32_t)cur) ? ((s & 1) ? -1 : 1) : 0; }
+static int sign_ctx_bulk(uint32_t up, uint32_t left, uint32_t right, uint32_t down, int cur) {
+  return sign_ctx_hv(sgn_of_bulk(left, cur) + sgn_of_bulk(right, cur), sgn_of_bulk(up, cur) + sgn_of_bulk(down, cur));
+}
+
 /* One codeblock, encode.  Kernel body BPCEngine.cu:1973-2025; Encode :1668-1721; SPP :770-843 +
  * :490-516; MRP :1249-1261 + :726-736.  q = coefficient plane (already (int)-truncated for the
  * lossy path), words = this block's 4096-word slot (pre-filled with -1 by the caller, :2431-2440). */
@@ -608,7 +646,21 @@ static int encode_block(const bpc_cfg* cfg, const int32_t* q, int Wa, int Ha, in
     int refP[32], sigP[32], sgnP[32]; /* per lane, :329-350 */
     lane_pointers(cfg, X, Y, Wa, Ha, MSB, refP, sigP, sgnP);
     uint32_t n[32][8];
-    for (int bp = MSB; bp >= 0; bp--) {
+    /* k > 0 (:1683-1697): planes below `consec` are left to the bulk pass and the LUT set min(consec, MSB) is used.
+     * The reference computes both per LANE; a block that straddles subbands makes its lanes leave the plane loop at
+     * different planes, which the reference does not survive (its decoder aborts on such streams) -- lane 0 decides
+     * here, exact for every block that lies inside one subband. */
+    int consec = 0;
+    if (cfg->k > 0.0f) {
+      int lvl, sb;
+      find_subband(X, Y, Wa, Ha, cfg->wl, &lvl, &sb);
+      consec = bulk_planes(cfg, lvl, sb, MSB);
+      int set = consec < MSB ? consec : MSB;
+      int per = pcso_lut_size((const int[8]){cfg->nBp, cfg->nSub, cfg->cR, cfg->cG, cfg->cS, 0, 0, 0}, cfg->wl);
+      for (int l = 0; l < 32; l++) { refP[l] += set * per; sigP[l] += set * per; sgnP[l] += set * per; }
+    }
+    int bp;
+    for (bp = MSB; bp >= consec; bp--) {
       /* ---- SPP ---- */
       for (int i = 0; i < CB; i++)
         for (int c = 0; c < 2; c++) {
@@ -655,6 +707,53 @@ static int encode_block(const bpc_cfg* cfg, const int32_t* q, int Wa, int Ha, in
             if ((act >> l) & 1) ac_encode(s, l, (s->S[l][2 * i + c] >> (bp + 1)) & 1, lut_at(cfg, refP[l]));
         }
       for (int l = 0; l < 32; l++) { refP[l] -= cfg->cR; sigP[l] -= cfg->cS; sgnP[l] -= cfg->cG; } /* :353-358 */
+    }
+    if (bp >= 0) {
+      /* ---- bulk pass from plane B = bp down to 0, one coefficient at a time (:1285-1420, :1640-1650): rows in order,
+       * column 0 then column 1; context and neighbour snapshot are taken ONCE per coefficient, before its planes ---- */
+      const int B = bp;
+      for (int i = 0; i < CB; i++)
+        for (int c = 0; c < 2; c++) {
+          int ctx[32];
+          uint32_t any = 0;
+          for (int l = 0; l < 32; l++) {
+            neighbours(s, l, i, c, n[l]);
+            if (!(s->S[l][2 * i + c] >> 31)) any = 1;
+          }
+          for (int l = 0; l < 32; l++) ctx[l] = any ? (B != 0 ? sig_ctx_bulk(n[l], B) : sig_ctx(n[l])) : 0;
+          for (int cur = B; cur >= 0; cur--) {
+            const int d = B - cur;
+            uint32_t sigm = 0, insig = 0, one = 0, need = 0;
+            for (int l = 0; l < 32; l++) { if (s->S[l][2 * i + c] >> 31) sigm |= 1u << l; else insig |= 1u << l; }
+            /* refinement of the already significant (:1292-1295) */
+            for (int l = 0; l < 32; l++) if (((sigm >> l) & 1) && s->size[l] == 0) need |= 1u << l;
+            ac_reserve(s, need, 0);
+            for (int l = 0; l < 32; l++)
+              if ((sigm >> l) & 1) ac_encode(s, l, (s->S[l][2 * i + c] >> (cur + 1)) & 1, lut_at(cfg, refP[l] - cfg->cR * d));
+            /* significance of the others (:1297-1299) */
+            need = 0;
+            for (int l = 0; l < 32; l++) if (((insig >> l) & 1) && s->size[l] == 0) need |= 1u << l;
+            ac_reserve(s, need, 0);
+            for (int l = 0; l < 32; l++)
+              if ((insig >> l) & 1) {
+                uint32_t b = (s->S[l][2 * i + c] >> (cur + 1)) & 1;
+                ac_encode(s, l, b, lut_at(cfg, sigP[l] + ctx[l] - cfg->cS * d));
+                if (b) one |= 1u << l;
+              }
+            /* sign of those that just became significant (:1301-1310) */
+            need = 0;
+            for (int l = 0; l < 32; l++) if (((one >> l) & 1) && s->size[l] == 0) need |= 1u << l;
+            ac_reserve(s, need, 0);
+            for (int l = 0; l < 32; l++)
+              if ((one >> l) & 1) {
+                uint32_t* w = &s->S[l][2 * i + c];
+                *w |= 1u << 31;
+                *w |= (uint32_t)cur << 24;
+                int sc = sign_ctx_bulk(n[l][1], n[l][3], n[l][4], n[l][6], cur);
+                ac_encode(s, l, ((*w & 1) == (uint32_t)(sc & 1)) ? 0 : 1, lut_at(cfg, sgnP[l] + (sc >> 1) - cfg->cG * d));
+              }
+          }
+        }
     }
     for (int l = 0; l < 32; l++) words[s->slot[l]] = (int32_t)s->lower[l]; /* flush :1719 */
   }
@@ -746,7 +845,7 @@ static void decode_block(const bpc_cfg* cfg, const int32_t* words, int size, int
 
 static void mkcfg(bpc_cfg* c, const int hdr[8], int wl, const int32_t* lut, int lutN) {
   c->nBp = hdr[0]; c->nSub = hdr[1]; c->cR = hdr[2]; c->cG = hdr[3]; c->cS = hdr[4]; c->prec = hdr[5];
-  c->wl = wl; c->lut = lut; c->lutN = lutN;
+  c->wl = wl; c->lut = lut; c->lutN = lutN; c->k = 0.0f;
 }
 
 /* Whole frame.  cs = sparse int32 codestream [A] (filled with -1 here, BPCEngine.cu:2431-2440),
@@ -760,6 +859,21 @@ int pcso_bpc_encode(const int32_t* q, int Wa, int Ha, int wl, const int hdr[8], 
   for (int cb = cb0; cb < cb1; cb++) {
     int32_t* w = cs + (size_t)cb * CBSZ;
     for (int k = 0; k < CBSZ; k++) w[k] = -1;
+    sizes[cb] = encode_block(&cfg, q, Wa, Ha, cb, w);
+  }
+  return 0;
+}
+
+/* The same with the complexity-scalability factor k (ENCODER only; lut = pcso_lut_load_component_k tables). */
+int pcso_bpc_encode_k(const int32_t* q, int Wa, int Ha, int wl, const int hdr[8], const int32_t* lut,
+                      int lutN, float k, int32_t* cs, int32_t* sizes, int cb0, int cb1) {
+  bpc_cfg cfg; mkcfg(&cfg, hdr, wl, lut, lutN);
+  cfg.k = k;
+  int nCB = (Wa / CB) * (Ha / CB);
+  if (cb1 <= 0 || cb1 > nCB) cb1 = nCB;
+  for (int cb = cb0; cb < cb1; cb++) {
+    int32_t* w = cs + (size_t)cb * CBSZ;
+    for (int j = 0; j < CBSZ; j++) w[j] = -1;
     sizes[cb] = encode_block(&cfg, q, Wa, Ha, cb, w);
   }
   return 0;

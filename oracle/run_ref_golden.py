@@ -68,6 +68,13 @@ K_CASES = [
     ("k07_s256x192_wl3_ll", "synth", 256, 192, 0, 3, 0, 1.0, "n1_lossless", True, 0.7),
     ("k1_v128_f3_wl2_q1", "synth", 128, 128, 3, 2, 1, 1.0, "video_lossy", True, 1.0),
     ("k65_s128_wl2_ll", "synth", 128, 128, 0, 2, 0, 1.0, "n1_lossless", True, 65.0),
+    # no codeblock straddles a subband here (LL2 is 64x64): every lane of a warp leaves the plane loop at the same plane
+    ("k05_s256_wl2_ll", "synth", 256, 256, 0, 2, 0, 1.0, "n1_lossless", True, 0.5),
+    ("k1_s256_wl2_ll", "synth", 256, 256, 0, 2, 0, 1.0, "n1_lossless", True, 1.0),
+    ("k2_s256_wl2_ll", "synth", 256, 256, 0, 2, 0, 1.0, "n1_lossless", True, 2.0),
+    ("k1_s256_wl2_q1", "synth", 256, 256, 0, 2, 1, 1.0, "n1_lossy", True, 1.0),
+    ("k1_noise256_wl2_ll", "noise", 256, 256, 0, 2, 0, 1.0, "n1_lossless", True, 1.0),
+    ("k0_s256_wl2_ll", "synth", 256, 256, 0, 2, 0, 1.0, "n1_lossless", True, 0),
 ]
 
 

@@ -1,0 +1,74 @@
+"""CPU test: the oracle's restatement of the reference's complexity-scalable ("bulk", -k > 0) ENCODER
+(BPC/BPCEngine.cu:1285-1662,1683-1716) against streams written by the unmodified reference binary on a B200
+(tests/golden/k_factor, made by oracle/run_ref_golden.py --k; LUT tables: tests/golden/lut_tables_k.npz, made by
+oracle/make_golden_k.py).  The new CUDA code does not implement this mode yet (PCS_E_UNSUPPORTED): this pins the
+oracle that has to exist first.
+
+Byte-exact for every geometry in which no codeblock straddles a subband.  Where one does (block 0 when the deepest
+subbands are narrower than 64), the lanes of that warp leave the reference's plane loop at different planes, which
+is undefined behaviour there -- its own decoder aborts on those streams -- so block 0 is exempt and all other
+blocks must still match."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from picsong_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KDIR = os.path.join(HERE, "golden", "k_factor")
+MAN = json.load(open(os.path.join(KDIR, "manifest.json")))
+TABLES = np.load(os.path.join(HERE, "golden", "lut_tables_k.npz"))
+STILLS = sorted(n for n, e in MAN.items() if not e["frames"])
+
+
+def _coefficients(e):
+    img = synth.noise_frame(e["W"], e["H"]) if e["kind"] == "noise" else synth.synth_frame(e["W"], e["H"], 0)
+    px = O.pad_mirror(img)
+    return O.truncate(O.dwt97_forward(px, e["wl"], e["qs"])) if e["type"] else O.dwt53_forward(px, e["wl"])
+
+
+@pytest.mark.parametrize("name", STILLS)
+def test_bulk_mode_encoder_matches_reference_binary(name):
+    e = MAN[name]
+    assert e["rc_enc"] == 0
+    key = f"{e['lut']}_wl{e['wl']}"
+    lut = O.Lut(TABLES[key + "_hdr"], TABLES[key])
+    q = _coefficients(e)
+    Ha, Wa = q.shape
+    ncb = (Wa // 64) * (Ha // 64)
+    cs, sizes = O.bpc_encode(q, e["wl"], lut, k=float(e["k"]))
+    ref = np.fromfile(os.path.join(KDIR, name + ".enc"), dtype=np.uint16)
+    straddles = (Wa >> e["wl"]) < 64 or (Ha >> e["wl"]) < 64
+    if not straddles:
+        mine = O.bsb_pack(cs, sizes, O.header_pack(e["W"], e["H"], e["wl"], e["type"], e["qs"], 0, k=float(e["k"])))
+        assert mine.size == ref.size and np.array_equal(mine, ref)
+        assert e["rc_dec"] == 0  # and the reference decodes its own stream
+        return
+    assert ref[8] == int(e["k"] * 1000)  # header word 8 carries k (BitStreamBuilder.cpp:82-93)
+    rcs, rsizes, _ = O.bsb_unpack(ref, ncb)
+    for b in range(1, ncb):  # block 0 straddles LL / HL of the deepest level
+        assert sizes[b] == rsizes[b], (name, b)
+        assert np.array_equal(cs[b * 4096: b * 4096 + sizes[b]], rcs[b * 4096: b * 4096 + rsizes[b]]), (name, b)
+
+
+def test_reference_decoder_only_survives_uniform_blocks():
+    """What the reference itself did with these streams (recorded, not recomputed): decode fails with an illegal
+    memory access exactly where a codeblock straddles subbands and k leaves planes to the bulk pass."""
+    for name, e in MAN.items():
+        Wa, Ha = -(-e["W"] // 64) * 64, -(-e["H"] // 64) * 64
+        straddles = (Wa >> e["wl"]) < 64 or (Ha >> e["wl"]) < 64
+        if straddles and e["k"] < 65:
+            assert e["rc_dec"] == 255 and "illegal memory access" in e["stdout_dec"], name
+        else:
+            assert e["rc_dec"] == 0 and (e["type"] or e["dec_equal_input"]), name
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/CUDA_ImCod/LUT"), reason="reference tree not present")
+def test_k_tables_fixture_matches_reference_files():
+    for key in [k for k in TABLES.files if not k.endswith("_hdr")]:
+        folder, wl = key.rsplit("_wl", 1)
+        lut = O.lut_load_k(f"/root/reference/CUDA_ImCod/LUT/{folder}/", int(wl))
+        assert np.array_equal(lut.table, TABLES[key]) and np.array_equal(lut.hdr, TABLES[key + "_hdr"])
