@@ -137,10 +137,14 @@ def bpc_encode(q: np.ndarray, wl: int, lut: Lut, cb0: int = 0, cb1: int = 0, k: 
 
 
 def bpc_decode(cs: np.ndarray, sizes: np.ndarray, Wa: int, Ha: int, wl: int, lut: Lut,
-               cb0: int = 0, cb1: int = 0) -> np.ndarray:
+               cb0: int = 0, cb1: int = 0, k: float = 0.0) -> np.ndarray:
     cs = np.ascontiguousarray(cs, dtype=np.int32)
     sizes = np.ascontiguousarray(sizes, dtype=np.int32)
     q = np.zeros((Ha, Wa), dtype=np.int32)
+    if k > 0:
+        lib().pcso_bpc_decode_k(_p(cs, C.c_int32), _p(sizes, C.c_int32), Wa, Ha, wl, _p(lut.hdr, C.c_int),
+                                _p(lut.table, C.c_int32), int(lut.table.size), C.c_float(k), _p(q, C.c_int32), cb0, cb1)
+        return q
     lib().pcso_bpc_decode(_p(cs, C.c_int32), _p(sizes, C.c_int32), Wa, Ha, wl, _p(lut.hdr, C.c_int),
                           _p(lut.table, C.c_int32), int(lut.table.size), _p(q, C.c_int32), cb0, cb1)
     return q
@@ -196,11 +200,11 @@ def encode_frame(img: np.ndarray, wl: int, lossy: bool, qs: float, lut: Lut, fir
     return bsb_pack(cs, sizes, hdr)
 
 
-def decode_frame(stream: np.ndarray, Wa: int, Ha: int, wl: int, lossy: bool, qs: float, lut: Lut) -> np.ndarray:
+def decode_frame(stream: np.ndarray, Wa: int, Ha: int, wl: int, lossy: bool, qs: float, lut: Lut, k: float = 0.0) -> np.ndarray:
     """Engines/DecodingEngine.cu:765-859 (grey): unpack -> BPC decode -> inverse DWT -> clamp."""
     ncb = (Wa // 64) * (Ha // 64)
     cs, sizes, _ = bsb_unpack(stream, ncb)
-    q = bpc_decode(cs, sizes, Wa, Ha, wl, lut)
+    q = bpc_decode(cs, sizes, Wa, Ha, wl, lut, k=k)
     return dwt97_inverse(q, wl, qs) if lossy else dwt53_inverse(q, wl)
 
 

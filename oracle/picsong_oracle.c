@@ -782,7 +782,17 @@ static void decode_block(const bpc_cfg* cfg, const int32_t* words, int size, int
     uint32_t mask = 0x3u << MSB; /* :1791 */
     if (MSB == 0) mask &= 0x2;   /* :1804 */
     uint32_t n[32][8];
-    for (int bp = MSB; bp >= 0; bp--) {
+    int consec = 0;              /* k > 0: see encode_block (:1793-1810) */
+    if (cfg->k > 0.0f) {
+      int lvl, sb;
+      find_subband(X, Y, Wa, Ha, cfg->wl, &lvl, &sb);
+      consec = bulk_planes(cfg, lvl, sb, MSB);
+      int set = consec < MSB ? consec : MSB;
+      int per = pcso_lut_size((const int[8]){cfg->nBp, cfg->nSub, cfg->cR, cfg->cG, cfg->cS, 0, 0, 0}, cfg->wl);
+      for (int l = 0; l < 32; l++) { refP[l] += set * per; sigP[l] += set * per; sgnP[l] += set * per; }
+    }
+    int bp;
+    for (bp = MSB; bp >= consec; bp--) {
       for (int i = 0; i < CB; i++)
         for (int c = 0; c < 2; c++) {
           uint32_t act = 0, one = 0, need = 0;
@@ -832,6 +842,57 @@ static void decode_block(const bpc_cfg* cfg, const int32_t* words, int size, int
       if (bp == 1) mask = 0x2;  /* :1824 */
       for (int l = 0; l < 32; l++) { refP[l] -= cfg->cR; sigP[l] -= cfg->cS; sgnP[l] -= cfg->cG; }
     }
+    if (bp >= 0) { /* bulk pass, inverse of the one in encode_block (:1487-1530, :1535-1650) */
+      const int B = bp;
+      const uint32_t mask0 = mask;
+      for (int i = 0; i < CB; i++)
+        for (int c = 0; c < 2; c++) {
+          int ctx[32];
+          uint32_t any = 0;
+          for (int l = 0; l < 32; l++) {
+            neighbours(s, l, i, c, n[l]);
+            if (!(s->S[l][2 * i + c] >> 31)) any = 1;
+          }
+          for (int l = 0; l < 32; l++) ctx[l] = any ? (B != 0 ? sig_ctx_bulk(n[l], B) : sig_ctx(n[l])) : 0;
+          uint32_t m = mask0;  /* the mask is passed by value: every coefficient restarts from the plane-B mask */
+          for (int cur = B; cur >= 0; cur--) {
+            const int dd = B - cur;
+            uint32_t sigm = 0, insig = 0, one = 0, need = 0;
+            for (int l = 0; l < 32; l++) { if (s->S[l][2 * i + c] >> 31) sigm |= 1u << l; else insig |= 1u << l; }
+            for (int l = 0; l < 32; l++) if (((sigm >> l) & 1) && s->size[l] == 0) need |= 1u << l;
+            ac_reserve(s, need, 1);
+            for (int l = 0; l < 32; l++)
+              if ((sigm >> l) & 1) {
+                uint32_t sym = ac_decode(s, l, lut_at(cfg, refP[l] - cfg->cR * dd));
+                uint32_t* w = &s->S[l][2 * i + c];
+                *w &= ~m;
+                *w |= m & (((sym << 1) + 1) << cur);
+              }
+            need = 0;
+            for (int l = 0; l < 32; l++) if (((insig >> l) & 1) && s->size[l] == 0) need |= 1u << l;
+            ac_reserve(s, need, 1);
+            for (int l = 0; l < 32; l++)
+              if ((insig >> l) & 1)
+                if (ac_decode(s, l, lut_at(cfg, sigP[l] + ctx[l] - cfg->cS * dd))) one |= 1u << l;
+            need = 0;
+            for (int l = 0; l < 32; l++) if (((one >> l) & 1) && s->size[l] == 0) need |= 1u << l;
+            ac_reserve(s, need, 1);
+            for (int l = 0; l < 32; l++)
+              if ((one >> l) & 1) {
+                uint32_t* w = &s->S[l][2 * i + c];
+                *w |= m;
+                *w |= 1u << 31;
+                *w |= (uint32_t)cur << 24;
+                int sc = sign_ctx_bulk(n[l][1], n[l][3], n[l][4], n[l][6], cur);
+                uint32_t sym = ac_decode(s, l, lut_at(cfg, sgnP[l] + (sc >> 1) - cfg->cG * dd));
+                sym = ((sym & 1) == (uint32_t)(sc & 1)) ? 0 : 1;
+                *w |= sym;
+              }
+            m >>= 1;
+            if (cur == 1) m = 0x2;
+          }
+        }
+    }
   }
   for (int l = 0; l < 32; l++)
     for (int i = 0; i < CB; i++)
@@ -876,6 +937,16 @@ int pcso_bpc_encode_k(const int32_t* q, int Wa, int Ha, int wl, const int hdr[8]
     for (int j = 0; j < CBSZ; j++) w[j] = -1;
     sizes[cb] = encode_block(&cfg, q, Wa, Ha, cb, w);
   }
+  return 0;
+}
+
+int pcso_bpc_decode_k(const int32_t* cs, const int32_t* sizes, int Wa, int Ha, int wl, const int hdr[8],
+                      const int32_t* lut, int lutN, float k, int32_t* q, int cb0, int cb1) {
+  bpc_cfg cfg; mkcfg(&cfg, hdr, wl, lut, lutN);
+  cfg.k = k;
+  int nCB = (Wa / CB) * (Ha / CB);
+  if (cb1 <= 0 || cb1 > nCB) cb1 = nCB;
+  for (int cb = cb0; cb < cb1; cb++) decode_block(&cfg, cs + (size_t)cb * CBSZ, sizes[cb], Wa, Ha, cb, q);
   return 0;
 }
 

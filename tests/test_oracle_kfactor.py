@@ -72,3 +72,28 @@ def test_k_tables_fixture_matches_reference_files():
         folder, wl = key.rsplit("_wl", 1)
         lut = O.lut_load_k(f"/root/reference/CUDA_ImCod/LUT/{folder}/", int(wl))
         assert np.array_equal(lut.table, TABLES[key]) and np.array_equal(lut.hdr, TABLES[key + "_hdr"])
+
+
+@pytest.mark.parametrize("name", STILLS)
+def test_bulk_mode_decoder_inverts_the_encoder_and_matches_the_reference_decoder(name):
+    """pcso_bpc_decode_k (decodeBulkProcessing, BPCEngine.cu:1487-1530,1776-1837): exact coefficient round trip for
+    every case; for the geometries the reference can decode, the pixels decoded from the REFERENCE's stream are the
+    ones the reference decoder wrote (lossless: the input; 9/7: the stored PGM)."""
+    e = MAN[name]
+    key = f"{e['lut']}_wl{e['wl']}"
+    lut = O.Lut(TABLES[key + "_hdr"], TABLES[key])
+    q = _coefficients(e)
+    Ha, Wa = q.shape
+    k = float(e["k"])
+    cs, sizes = O.bpc_encode(q, e["wl"], lut, k=k)
+    assert np.array_equal(O.bpc_decode(cs, sizes, Wa, Ha, e["wl"], lut, k=k), q)
+    if e["rc_dec"] != 0:
+        return
+    ref = np.fromfile(os.path.join(KDIR, name + ".enc"), dtype=np.uint16)
+    out = O.decode_frame(ref, Wa, Ha, e["wl"], bool(e["type"]), e["qs"], lut, k=k)[: e["H"], : e["W"]]
+    if not e["type"]:
+        img = synth.noise_frame(e["W"], e["H"]) if e["kind"] == "noise" else synth.synth_frame(e["W"], e["H"], 0)
+        assert e["dec_equal_input"] and np.array_equal(out, img)
+    else:
+        d = np.fromfile(os.path.join(KDIR, name + ".dec"), dtype=np.uint8)
+        assert np.array_equal(out, d[d.size - e["W"] * e["H"]:].reshape(e["H"], e["W"]))
