@@ -24,5 +24,10 @@ for e in man.values():
     lut = O.lut_load_k(f"{LUT}/{e['lut']}/", e["wl"])
     out[key] = lut.table
     out[key + "_hdr"] = lut.hdr
+for e in man.values():  # RGB cases: component 1, 2 tables (files G, B) as well
+    if e["kind"] != "rgb":
+        continue
+    for c in (1, 2):
+        out[f"{e['lut']}_wl{e['wl']}_c{c}"] = O.lut_load_k(f"{LUT}/{e['lut']}/", e["wl"], c).table
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "lut_tables_k.npz"), **out)
 print({k: v.shape for k, v in out.items()})

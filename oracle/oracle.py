@@ -231,7 +231,7 @@ def rgb_inverse(comps, lossy: bool) -> np.ndarray:
     return out
 
 
-def encode_rgb_frame(rgb: np.ndarray, wl: int, lossy: bool, qs: float, luts, header_on, frames: int = 0):
+def encode_rgb_frame(rgb: np.ndarray, wl: int, lossy: bool, qs: float, luts, header_on, frames: int = 0, k: float = 0.0):
     """Engines/CodingEngine.cu:598-630,680-710 (stills: component i is coded with iter = i, so only component 0
     carries the header) and :764-810 (video: iter = frame index for all three components).
     rgb: u8 (3, H, W); luts: the three component tables; header_on: 3 bools.  Returns the three streams."""
@@ -248,8 +248,8 @@ def encode_rgb_frame(rgb: np.ndarray, wl: int, lossy: bool, qs: float, luts, hea
         else:
             q = np.empty((Ha, Wa), dtype=np.int32)
             assert lib().pcso_dwt53_forward_plane(_p(comps[c], C.c_int32), Wa, Ha, wl, _p(q, C.c_int32)) == 0
-        cs, sizes = bpc_encode(q, wl, luts[c])
-        hdr = header_pack(W, H, wl, lossy, qs, frames, isRGB=1) if header_on[c] else None
+        cs, sizes = bpc_encode(q, wl, luts[c], k=k)
+        hdr = header_pack(W, H, wl, lossy, qs, frames, isRGB=1, k=k) if header_on[c] else None
         streams.append(bsb_pack(cs, sizes, hdr))
     return streams
 

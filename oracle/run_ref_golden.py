@@ -75,6 +75,8 @@ K_CASES = [
     ("k1_s256_wl2_q1", "synth", 256, 256, 0, 2, 1, 1.0, "n1_lossy", True, 1.0),
     ("k1_noise256_wl2_ll", "noise", 256, 256, 0, 2, 0, 1.0, "n1_lossless", True, 1.0),
     ("k0_s256_wl2_ll", "synth", 256, 256, 0, 2, 0, 1.0, "n1_lossless", True, 0),
+    ("k1_v256_f3_wl2_q1", "synth", 256, 256, 3, 2, 1, 1.0, "video_lossy", True, 1.0),
+    ("k1_rgb256_wl2_ll", "rgb", 256, 256, 0, 2, 0, 1.0, "n1_lossless", True, 1.0),
 ]
 
 

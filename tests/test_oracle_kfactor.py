@@ -21,7 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 KDIR = os.path.join(HERE, "golden", "k_factor")
 MAN = json.load(open(os.path.join(KDIR, "manifest.json")))
 TABLES = np.load(os.path.join(HERE, "golden", "lut_tables_k.npz"))
-STILLS = sorted(n for n, e in MAN.items() if not e["frames"])
+STILLS = sorted(n for n, e in MAN.items() if not e["frames"] and e["kind"] != "rgb")
 
 
 def _coefficients(e):
@@ -66,12 +66,50 @@ def test_reference_decoder_only_survives_uniform_blocks():
             assert e["rc_dec"] == 0 and (e["type"] or e["dec_equal_input"]), name
 
 
+def _lengths(e):
+    return [int(x) for x in e["size_text"].replace(",", " ").split()]
+
+
+def test_bulk_mode_video_frames_match_reference_binary():
+    """-video 1 -k 1: every frame is coded with the same rules, only frame 0 carries the header (k in word 8)."""
+    name = "k1_v256_f3_wl2_q1"
+    e = MAN[name]
+    lut = O.Lut(TABLES[f"{e['lut']}_wl{e['wl']}_hdr"], TABLES[f"{e['lut']}_wl{e['wl']}"])
+    ref = np.fromfile(os.path.join(KDIR, name + ".enc"), dtype=np.uint16)
+    off = 0
+    for f, n in enumerate(_lengths(e)):
+        mine = O.encode_frame(synth.synth_frame(e["W"], e["H"], f), e["wl"], True, e["qs"], lut, first=(f == 0),
+                              frames=e["frames"], k=float(e["k"]))
+        assert mine.size == n and np.array_equal(mine, ref[off:off + n]), f
+        off += n
+    assert off == ref.size
+
+
+def test_bulk_mode_rgb_components_match_reference_binary():
+    """-isRGB 1 -k 1: component c uses the LUT sets of file letter R / G / B."""
+    name = "k1_rgb256_wl2_ll"
+    e = MAN[name]
+    key = f"{e['lut']}_wl{e['wl']}"
+    luts = [O.Lut(TABLES[key + "_hdr"], TABLES[key if c == 0 else f"{key}_c{c}"]) for c in range(3)]
+    streams = O.encode_rgb_frame(synth.synth_rgb(e["W"], e["H"], 0), e["wl"], False, 1.0, luts, [True, False, False], 0,
+                                 k=float(e["k"]))
+    ref = np.fromfile(os.path.join(KDIR, name + ".enc"), dtype=np.uint16)
+    off = 0
+    for c, n in enumerate(_lengths(e)):
+        assert streams[c].size == n and np.array_equal(streams[c], ref[off:off + n]), c
+        off += n
+    assert off == ref.size and e["rc_dec"] == 0 and e["dec_equal_input"]
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/CUDA_ImCod/LUT"), reason="reference tree not present")
 def test_k_tables_fixture_matches_reference_files():
     for key in [k for k in TABLES.files if not k.endswith("_hdr")]:
-        folder, wl = key.rsplit("_wl", 1)
-        lut = O.lut_load_k(f"/root/reference/CUDA_ImCod/LUT/{folder}/", int(wl))
-        assert np.array_equal(lut.table, TABLES[key]) and np.array_equal(lut.hdr, TABLES[key + "_hdr"])
+        folder, rest = key.rsplit("_wl", 1)
+        wl, comp = (rest.split("_c") + ["0"])[:2]
+        lut = O.lut_load_k(f"/root/reference/CUDA_ImCod/LUT/{folder}/", int(wl), int(comp))
+        assert np.array_equal(lut.table, TABLES[key])
+        if comp == "0":
+            assert np.array_equal(lut.hdr, TABLES[key + "_hdr"])
 
 
 @pytest.mark.parametrize("name", STILLS)
