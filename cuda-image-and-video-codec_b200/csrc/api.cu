@@ -37,6 +37,8 @@ int dwt_inverse_rgb(const int32_t*, uint8_t*, void*, int, int, int, int, int, bo
 int dwt_inverse(const int32_t*, uint8_t*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t, DwtAux*);
 int bpc_encode(const void*, bool, uint16_t*, int32_t*, const BpcArgs&, cudaStream_t);
 int bpc_decode(const uint16_t*, const int32_t*, int32_t*, const BpcArgs&, cudaStream_t);
+int bpc_encode_k(const void*, bool, uint16_t*, int32_t*, const BpcKArgs&, cudaStream_t);
+int bpc_decode_k(const uint16_t*, const int32_t*, int32_t*, const BpcKArgs&, cudaStream_t);
 int export_ref_codestream(const uint16_t*, const int32_t*, int32_t*, long long, cudaStream_t);
 int bsb_pack(const uint16_t*, const int32_t*, uint16_t*, long long*, void*, const BsbArgs&, cudaStream_t);
 int bsb_unpack(const uint16_t*, const long long*, uint16_t*, int32_t*, void*, const BsbArgs&, cudaStream_t);
@@ -73,6 +75,8 @@ struct pcs_ctx {
   long long* d_soff = nullptr;     // [kSlots][planes + 1]
   void* d_sstatus = nullptr;       // [kSlots] look-back status areas
   size_t status_bytes = 0;
+  int32_t* d_lutk = nullptr;       // k > 0: flat tables of all bit-plane files, [ncomp][files][per]
+  int lut_files = 1;               // table sets per component in `lut` (1 for k == 0)
   void* d_dwtq = nullptr;          // [1 + kSlots] work-queue counter areas of the forward DWT
   size_t dwtq_bytes = 0;
   DwtAux* aux = nullptr;           // auxiliary streams of the batched DWT calls (device-buffer entry points)
@@ -123,11 +127,11 @@ int build_prob_tables(pcs_ctx* c) {
     return PCS_E_LUT_RANGE;
   const int R = (nSub * wl + 1) * nBp * cR, S = (nSub * wl + 1) * nBp * cS;
   const int n = R + S + (nSub * wl + 1) * nBp * cG;  // entries per component
-  if ((long long)c->lut.size() < (long long)n * c->ncomp) return PCS_E_LUT;
+  if ((long long)c->lut.size() < (long long)n * c->lut_files * c->ncomp) return PCS_E_LUT;
   const int nrows = (nSub * wl + 1) * nBp + 32;
   std::vector<uint4> tab4((size_t)nrows * c->ncomp, make_uint4(0, 0, 0, 0));
   for (int comp = 0; comp < c->ncomp; ++comp) {
-    const int32_t* lut = c->lut.data() + (size_t)comp * n;
+    const int32_t* lut = c->lut.data() + (size_t)comp * n * c->lut_files;  // set 0 of the component (the k == 0 tables)
     auto at = [&](long long i) -> int { return (i >= 0 && i < n) ? lut[(size_t)i] : 0; };
     for (int r = 0; r < nrows; ++r) {
       uint4& t = tab4[(size_t)comp * nrows + r];
@@ -151,6 +155,11 @@ int build_prob_tables(pcs_ctx* c) {
   c->nrows = nrows;
   PCS_CUDA_TRY(cudaMalloc(&c->d_tab4, tab4.size() * sizeof(uint4)));
   PCS_CUDA_TRY(cudaMemcpy(c->d_tab4, tab4.data(), tab4.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+  if (c->p.k_factor > 0) {  // the complexity-scalable kernels index the flat tables the way the reference does
+    const size_t total = (size_t)n * c->lut_files * c->ncomp;
+    PCS_CUDA_TRY(cudaMalloc(&c->d_lutk, total * sizeof(int32_t)));
+    PCS_CUDA_TRY(cudaMemcpy(c->d_lutk, c->lut.data(), total * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
   return PCS_OK;
 }
 
@@ -192,7 +201,27 @@ int run_dwt_inverse(pcs_ctx* c, const Ws& w, const int32_t* d_q, uint8_t* d_px, 
   return rgb_inverse(w.tplanes, d_px, p.width, p.height, c->Wa, c->Ha, p.lossy != 0, flat, frames, st);
 }
 
+BpcKArgs bpc_k_args(const pcs_ctx* c, int frames, int comp) {
+  BpcKArgs a{};
+  const int32_t* h = c->p.lut_header;
+  a.Wa = c->Wa; a.Ha = c->Ha; a.nbx = c->Wa / kCB; a.ncb = c->ncb; a.wl = c->p.wavelet_levels;
+  a.nBp = h[0]; a.nSub = h[1]; a.cR = h[2]; a.cG = h[3]; a.cS = h[4]; a.prec = h[5];
+  a.total_cb = c->ncb * frames; a.A = (long long)c->A;
+  a.pstep = c->ncomp; a.pfirst = comp;
+  a.per = pcs_lut_size(h, a.wl); a.lutN = a.per * c->lut_files;
+  a.k = c->p.k_factor;
+  a.lut = c->d_lutk + (size_t)comp * a.lutN;
+  return a;
+}
+
 int run_bpc_encode(pcs_ctx* c, const void* d_coeff, bool is_float, uint16_t* d_cw, int32_t* d_sizes, int frames, cudaStream_t st) {
+  if (c->p.k_factor > 0) {  // complexity-scalable mode: the lane-per-column-pair kernels of bpc.cu
+    for (int comp = 0; comp < c->ncomp; ++comp) {
+      int rc = bpc_encode_k(d_coeff, is_float, d_cw, d_sizes, bpc_k_args(c, frames, comp), st);
+      if (rc) return rc;
+    }
+    return PCS_OK;
+  }
   for (int comp = 0; comp < c->ncomp; ++comp) {  // one launch per component: each has its own probability table
     int rc = bpc_encode(d_coeff, is_float, d_cw, d_sizes, bpc_args(c, frames, comp), st);
     if (rc) return rc;
@@ -201,6 +230,13 @@ int run_bpc_encode(pcs_ctx* c, const void* d_coeff, bool is_float, uint16_t* d_c
 }
 
 int run_bpc_decode(pcs_ctx* c, const uint16_t* d_cw, const int32_t* d_sizes, int32_t* d_q, int frames, cudaStream_t st) {
+  if (c->p.k_factor > 0) {
+    for (int comp = 0; comp < c->ncomp; ++comp) {
+      int rc = bpc_decode_k(d_cw, d_sizes, d_q, bpc_k_args(c, frames, comp), st);
+      if (rc) return rc;
+    }
+    return PCS_OK;
+  }
   for (int comp = 0; comp < c->ncomp; ++comp) {
     int rc = bpc_decode(d_cw, d_sizes, d_q, bpc_args(c, frames, comp), st);
     if (rc) return rc;
@@ -222,7 +258,7 @@ int32_t pcs_create(const pcs_params* params, pcs_ctx** out) {
       p.coding_passes > 3 || p.k_factor < 0 || p.k_factor > 65.535f || p.max_batch < 1)
     return PCS_E_ARG;
   if (p.lossy && !(p.quant_size > 0)) return PCS_E_ARG;
-  if (p.coding_passes != 2 || p.k_factor != 0 || p.is_signed || p.bit_depth != 8) return PCS_E_UNSUPPORTED;
+  if (p.coding_passes != 2 || p.is_signed || p.bit_depth != 8) return PCS_E_UNSUPPORTED;
   // RGB: `-isRGB 1` with the default `-components 1` is what the reference's own examples use (README.md:105-115);
   // `-components 3` is accepted as well.  Grey: one component.
   if (p.is_rgb ? (p.components != 1 && p.components != 3) : p.components != 1) return PCS_E_UNSUPPORTED;
@@ -245,6 +281,9 @@ int32_t pcs_create(const pcs_params* params, pcs_ctx** out) {
   c->scratch_elems = dwt_scratch_elems(Wa, Ha, p.wavelet_levels);
   const char* t = std::getenv("PCS_STAGE_TIMING");
   c->timing = t && t[0] == '1';
+  // k > 0: `lut` holds the tables of ALL bit-plane files of every component (pcs_lut_load_k), header[7] sets each
+  c->lut_files = p.k_factor > 0 ? p.lut_header[7] : 1;
+  if (c->lut_files < 1 || c->lut_files > 32) { delete c; return PCS_E_LUT_RANGE; }
   int rc = build_prob_tables(c);
   if (rc != PCS_OK) { pcs_destroy(c); return rc; }
   const size_t B = (size_t)p.max_batch, PL = B * c->ncomp;  // frames, planes
@@ -284,7 +323,7 @@ void pcs_destroy(pcs_ctx* c) {
   cudaFree(c->d_scratch); cudaFree(c->d_status); cudaFree(c->d_px); cudaFree(c->d_tplanes); cudaFree(c->d_coeff); cudaFree(c->d_cw);
   cudaFree(c->d_sizes); cudaFree(c->d_stream); cudaFree(c->d_off);
   if (c->h_off) cudaFreeHost(c->h_off);
-  cudaFree(c->d_sstatus); cudaFree(c->d_soff); cudaFree(c->d_dwtq);
+  cudaFree(c->d_sstatus); cudaFree(c->d_soff); cudaFree(c->d_dwtq); cudaFree(c->d_lutk);
   for (auto& s2 : c->sstream) if (s2) cudaStreamDestroy(s2);
   for (auto& e2 : c->sev) if (e2) cudaEventDestroy(e2);
   for (auto& e2 : c->kev) if (e2) cudaEventDestroy(e2);

@@ -665,6 +665,319 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Complexity-scalable mode (-k > 0).  The planes below `consec` of a codeblock are coded coefficient by
+// coefficient ("bulk" pass, BPC/BPCEngine.cu:1285-1662,1683-1716,1776-1837) with the LUT set min(consec, MSB) of the
+// multi-file tables (Engines/Engine.cu:12-100).  This path is a plain lane-per-column-pair kernel with the state words
+// of the reference (magnitude << 1 | sign, flags in bits 31 / 29, significance plane in bits 28:24) in shared memory:
+// it is the SIMT form of oracle/picsong_oracle.c (pcso_bpc_encode_k / pcso_bpc_decode_k), which is pinned byte for
+// byte on reference runs.  Functionally complete, not yet tuned: the bit-sliced kernels above remain the k = 0 path.
+// As in the oracle, lane 0's subband decides `consec` for the whole block (exact for every block inside one subband;
+// a block that straddles subbands is undefined behaviour in the reference, whose own decoder aborts on it).
+// ---------------------------------------------------------------------------------------------
+__constant__ float kL2Norm[10][4] = {  // BPC/BPCEngine.cuh:158-169
+    {1.965908f, 1.0112865f, 1.0112865f, 0.52021784f}, {4.1224113f, 1.9968134f, 1.9968134f, 0.96721643f},
+    {8.416739f, 4.1833673f, 4.1833673f, 2.0792568f},  {16.935543f, 8.534108f, 8.534108f, 4.3004827f},
+    {33.924816f, 17.166693f, 17.166693f, 8.686718f},  {67.87687f, 34.385098f, 34.385098f, 17.41882f},
+    {135.76744f, 68.7964f, 68.7964f, 34.860676f},     {271.5416f, 137.60588f, 137.60588f, 69.73287f},
+    {543.0866f, 275.21814f, 275.21814f, 139.47136f},  {1086.1624f, 550.43286f, 550.43286f, 278.94202f}};
+
+struct KCoder { unsigned lower, size, slot, code, count; };
+
+__device__ __forceinline__ int klut(const BpcKArgs& a, int idx) { return (idx >= 0 && idx < a.lutN) ? __ldg(a.lut + idx) : 0; }
+__device__ __forceinline__ void k_subband(int X, int Y, const BpcKArgs& a, int& lvl, int& sb) {  // BPCEngine.cu:143-170
+  for (int e = 1; e <= a.wl; ++e) {
+    const bool bx = X >= (a.Wa >> e), by = Y >= (a.Ha >> e);
+    if (bx || by) { lvl = e - 1; sb = bx ? (by ? 2 : 0) : 1; return; }
+  }
+  lvl = a.wl; sb = 0;
+}
+__device__ __forceinline__ int k_sign_hv(int h, int v) {  // BPCEngine.cu:252-293
+  if (h == 0) return v == 0 ? 0 : (v > 0 ? 2 : 3);
+  if (h > 0) return v == 0 ? 4 : (v > 0 ? 6 : 0);
+  return v == 0 ? 5 : (v > 0 ? 1 : 7);
+}
+__device__ __forceinline__ int k_sgn(unsigned s) { return (s >> 31) ? ((s & 1u) ? -1 : 1) : 0; }
+__device__ __forceinline__ int k_sgn_bulk(unsigned s, int cur) {
+  return ((s >> 31) && ((s >> 24) & 31u) >= (unsigned)cur) ? ((s & 1u) ? -1 : 1) : 0;
+}
+// neighbour snapshot of (row i, column c) of this lane: 0 up-left, 1 up, 2 up-right, 3 left, 4 right, 5 down-left,
+// 6 down, 7 down-right; outside the codeblock counts as 0 (BPCEngine.cu:446-484)
+__device__ __forceinline__ void k_neighbours(const unsigned (*S)[32], int lane, int i, int c, unsigned (&n)[8]) {
+  auto at = [&](int l, int row, int col) -> unsigned {
+    return (row < 0 || row >= kCB || l < 0 || l > 31) ? 0u : S[2 * row + col][l];
+  };
+  if (c == 0) {
+    n[0] = at(lane - 1, i - 1, 1); n[1] = at(lane, i - 1, 0); n[2] = at(lane, i - 1, 1);
+    n[3] = at(lane - 1, i, 1);                                 n[4] = at(lane, i, 1);
+    n[5] = at(lane - 1, i + 1, 1); n[6] = at(lane, i + 1, 0); n[7] = at(lane, i + 1, 1);
+  } else {
+    n[0] = at(lane, i - 1, 0); n[1] = at(lane, i - 1, 1); n[2] = at(lane + 1, i - 1, 0);
+    n[3] = at(lane, i, 0);                                 n[4] = at(lane + 1, i, 0);
+    n[5] = at(lane, i + 1, 0); n[6] = at(lane, i + 1, 1); n[7] = at(lane + 1, i + 1, 0);
+  }
+}
+__device__ __forceinline__ int k_ctx(const unsigned (&n)[8]) {
+  int c = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) c += (int)(n[j] >> 31);
+  return c;
+}
+__device__ __forceinline__ int k_ctx_bulk(const unsigned (&n)[8], int B) {
+  int c = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) c += (int)(((n[j] >> 24) & 31u) >= (unsigned)B);
+  return c;
+}
+// one call site of the interval coder for the whole warp (BPCEngine.cu:371-442), slots handed out in lane order
+__device__ __forceinline__ void k_enc(KCoder& c, bool act, unsigned bit, int p, unsigned prec, unsigned short* out, unsigned lt) {
+  const bool need = act && c.size == 0;
+  const unsigned m = __ballot_sync(kFull, need);
+  if (need) { c.lower = 0; c.size = 0xFFFFu; c.slot = 1u + min(c.count + (unsigned)__popc(m & lt), 4094u); }
+  c.count = min(c.count + (unsigned)__popc(m), 4095u);
+  if (act) {
+    const unsigned t = ((c.size * (unsigned)p) >> prec) + bit;
+    if (bit == 0) c.size = t;
+    else { c.size -= t; c.lower += t; }
+    if (c.size == 0) out[c.slot] = (unsigned short)c.lower;
+  }
+}
+__device__ __forceinline__ unsigned k_dec(KCoder& c, bool act, int p, unsigned prec, const unsigned short* in, unsigned lt) {
+  const bool need = act && c.size == 0;
+  const unsigned m = __ballot_sync(kFull, need);
+  if (need) { c.lower = 0; c.size = 0xFFFFu; c.slot = 1u + min(c.count + (unsigned)__popc(m & lt), 4094u); c.code = in[c.slot]; }
+  c.count = min(c.count + (unsigned)__popc(m), 4095u);
+  unsigned sym = 0;
+  if (act) {
+    const unsigned t = ((c.size * (unsigned)p) >> prec) + 1u, lim = c.lower + t;
+    if (c.code >= lim) { c.size -= t; c.lower = lim; sym = 1; }
+    else c.size = t - 1u;
+  }
+  return sym;
+}
+// planes [0, consec) of a block go to the bulk pass (BPCEngine.cu:1683-1692)
+__device__ __forceinline__ int k_consec(const BpcKArgs& a, int X, int Y, int MSB) {
+  int lvl, sb;
+  k_subband(X, Y, a, lvl, sb);
+  const float norm = (a.wl == lvl) ? kL2Norm[max(lvl - 1, 0)][0] : kL2Norm[lvl][3 - sb];
+  return max((int)floorf((float)MSB * __fdiv_rn(a.k, norm)), 0);
+}
+__device__ __forceinline__ void k_pointers(const BpcKArgs& a, int X, int Y, int lane, int MSB, int consec, int& refP, int& sigP, int& sgnP) {
+  int lvl, sb;
+  k_subband(X + 2 * lane, Y, a, lvl, sb);  // per lane, as the reference (BPCEngine.cu:1975-1990)
+  const int R = a.nSub * a.nBp * a.cR * a.wl + a.nBp * a.cR, Sg = a.nSub * a.nBp * a.cS * a.wl + a.nBp * a.cS;
+  const int g = (lvl * a.nSub + sb) * a.nBp + MSB, off = min(consec, MSB) * a.per;  // LUT set (BPCEngine.cu:329-350)
+  refP = g * a.cR + off; sigP = R + g * a.cS + off; sgnP = R + Sg + g * a.cG + off;
+}
+
+constexpr int kKWarps = 2;
+
+template <typename T>
+__global__ void __launch_bounds__(32 * kKWarps) bpc_encode_k_kernel(const T* __restrict__ coeff, unsigned short* __restrict__ cw,
+                                                                   int* __restrict__ sizes, const BpcKArgs a) {
+  __shared__ unsigned s_S[kKWarps][2 * kCB][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int w = blockIdx.x * kKWarps + wib;
+  if (w >= a.total_cb) return;
+  const int frame = (w / a.ncb) * a.pstep + a.pfirst, cb = w % a.ncb;
+  const int X = (cb % a.nbx) * kCB, Y = (cb / a.nbx) * kCB;
+  const T* src = coeff + (size_t)frame * a.A + (size_t)Y * a.Wa + X + 2 * lane;
+  const size_t blk = (size_t)frame * a.ncb + cb;
+  unsigned short* out = cw + blk * kCBWords;
+  unsigned (*S)[32] = s_S[wib];
+  const unsigned lt = (1u << lane) - 1u, prec = (unsigned)a.prec;
+
+  unsigned ormag = 0;
+  for (int i = 0; i < kCB; ++i) {
+    int v0, v1;
+    load2<T>(src + (size_t)i * a.Wa, v0, v1);
+    const unsigned m0 = umag(v0), m1 = umag(v1);
+    S[2 * i][lane] = (m0 << 1) + (v0 < 0 ? 1u : 0u);  // BPCEngine.cu:41-63
+    S[2 * i + 1][lane] = (m1 << 1) + (v1 < 0 ? 1u : 0u);
+    ormag |= m0 | m1;
+  }
+  ormag = __reduce_or_sync(kFull, ormag);
+  const int MSB = ormag ? 31 - __clz(ormag) : 32;
+  if (MSB == 32) {
+    if (lane == 0) { out[0] = 32; sizes[blk] = 1; }
+    return;
+  }
+  if (lane == 0) out[0] = (unsigned short)MSB;
+  __syncwarp();
+  const int consec = k_consec(a, X, Y, MSB);
+  int refP, sigP, sgnP;
+  k_pointers(a, X, Y, lane, MSB, consec, refP, sigP, sgnP);
+  KCoder ac; ac.lower = 0; ac.size = 0; ac.slot = 0; ac.code = 0; ac.count = 0;
+  unsigned n[8];
+  int bp;
+  for (bp = MSB; bp >= consec; --bp) {
+    // significance propagation pass (BPCEngine.cu:770-843, 490-516)
+    for (int i = 0; i < kCB; ++i)
+      for (int c = 0; c < 2; ++c) {
+        k_neighbours(S, lane, i, c, n);
+        unsigned wd = S[2 * i + c][lane];
+        __syncwarp();
+        const bool act = !(wd >> 31);
+        const unsigned bit = (wd >> (bp + 1)) & 1u;
+        k_enc(ac, act, bit, klut(a, sigP + k_ctx(n)), prec, out, lt);
+        const bool one = act && bit;
+        int sc = 0;
+        if (one) {
+          wd |= 1u << 31; wd |= (unsigned)bp << 24;
+          sc = k_sign_hv(k_sgn(n[3]) + k_sgn(n[4]), k_sgn(n[1]) + k_sgn(n[6]));
+        }
+        k_enc(ac, one, ((wd & 1u) == (unsigned)(sc & 1)) ? 0u : 1u, klut(a, sgnP + (sc >> 1)), prec, out, lt);
+        S[2 * i + c][lane] = wd;
+        __syncwarp();
+      }
+    // magnitude refinement pass (BPCEngine.cu:1249-1261, 726-736)
+    for (int i = 0; i < kCB; ++i)
+      for (int c = 0; c < 2; ++c) {
+        unsigned wd = S[2 * i + c][lane];
+        const bool act = (wd >> 29) & 1u;
+        if (!act && (wd >> 31)) { wd |= 1u << 29; S[2 * i + c][lane] = wd; }
+        k_enc(ac, act, (wd >> (bp + 1)) & 1u, klut(a, refP), prec, out, lt);
+      }
+    __syncwarp();
+    refP -= a.cR; sigP -= a.cS; sgnP -= a.cG;
+  }
+  if (bp >= 0) {
+    // bulk pass: planes B..0 of one coefficient at a time; context and neighbour snapshot fixed per coefficient
+    const int B = bp;
+    for (int i = 0; i < kCB; ++i)
+      for (int c = 0; c < 2; ++c) {
+        k_neighbours(S, lane, i, c, n);
+        unsigned wd = S[2 * i + c][lane];
+        __syncwarp();
+        const bool any = __any_sync(kFull, !(wd >> 31));
+        const int ctx = any ? (B != 0 ? k_ctx_bulk(n, B) : k_ctx(n)) : 0;
+        for (int cur = B; cur >= 0; --cur) {
+          const int d = B - cur;
+          const bool sig = wd >> 31;
+          const unsigned bit = (wd >> (cur + 1)) & 1u;
+          k_enc(ac, sig, bit, klut(a, refP - a.cR * d), prec, out, lt);
+          k_enc(ac, !sig, bit, klut(a, sigP + ctx - a.cS * d), prec, out, lt);
+          const bool one = !sig && bit;
+          int sc = 0;
+          if (one) {
+            wd |= 1u << 31; wd |= (unsigned)cur << 24;
+            sc = k_sign_hv(k_sgn_bulk(n[3], cur) + k_sgn_bulk(n[4], cur), k_sgn_bulk(n[1], cur) + k_sgn_bulk(n[6], cur));
+          }
+          k_enc(ac, one, ((wd & 1u) == (unsigned)(sc & 1)) ? 0u : 1u, klut(a, sgnP + (sc >> 1) - a.cG * d), prec, out, lt);
+        }
+        S[2 * i + c][lane] = wd;
+        __syncwarp();
+      }
+  }
+  out[ac.slot] = (unsigned short)ac.lower;  // flush (BPCEngine.cu:1719)
+  const int size = (int)ac.count + 1;
+  __syncwarp();
+  if (size == kCBWords) {  // expansion fallback (BPCEngine.cu:2015-2024,1904-1912)
+    for (int kk = 0; kk < 2 * kCB; ++kk) out[lane * 2 * kCB + kk] = (unsigned short)(S[kk][lane] & 0xFFFFu);
+  }
+  if (lane == 0) sizes[blk] = size;
+}
+
+__global__ void __launch_bounds__(32 * kKWarps) bpc_decode_k_kernel(const unsigned short* __restrict__ cw, const int* __restrict__ sizes,
+                                                                   int* __restrict__ q, const BpcKArgs a) {
+  __shared__ unsigned s_S[kKWarps][2 * kCB][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int w = blockIdx.x * kKWarps + wib;
+  if (w >= a.total_cb) return;
+  const int frame = (w / a.ncb) * a.pstep + a.pfirst, cb = w % a.ncb;
+  const int X = (cb % a.nbx) * kCB, Y = (cb / a.nbx) * kCB;
+  int* dst = q + (size_t)frame * a.A + (size_t)Y * a.Wa + X + 2 * lane;
+  const size_t blk = (size_t)frame * a.ncb + cb;
+  const unsigned short* in = cw + blk * kCBWords;
+  unsigned (*S)[32] = s_S[wib];
+  const unsigned lt = (1u << lane) - 1u, prec = (unsigned)a.prec;
+  const int size = sizes[blk];
+  const int MSB = in[0];
+  for (int kk = 0; kk < 2 * kCB; ++kk) S[kk][lane] = 0u;
+  __syncwarp();
+  if (size == kCBWords) {  // raw block (BPCEngine.cu:2197-2200,1914-1922)
+    for (int kk = 0; kk < 2 * kCB; ++kk) S[kk][lane] = in[lane * 2 * kCB + kk];
+  } else if (MSB < 23) {   // 32 = all-zero block; 23..31 cannot be produced by the coder
+    const int consec = k_consec(a, X, Y, MSB);
+    int refP, sigP, sgnP;
+    k_pointers(a, X, Y, lane, MSB, consec, refP, sigP, sgnP);
+    KCoder ac; ac.lower = 0; ac.size = 0; ac.slot = 0; ac.code = 0; ac.count = 0;
+    unsigned mask = 0x3u << MSB;  // decoded bit + mid-point approximation bit (BPCEngine.cu:1791-1824)
+    if (MSB == 0) mask &= 0x2u;
+    unsigned n[8];
+    int bp;
+    for (bp = MSB; bp >= consec; --bp) {
+      for (int i = 0; i < kCB; ++i)
+        for (int c = 0; c < 2; ++c) {
+          k_neighbours(S, lane, i, c, n);
+          unsigned wd = S[2 * i + c][lane];
+          __syncwarp();
+          const bool act = !(wd >> 31);
+          const bool one = k_dec(ac, act, klut(a, sigP + k_ctx(n)), prec, in, lt) != 0;
+          int sc = 0;
+          if (one) {
+            wd |= mask; wd |= 1u << 31; wd |= (unsigned)bp << 24;
+            sc = k_sign_hv(k_sgn(n[3]) + k_sgn(n[4]), k_sgn(n[1]) + k_sgn(n[6]));
+          }
+          const unsigned sym = k_dec(ac, one, klut(a, sgnP + (sc >> 1)), prec, in, lt);
+          if (one) wd |= ((sym & 1u) == (unsigned)(sc & 1)) ? 0u : 1u;
+          S[2 * i + c][lane] = wd;
+          __syncwarp();
+        }
+      for (int i = 0; i < kCB; ++i)
+        for (int c = 0; c < 2; ++c) {
+          unsigned wd = S[2 * i + c][lane];
+          const bool act = (wd >> 29) & 1u;
+          if (!act && (wd >> 31)) wd |= 1u << 29;
+          const unsigned sym = k_dec(ac, act, klut(a, refP), prec, in, lt);
+          if (act) { wd &= ~mask; wd |= mask & (((sym << 1) + 1u) << bp); }
+          S[2 * i + c][lane] = wd;
+        }
+      __syncwarp();
+      mask >>= 1;
+      if (bp == 1) mask = 0x2u;
+      refP -= a.cR; sigP -= a.cS; sgnP -= a.cG;
+    }
+    if (bp >= 0) {
+      const int B = bp;
+      const unsigned mask0 = mask;
+      for (int i = 0; i < kCB; ++i)
+        for (int c = 0; c < 2; ++c) {
+          k_neighbours(S, lane, i, c, n);
+          unsigned wd = S[2 * i + c][lane];
+          __syncwarp();
+          const bool any = __any_sync(kFull, !(wd >> 31));
+          const int ctx = any ? (B != 0 ? k_ctx_bulk(n, B) : k_ctx(n)) : 0;
+          unsigned m = mask0;
+          for (int cur = B; cur >= 0; --cur) {
+            const int d = B - cur;
+            const bool sig = wd >> 31;
+            const unsigned rs = k_dec(ac, sig, klut(a, refP - a.cR * d), prec, in, lt);
+            if (sig) { wd &= ~m; wd |= m & (((rs << 1) + 1u) << cur); }
+            const bool one = k_dec(ac, !sig, klut(a, sigP + ctx - a.cS * d), prec, in, lt) != 0;
+            int sc = 0;
+            if (one) {
+              wd |= m; wd |= 1u << 31; wd |= (unsigned)cur << 24;
+              sc = k_sign_hv(k_sgn_bulk(n[3], cur) + k_sgn_bulk(n[4], cur), k_sgn_bulk(n[1], cur) + k_sgn_bulk(n[6], cur));
+            }
+            const unsigned sym = k_dec(ac, one, klut(a, sgnP + (sc >> 1) - a.cG * d), prec, in, lt);
+            if (one) wd |= ((sym & 1u) == (unsigned)(sc & 1)) ? 0u : 1u;
+            m >>= 1;
+            if (cur == 1) m = 0x2u;
+          }
+          S[2 * i + c][lane] = wd;
+          __syncwarp();
+        }
+    }
+  }
+  __syncwarp();
+  for (int i = 0; i < kCB; ++i) {  // BPCEngine.cu:94-111
+    const unsigned w0 = S[2 * i][lane], w1 = S[2 * i + 1][lane];
+    const int v0 = (int)((w0 & 0xFFFFFFu) >> 1), v1 = (int)((w1 & 0xFFFFFFu) >> 1);
+    *reinterpret_cast<int2*>(dst + (size_t)i * a.Wa) = make_int2((w0 & 1u) ? -v0 : v0, (w1 & 1u) ? -v1 : v1);
+  }
+}
+
 // Debug/parity export: the reference's int32 sparse `DCodeStreamValues` layout, -1 filled.
 __global__ void export_ref_cs_kernel(const unsigned short* cw, const int* sizes, int* ref, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -687,6 +1000,21 @@ int bpc_decode(const uint16_t* d_cw, const int32_t* d_sizes, int32_t* d_q, const
   const int blocks = (a.total_cb + 3) / 4;
   if (a.prec == 7) bpc_decode_kernel<7><<<blocks, 128, 0, st>>>(d_cw, d_sizes, d_q, a);
   else bpc_decode_kernel<0><<<blocks, 128, 0, st>>>(d_cw, d_sizes, d_q, a);
+  ++g_launches;
+  return (int)cudaGetLastError();
+}
+
+int bpc_encode_k(const void* d_coeff, bool is_float, uint16_t* d_cw, int32_t* d_sizes, const BpcKArgs& a, cudaStream_t st) {
+  const int blocks = (a.total_cb + kKWarps - 1) / kKWarps;
+  if (is_float) bpc_encode_k_kernel<float><<<blocks, 32 * kKWarps, 0, st>>>(static_cast<const float*>(d_coeff), d_cw, d_sizes, a);
+  else bpc_encode_k_kernel<int><<<blocks, 32 * kKWarps, 0, st>>>(static_cast<const int*>(d_coeff), d_cw, d_sizes, a);
+  ++g_launches;
+  return (int)cudaGetLastError();
+}
+
+int bpc_decode_k(const uint16_t* d_cw, const int32_t* d_sizes, int32_t* d_q, const BpcKArgs& a, cudaStream_t st) {
+  const int blocks = (a.total_cb + kKWarps - 1) / kKWarps;
+  bpc_decode_k_kernel<<<blocks, 32 * kKWarps, 0, st>>>(d_cw, d_sizes, d_q, a);
   ++g_launches;
   return (int)cudaGetLastError();
 }

@@ -93,7 +93,28 @@ int32_t pcs_lut_load(const char* folder, int32_t wl, int32_t header[8], int32_t*
 
 // RGB path: component i is coded with the i-th table set, files "R", "G", "B" (Engines/Engine.cu:124-139,
 // Engines/CodingEngine.cu:616,696,790).
+static int32_t lut_load_file(const char* folder, int32_t wl, int32_t component, int file, int32_t header[8], int32_t* table, int32_t capacity);
 int32_t pcs_lut_load_component(const char* folder, int32_t wl, int32_t component, int32_t header[8], int32_t* table, int32_t capacity) {
+  return lut_load_file(folder, wl, component, 0, header, table, capacity);
+}
+
+// k > 0 (Engines/Engine.cu:12-100): the tables of the bit-plane files `_0 .. _(AMOUNT_OF_BITPLANE_FILES - 1)` of one
+// component back to back, pcs_lut_size() ints each; BPCEngine::initializeLUTPointers selects set s by adding s * size
+// (BPC/BPCEngine.cu:333).  The file index only enters the file name (IO/IOManager.ipp:445-447).
+int32_t pcs_lut_load_k(const char* folder, int32_t wl, int32_t component, int32_t header[8], int32_t* table, int32_t capacity) {
+  if (!folder) return PCS_E_ARG;
+  if (!read_lut_header(std::string(folder), header)) return PCS_E_LUT;
+  const int files = header[7], n = pcs_lut_size(header, wl);
+  if (files < 1 || files > 32 || n <= 0) return PCS_E_LUT;
+  if ((long long)n * files > capacity) return PCS_E_NOMEM;
+  for (int j = 0; j < files; ++j) {
+    const int32_t r = lut_load_file(folder, wl, component, j, header, table + (size_t)j * n, n);
+    if (r < 0) return r;
+  }
+  return n * files;
+}
+
+static int32_t lut_load_file(const char* folder, int32_t wl, int32_t component, int file, int32_t header[8], int32_t* table, int32_t capacity) {
   if (!folder || wl < 1 || wl > 10 || component < 0 || component > 2) return PCS_E_ARG;
   const std::string dir(folder);
   if (!read_lut_header(dir, header)) return PCS_E_LUT;
@@ -105,9 +126,10 @@ int32_t pcs_lut_load_component(const char* folder, int32_t wl, int32_t component
   const int R = (nSub * wl + 1) * nBp * cR, S = (nSub * wl + 1) * nBp * cS;
   static const char* const kComp[3] = {"R", "G", "B"};
   const std::string comp = header[6] == 1 ? "" : kComp[component];
-  if (!read_lut_section(dir + "ref" + comp + ".txt_0", t, 0, nBp, cR, wl)) return PCS_E_LUT;
-  if (!read_lut_section(dir + "sig" + comp + ".txt_0", t, R, nBp, cS, wl)) return PCS_E_LUT;
-  if (!read_lut_section(dir + "sign" + comp + ".txt_0", t, R + S, nBp, cG, wl)) return PCS_E_LUT;
+  const std::string sfx = ".txt_" + std::to_string(file);
+  if (!read_lut_section(dir + "ref" + comp + sfx, t, 0, nBp, cR, wl)) return PCS_E_LUT;
+  if (!read_lut_section(dir + "sig" + comp + sfx, t, R, nBp, cS, wl)) return PCS_E_LUT;
+  if (!read_lut_section(dir + "sign" + comp + sfx, t, R + S, nBp, cG, wl)) return PCS_E_LUT;
   std::memcpy(table, t.data(), (size_t)n * sizeof(int32_t));
   return n;
 }

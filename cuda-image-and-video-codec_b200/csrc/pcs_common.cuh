@@ -35,6 +35,16 @@ struct BpcArgs {
   const uint4* tab4;               // [nrows] probability rows of this launch's component, as bytes: x = sig ctx 0..3, y = sig ctx 4..7, z = sig ctx 8 | ref << 8, w = sign ctx 0..3
 };
 // Arguments of the bit-stream builder kernels (bsb.cu)
+// complexity-scalable mode (k > 0): flat int32 tables of all bit-plane files, reference indexing
+struct BpcKArgs {
+  int Wa, Ha, nbx, ncb, wl, nBp, nSub, cR, cS, cG, prec, total_cb;
+  int pstep, pfirst;
+  int per, lutN;                   // ints per LUT set (file), ints in `lut`
+  long long A;
+  float k;
+  const int* lut;                  // this launch's component: [files][per]
+};
+
 struct BsbArgs {
   int ncb;                // codeblocks per frame
   int batch;              // frames

@@ -28,6 +28,7 @@ SYMBOLS = {
     "pcs_lut_load": (_I32, [C.c_char_p, _I32, C.POINTER(_I32), C.POINTER(_I32), _I32]),
     "pcs_lut_size": (_I32, [C.POINTER(_I32), _I32]),
     "pcs_lut_load_component": (_I32, [C.c_char_p, _I32, _I32, C.POINTER(_I32), C.POINTER(_I32), _I32]),
+    "pcs_lut_load_k": (_I32, [C.c_char_p, _I32, _I32, C.POINTER(_I32), C.POINTER(_I32), _I32]),
     "pcs_frame_planes": (_I32, [_VP]),
     "pcs_header_pack": (None, [C.POINTER(PcsParams), _U16P]),
     "pcs_header_unpack": (_I32, [_U16P, C.POINTER(PcsParams)]),

@@ -41,16 +41,16 @@ class Lut:
     table: np.ndarray
 
 
-def load_lut(folder: str, wl: int, rgb: bool = False) -> Lut:
-    """Engine::initLUT for k=0 (Engines/Engine.cu:101-141 of the reference): the "R" table set for greyscale,
-    the R, G and B sets back to back for the RGB path."""
+def load_lut(folder: str, wl: int, rgb: bool = False, k: bool = False) -> Lut:
+    """Engine::initLUT (Engines/Engine.cu:8-141 of the reference): the "R" table set for greyscale, the R, G and B sets
+    back to back for the RGB path; k=True: all bit-plane files of each component (for Params(k > 0))."""
     lib = _lib.load()
     hdr = (C.c_int32 * 8)()
-    cap = 1 << 16
+    cap = 1 << 20 if k else 1 << 16
     parts = []
     for comp in range(3 if rgb else 1):
         tab = (C.c_int32 * cap)()
-        n = lib.pcs_lut_load_component(folder.encode(), wl, comp, hdr, tab, cap)
+        n = (lib.pcs_lut_load_k if k else lib.pcs_lut_load_component)(folder.encode(), wl, comp, hdr, tab, cap)
         if n <= 0:
             raise PcsError(f"pcs_lut_load_component({folder!r}, wl={wl}, {comp}) failed: {n}")
         parts.append(np.array(tab[:n], dtype=np.int32))

@@ -78,6 +78,12 @@ int32_t pcs_lut_size(const int32_t header[8], int32_t wavelet_levels);
  * context pcs_params.lut is the three component tables back to back (lut_len = 3 * pcs_lut_size). */
 int32_t pcs_lut_load_component(const char* folder, int32_t wavelet_levels, int32_t component, int32_t header[8],
                                int32_t* table, int32_t capacity);
+/* Complexity-scalable mode (-k > 0, Engines/Engine.cu:12-100): the tables of ALL bit-plane files `*_0 .. *_(n-1)`
+ * (n = header[7], AMOUNT_OF_BITPLANE_FILES) of one component back to back, pcs_lut_size() ints each.  A context
+ * created with k_factor > 0 expects these tables (lut_len = components * n * pcs_lut_size()) instead of the k = 0
+ * ones.  Returns the number of ints written or a negative PCS_E_* code. */
+int32_t pcs_lut_load_k(const char* folder, int32_t wavelet_levels, int32_t component, int32_t header[8],
+                       int32_t* table, int32_t capacity);
 
 /* BitStreamBuilder::setExtraInformation (BitStreamBuilder/BitStreamBuilder.cpp:35-94) */
 void pcs_header_pack(const pcs_params* p, uint16_t out[9]);

@@ -65,7 +65,8 @@ def test_parameter_validation_and_no_cpu_fallback(lut_root):
     assert create(wl=0)[0] == -1 and create(wl=11)[0] == -1        # PCS_E_ARG
     assert create(cb_height=17)[0] == -1 and create(cb_width=65)[0] == -1
     assert create(qs=1.5)[0] == -1 and create(width=0)[0] == -1
-    assert create(cp=3)[0] == -4 and create(k=1.0)[0] == -4        # PCS_E_UNSUPPORTED (out of scope)
+    assert create(cp=3)[0] == -4                                    # PCS_E_UNSUPPORTED (out of scope)
+    assert create(k=1.0)[0] == -2                                   # PCS_E_LUT: k > 0 needs the tables of all bit-plane files
     import torch
     if not torch.cuda.is_available():
         rc, ctx = create()
