@@ -29,11 +29,13 @@ pcs_ctx* Engine::makeContext(int maxBatch, unsigned flags) {
   p.frames = _numberOfFrames; p.bit_depth = _img->bitDepth; p.bits_per_sample = _img->bitsPerSample;
   p.endianess = _img->endianess; p.is_signed = _img->signedOrUnsigned; p.components = _img->components; p.is_rgb = _img->isRGB;
   p.max_batch = maxBatch; p.flags = flags;
-  // greyscale codes with the "R" table set; the RGB path codes component i with set i (Engines/Engine.cu:124-139)
-  std::vector<int32_t> table(3 << 16);
+  // greyscale codes with the "R" table set; the RGB path codes component i with set i (Engines/Engine.cu:124-139);
+  // k > 0 loads every bit-plane file of a component (Engines/Engine.cu:12-100)
+  std::vector<int32_t> table(_k > 0 ? (3 << 20) : (3 << 16));
   int n = 0;
   for (int comp = 0; comp < (_img->isRGB ? 3 : 1); ++comp) {
-    const int m = pcs_lut_load_component(_lutPath.c_str(), _waveletLevels, comp, p.lut_header, table.data() + n, (int)table.size() - n);
+    const int m = _k > 0 ? pcs_lut_load_k(_lutPath.c_str(), _waveletLevels, comp, p.lut_header, table.data() + n, (int)table.size() - n)
+                         : pcs_lut_load_component(_lutPath.c_str(), _waveletLevels, comp, p.lut_header, table.data() + n, (int)table.size() - n);
     if (m <= 0) die("Error opening LUT files in " + _lutPath);
     n += m;
   }
@@ -41,7 +43,7 @@ pcs_ctx* Engine::makeContext(int maxBatch, unsigned flags) {
   pcs_ctx* ctx = nullptr;
   const int rc = pcs_create(&p, &ctx);
   if (rc == PCS_E_ARG) die("Incorrect parameters. Please choose valid values.", -1);
-  if (rc == PCS_E_UNSUPPORTED) die("This build covers the 8-bit unsigned 2-coding-pass k=0 paths, grey and RGB (cp=3, k>0 and signed input are out of scope).", -1);
+  if (rc == PCS_E_UNSUPPORTED) die("This build covers the 8-bit unsigned 2-coding-pass paths, grey and RGB, k >= 0 (cp=3 and signed input are out of scope).", -1);
   if (rc != 0) die("pcs_create failed with code " + std::to_string(rc) + (rc > 0 ? " (CUDA error: is a GPU present? there is no CPU fallback)" : ""));
   return ctx;
 }

@@ -31,7 +31,7 @@ enum {
   PCS_E_ARG = -1,        /* invalid parameter ("Incorrect parameters", Launcher.cu:132-136) */
   PCS_E_LUT = -2,        /* LUT folder unreadable / malformed */
   PCS_E_LUT_RANGE = -3,  /* LUT shape or probability outside what the coder supports */
-  PCS_E_UNSUPPORTED = -4,/* cp==3, k>0, signed / 16-bit input: out of scope */
+  PCS_E_UNSUPPORTED = -4,/* cp==3, signed / 16-bit input: out of scope */
   PCS_E_NOMEM = -5,
   PCS_E_STREAM = -6,     /* malformed codestream */
   PCS_E_BATCH = -7       /* batch larger than pcs_params.max_batch */
@@ -51,7 +51,7 @@ typedef struct pcs_params {
   int32_t lossy;              /* setWType: 0 = reversible 5/3, 1 = irreversible 9/7 */
   float quant_size;           /* setQSizes (-qs), (0,1] */
   int32_t coding_passes;      /* setCodingPasses: 2 (3 is out of scope) */
-  float k_factor;             /* setKFactor: 0 (bulk mode is out of scope) */
+  float k_factor;             /* setKFactor (-k): 0, or > 0 = complexity-scalable mode (needs the pcs_lut_load_k tables) */
   int32_t cb_width, cb_height;/* setCBWidth/setCBHeight: header-only values (64, 18..20) */
   int32_t frames;             /* setNumberOfFrames: value written to the header (0 for stills) */
   int32_t bit_depth, bits_per_sample, endianess, is_signed, components, is_rgb;

@@ -34,3 +34,33 @@ def materialize(folder: str, dst_root: str) -> str:
 
 def materialize_all(dst_root: str):
     return {f: materialize(f, dst_root) for f in FOLDERS}
+
+
+def materialize_k(folder: str, wl: int, dst_root: str) -> str:
+    """A LUT folder with ALL bit-plane files (`*_0 .. *_(n-1)`, the complexity-scalable mode) rebuilt from the parsed
+    tables of tests/golden/lut_tables_k.npz (made by oracle/make_golden_k.py for exactly this folder and level count).
+    Every (group, bit-plane) row is written out, so the text loaders re-create the same tables."""
+    z = np.load(os.path.join(_HERE, "golden", "lut_tables_k.npz"))
+    key = f"{folder}_wl{wl}"
+    hdr = [int(v) for v in z[key + "_hdr"]]
+    nBp, nSub, cR, cG, cS, files = hdr[0], hdr[1], hdr[2], hdr[3], hdr[4], hdr[7]
+    groups = nSub * wl + 1
+    R, S, G = groups * nBp * cR, groups * nBp * cS, groups * nBp * cG
+    per = R + S + G
+    d = os.path.join(dst_root, f"{folder}_k_wl{wl}")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "header.txt"), "w") as f:
+        f.write("\n".join(f"{n};{v}" for n, v in zip(_HDR_NAMES, hdr)))
+    for comp, letter in enumerate("RGB"):
+        ck = key if comp == 0 else f"{key}_c{comp}"
+        if ck not in z.files:
+            continue
+        tab = z[ck].reshape(files, per)
+        for j in range(files):
+            for sec, base, ctx in (("ref", 0, cR), ("sig", R, cS), ("sign", R + S, cG)):
+                with open(os.path.join(d, f"{sec}{letter}.txt_{j}"), "w") as f:
+                    for g in range(groups):
+                        for bp in range(nBp):
+                            v = tab[j, base + (g * nBp + bp) * ctx: base + (g * nBp + bp + 1) * ctx]
+                            f.write(f"{g // nSub} {g % nSub} {bp} : " + " ".join(str(int(x)) for x in v) + " \n")
+    return d + "/"

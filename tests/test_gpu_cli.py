@@ -81,3 +81,26 @@ def test_cli_rgb(tmp_path, golden, lut_root):
     assert rc == 0, out
     d = np.abs(np.fromfile(dec, dtype=np.uint8).astype(int) - golden.decoded("rgbv256_f2_wl3_q1").astype(int))
     assert d.max() <= 1 and (d != 0).mean() <= 1e-4
+
+
+def test_cli_k_factor(tmp_path):
+    """-k 1: the complexity-scalable mode through the command line; stream identical to the reference binary's
+    (tests/golden/k_factor), the decoder takes k from the header and reproduces the input."""
+    import json
+
+    import lut_fixture
+    from picsong_b200 import synth
+    kdir = os.path.join(ROOT, "tests", "golden", "k_factor")
+    e = json.load(open(os.path.join(kdir, "manifest.json")))["k1_s256_wl2_ll"]
+    lut = lut_fixture.materialize_k("n1_lossless", 2, str(tmp_path))
+    raw, enc, dec = tmp_path / "k.raw", tmp_path / "k.pcs", tmp_path / "k.pgm"
+    img = synth.synth_frame(256, 256, 0)
+    img.tofile(raw)
+    rc, out = run(["-cd", 0, "-wl", 2, "-cp", 2, "-type", 0, "-qs", 1, "-i", raw, "-o", enc, "-cbWidth", 64, "-cbHeight", 18,
+                   "-xSize", 256, "-ySize", 256, "-video", 0, "-LUTFolder", lut, "-k", 1])
+    assert rc == 0, out
+    assert np.array_equal(np.fromfile(enc, dtype=np.uint16), np.fromfile(os.path.join(kdir, "k1_s256_wl2_ll.enc"), dtype=np.uint16))
+    rc, out = run(["-cd", 1, "-i", enc, "-o", dec, "-LUTFolder", lut, "-video", 0])
+    assert rc == 0, out
+    blob = open(dec, "rb").read()
+    assert np.array_equal(np.frombuffer(blob[len(b"P5\n256 256\n255\n"):], dtype=np.uint8), img.reshape(-1)) and e["rc_dec"] == 0

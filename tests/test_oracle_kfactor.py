@@ -135,3 +135,22 @@ def test_bulk_mode_decoder_inverts_the_encoder_and_matches_the_reference_decoder
     else:
         d = np.fromfile(os.path.join(KDIR, name + ".dec"), dtype=np.uint8)
         assert np.array_equal(out, d[d.size - e["W"] * e["H"]:].reshape(e["H"], e["W"]))
+
+
+def test_text_loaders_rebuild_k_tables(tmp_path):
+    """The folder written back by lut_fixture.materialize_k parses to the same tables with the oracle's loader and
+    with the product's (pcs_lut_load_k, C ABI) -- no reference tree needed."""
+    import ctypes as C
+
+    import lut_fixture
+    from picsong_b200 import _lib
+    lib = _lib.load()
+    for folder, wl, comps in (("n1_lossless", 2, 3), ("n1_lossy", 2, 1), ("video_lossy", 2, 1)):
+        d = lut_fixture.materialize_k(folder, wl, str(tmp_path))
+        for c in range(comps):
+            want = TABLES[f"{folder}_wl{wl}" if c == 0 else f"{folder}_wl{wl}_c{c}"]
+            assert np.array_equal(O.lut_load_k(d, wl, c).table, want)
+            hdr = (C.c_int32 * 8)()
+            tab = (C.c_int32 * (1 << 20))()
+            n = lib.pcs_lut_load_k(d.encode(), wl, c, hdr, tab, 1 << 20)
+            assert n == want.size and np.array_equal(np.array(tab[:n], dtype=np.int32), want)
