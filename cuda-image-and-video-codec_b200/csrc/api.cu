@@ -109,7 +109,8 @@ BsbArgs bsb_args(const pcs_ctx* c, int planes, int first_plane) {
   a.ncb = c->ncb; a.batch = planes; a.first_frame_index = first_plane;
   // stills: component i is coded with iter = i, video: every component of frame f with iter = f
   // (CodingEngine.cu:620,700 vs :790,902) -> the three planes of video frame 0 all carry the header
-  a.hdr_count = (c->ncomp == 3 && c->p.frames > 0) ? 3 : 1;
+  // (PCS_F_STILLS: the caller codes stills although `frames`, a header-only value, is > 0)
+  a.hdr_count = (c->ncomp == 3 && c->p.frames > 0 && !(c->p.flags & PCS_F_STILLS)) ? 3 : 1;
   uint16_t h[9];
   pcs_header_pack(&c->p, h);
   for (int i = 0; i < 9; ++i) a.hdr[i] = h[i];
@@ -129,6 +130,7 @@ int build_prob_tables(pcs_ctx* c) {
   const int n = R + S + (nSub * wl + 1) * nBp * cG;  // entries per component
   if ((long long)c->lut.size() < (long long)n * c->lut_files * c->ncomp) return PCS_E_LUT;
   const int nrows = (nSub * wl + 1) * nBp + 32;
+  if (nrows > kMaxProbRows) return PCS_E_LUT_RANGE;  // e.g. nBp = 16 at wl = 10: more rows than the decoder stages
   std::vector<uint4> tab4((size_t)nrows * c->ncomp, make_uint4(0, 0, 0, 0));
   for (int comp = 0; comp < c->ncomp; ++comp) {
     const int32_t* lut = c->lut.data() + (size_t)comp * n * c->lut_files;  // set 0 of the component (the k == 0 tables)
@@ -530,7 +532,7 @@ int32_t pcs_encode_frames(pcs_ctx* c, const uint8_t* h_px, int32_t nframes, int3
     PCS_CUDA_TRY(cudaEventSynchronize(s.ev));
     const size_t words = (size_t)s.h_off[b * nc];
     if (written + words > cap) return fail(c, PCS_E_NOMEM, "output capacity too small");
-    PCS_CUDA_TRY(cudaMemcpyAsync(h_stream + written, s.stream, words * 2, cudaMemcpyDeviceToHost, s.st));
+    PCS_CUDA_TRY(cudaMemcpyAsync(h_stream + written, s.stream, words * 2, cudaMemcpyDefault, s.st));
     if (h_len) for (int f = 0; f < b * nc; ++f) h_len[(size_t)f0 * nc + f] = (int32_t)(s.h_off[f + 1] - s.h_off[f]);
     written += words;
     return PCS_OK;
@@ -546,7 +548,7 @@ int32_t pcs_encode_frames(pcs_ctx* c, const uint8_t* h_px, int32_t nframes, int3
     while (finished <= i - nslots) { int rc = finish(finished++); if (rc) return rc; }  // frees the slot (same stream: ordered)
     Slot s = make_slot(c, i % nslots, sb);
     const int f0 = plan[i].f0, b = plan[i].b;
-    PCS_CUDA_TRY(cudaMemcpyAsync(s.px, h_px + (size_t)f0 * fpx, (size_t)b * fpx, cudaMemcpyHostToDevice, s.st));
+    PCS_CUDA_TRY(cudaMemcpyAsync(s.px, h_px + (size_t)f0 * fpx, (size_t)b * fpx, cudaMemcpyDefault, s.st));
     if (i >= depth && depth < nslots) PCS_CUDA_TRY(cudaStreamWaitEvent(s.st, c->kev[(i - depth) % nslots], 0));
     int rc = run_dwt_forward(c, s.w, s.px, s.w.coeff, true, b, s.st, nullptr);
     if (rc) return rc;
@@ -588,7 +590,7 @@ int32_t pcs_decode_frames(pcs_ctx* c, const uint16_t* h_stream, const int32_t* h
       s.h_off[f] = off; off += len;
     }
     s.h_off[b * nc] = off;
-    PCS_CUDA_TRY(cudaMemcpyAsync(s.stream, h_stream + consumed, (size_t)off * 2, cudaMemcpyHostToDevice, s.st));
+    PCS_CUDA_TRY(cudaMemcpyAsync(s.stream, h_stream + consumed, (size_t)off * 2, cudaMemcpyDefault, s.st));
     PCS_CUDA_TRY(cudaMemcpyAsync(s.d_off, s.h_off, (size_t)(b * nc + 1) * sizeof(long long), cudaMemcpyHostToDevice, s.st));
     PCS_CUDA_TRY(cudaEventRecord(s.ev, s.st));
     if (i >= depth && depth < nslots) PCS_CUDA_TRY(cudaStreamWaitEvent(s.st, c->kev[(i - depth) % nslots], 0));
@@ -599,7 +601,7 @@ int32_t pcs_decode_frames(pcs_ctx* c, const uint16_t* h_stream, const int32_t* h
     rc = run_dwt_inverse(c, s.w, s.w.coeff, s.px, b, s.st, nullptr);
     if (rc) return rc;
     PCS_CUDA_TRY(cudaEventRecord(c->kev[i % nslots], s.st));
-    PCS_CUDA_TRY(cudaMemcpyAsync(h_px + (size_t)f0 * fpx, s.px, (size_t)b * fpx, cudaMemcpyDeviceToHost, s.st));
+    PCS_CUDA_TRY(cudaMemcpyAsync(h_px + (size_t)f0 * fpx, s.px, (size_t)b * fpx, cudaMemcpyDefault, s.st));
     consumed += (size_t)off;
   }
   for (int k = 0; k < nslots; ++k) PCS_CUDA_TRY(cudaStreamSynchronize(c->sstream[k]));

@@ -455,7 +455,6 @@ __device__ __forceinline__ unsigned dec_step(unsigned actw, unsigned bitm, unsig
   return b;
 }
 
-constexpr int kMaxProbRows = (3 * kMaxLevels + 1) * 15 + 32;  // shipped tables: nSub = 3, nBp = 15
 
 #ifndef PCS_DEC_MINB
 #define PCS_DEC_MINB 5

@@ -97,12 +97,13 @@ void CodingEngine::engineManager(int cType) {
   const int planes = _img->isRGB ? 3 : 1;  // RGB input: planar R, G, B planes per frame (IOManager.ipp:72-112 with iter = 3f+c)
   const size_t fpx = (size_t)_img->width * _img->height * planes;
   const int batch = (int)batchFor(_img, frames);
-  pcs_ctx* ctx = makeContext(batch, 0);
+  pcs_ctx* ctx = makeContext(batch, video ? 0u : PCS_F_STILLS);  // stills: only plane 0 carries the header, whatever -frames says
   std::ifstream in(_img->name, std::ios::binary);
   if (!in) die("Error opening input file " + _img->name);
   std::remove(_outputFile.c_str());                       // replaceExistingFile, IOManager.ipp:158-170
   std::remove((_outputFile + "_SIZE").c_str());
   std::ofstream out(_outputFile, std::ios::binary | std::ios::trunc);
+  if (!out) die("Error opening output file " + _outputFile);
   const size_t maxWords = (size_t)batch * pcs_frame_max_stream_words(ctx);
   PinnedRing ring((size_t)batch * fpx, maxWords, (size_t)batch * planes);
   if (!ring.ok()) die("pinned host allocation failed");
@@ -174,7 +175,7 @@ void DecodingEngine::engineManager(int cType) {
   const size_t fpx = (size_t)_img->width * _img->height * planes;
   const int batch = (int)batchFor(_img, frames);
   // PCS_F_REF_FLAT_CROP keeps the reference's output byte order when the width is not a multiple of 64
-  pcs_ctx* ctx = makeContext(batch, std::getenv("PICSONG_PROPER_CROP") ? 0u : PCS_F_REF_FLAT_CROP);
+  pcs_ctx* ctx = makeContext(batch, (std::getenv("PICSONG_PROPER_CROP") ? 0u : PCS_F_REF_FLAT_CROP) | (video ? 0u : PCS_F_STILLS));
   std::vector<int32_t> lens((size_t)frames * planes);
   in.seekg(0, std::ios::end);
   const size_t fileWords = (size_t)in.tellg() / 2;
@@ -183,7 +184,10 @@ void DecodingEngine::engineManager(int cType) {
     std::string tok;
     for (int f = 0; f < frames * planes; ++f) {
       if (!std::getline(s, tok, ',')) die("_SIZE sidecar is missing or too short");
-      lens[f] = std::stoi(tok);
+      char* end = nullptr;
+      const long v = std::strtol(tok.c_str(), &end, 10);
+      if (end == tok.c_str() || v <= 0 || v > 0x7fffffffL) die("_SIZE sidecar malformed");
+      lens[f] = (int32_t)v;
     }
   } else {
     lens[0] = (int32_t)fileWords;
@@ -191,6 +195,7 @@ void DecodingEngine::engineManager(int cType) {
   in.seekg(0);
   std::remove(_outputFile.c_str());
   std::ofstream out(_outputFile, std::ios::binary | std::ios::trunc);
+  if (!out) die("Error opening output file " + _outputFile);
   if (!video && planes == 1) out << "P5\n" << _img->width << " " << _img->height << "\n" << ((2 << (_img->bitDepth - 1)) - 1) << "\n";
   const size_t maxWords = (size_t)batch * pcs_frame_max_stream_words(ctx);
   // here the ring's "in" side holds pixels (output of the GPU) and its "out" side codestream words (input)

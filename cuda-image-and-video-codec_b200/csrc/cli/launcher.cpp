@@ -4,6 +4,7 @@
 // an alias of `-cbHeight` (the name its parser reads).
 #include <algorithm>
 #include <chrono>
+#include <exception>
 #include <iostream>
 #include <string>
 #include <vector>
@@ -37,14 +38,25 @@ void printHelp() {  // IO/CommandLineParser.cpp:28-49
                " -cbWidth / -cbLength DWT block size written to the header (64 / 18..20); -cbHeight is the same flag\n"
                " -video [0|1] -frames N   video mode (writes <out>_SIZE)\n"
                " -LUTFolder <dir/>    probability tables\n"
-               " -k [0..65.535]       complexity scalability (0 only in this build)\n"
+               " -k [0..65.535]       complexity scalability (0 = off; > 0 needs the LUT folder's bit-plane files *_0 .. *_15)\n"
                " -numberOfStreams N   accepted for compatibility (frames are batched instead)\n"
                " -bps -endianess -signedOrUnsigned -components -isRGB -avoidSizeCheck   as in the reference\n";
 }
 
 }  // namespace
 
+static int run(int argc, char** argv);
+
 int main(int argc, char** argv) {
+  try {
+    return run(argc, argv);
+  } catch (const std::exception&) {  // std::stoi / std::stof on a malformed flag value
+    std::cout << "Incorrect parameters. Please choose valid values." << std::endl;  // Launcher.cu:132-136
+    return 255;
+  }
+}
+
+static int run(int argc, char** argv) {
   auto start = std::chrono::steady_clock::now();
   InputParser ip(argc, argv);
   if (ip.has("-h")) { printHelp(); return 0; }

@@ -10,6 +10,10 @@ namespace pcs {
 constexpr int kCB = 64;          // codeblock edge (BPC/BPCEngine.cuh:29-36 of the reference)
 constexpr int kCBWords = 4096;   // words reserved per codeblock
 constexpr int kMaxLevels = 10;   // Launcher.cu:132 accepts wl in [1,10]
+// Probability rows the k = 0 decoder stages in shared memory: (nSub * wl + 1) * nBp + 32 for the shipped table shape
+// (nSub = 3, nBp = 15) at the deepest wl.  pcs_create refuses tables with more rows (PCS_E_LUT_RANGE) so that the
+// encoder (global reads) and the decoder (shared copy) can never disagree on a row.
+constexpr int kMaxProbRows = (3 * kMaxLevels + 1) * 15 + 32;
 
 // Whole-sample symmetric extension: fold an index into [0, n), period 2(n-1).
 // (x[-i] = x[i], x[n-1+i] = x[n-1-i]; DWT/DWTGenerator.cu:148-150,285,290 mirror rule.)

@@ -249,6 +249,18 @@ class Codec:
                                           lens.ctypes.data, C.byref(total)), "pcs_encode_frames", self.ctx)
         return out[: total.value], lens
 
+    def encode_frames_into(self, frames: np.ndarray, first_frame_index: int, out_ptr: int, capacity_words: int):
+        """pcs_encode_frames with a raw destination pointer (host or DEVICE memory, uint16 units) -> (total words,
+        lengths).  The multi-rank path keeps the packed stream in HBM this way until the all-gather of the lengths has
+        told the rank where its bytes go in the concatenated host stream (sharding.ShardedVideo)."""
+        assert frames.dtype == np.uint8 and frames.flags["C_CONTIGUOUS"]
+        n = frames.shape[0]
+        lens = np.zeros(n * self.planes, dtype=np.int32)
+        total = C.c_size_t()
+        _check(self.lib.pcs_encode_frames(self.ctx, frames.ctypes.data, n, first_frame_index, C.c_void_p(out_ptr), capacity_words,
+                                          lens.ctypes.data, C.byref(total)), "pcs_encode_frames", self.ctx)
+        return int(total.value), lens
+
     def decode_frames(self, stream: np.ndarray, lens: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
         stream = np.ascontiguousarray(stream, dtype=np.uint16)
         lens = np.ascontiguousarray(lens, dtype=np.int32)

@@ -42,6 +42,11 @@ enum {
                                   W_a-stride plane" quirk (IO/IOManager.ipp:222-225,332-335) instead of
                                   a proper W x H crop.  Identical whenever W is a multiple of 64. */
 
+#define PCS_F_STILLS 2u        /* the context codes stills although `frames` (a header-only value) is > 0:
+                                  RGB component i is coded with iter = i (Engines/CodingEngine.cu:620,700), so only
+                                  plane 0 carries the header; without the flag frames > 0 means video, where the three
+                                  planes of frame 0 all do (CodingEngine.cu:790,902). */
+
 typedef struct pcs_ctx pcs_ctx;
 
 /* Mirrors the Engine setters (Engines/Engine.cuh:28-44) + Image fields (Image/Image.hpp:52-62). */
@@ -168,7 +173,11 @@ int32_t pcs_export_ref_codestream(pcs_ctx* ctx, const uint16_t* d_codewords, con
 
 /* h_pixels: uint8 [nframes][height][width].  h_stream receives the frames back to back;
  * h_frame_len[f] = length of frame f in uint16 units (the `_SIZE` sidecar values).  Returns the
- * total number of uint16 written through *total_words. */
+ * total number of uint16 written through *total_words.  nframes is not limited by max_batch (the
+ * call pipelines chunks of frames through the workspace).  The pixel and stream pointers of both
+ * calls may also be DEVICE pointers (copies are issued with cudaMemcpyDefault): the multi-rank
+ * path keeps a rank's packed stream in HBM until the all-gather of the lengths has told it where
+ * in the concatenated host stream its bytes go (picsong_b200/sharding.py). */
 int32_t pcs_encode_frames(pcs_ctx* ctx, const uint8_t* h_pixels, int32_t nframes, int32_t first_frame_index,
                           uint16_t* h_stream, size_t capacity_words, int32_t* h_frame_len,
                           size_t* total_words);

@@ -17,7 +17,10 @@
  * removeOffsetAndApplyMaxMin[Lossy] (DecodingEngine.cu:706-729), which the reference defines as
  * file-local kernels; they are elementwise and not part of what is being measured against.
  *
- * usage: ref_harness W H wl type qs LUTFolder/ input.raw frames iters dump_prefix|- [json_out]
+ * usage: ref_harness W H wl type qs LUTFolder/ input.raw frames iters dump_prefix|- [json_out] [coef=plane.i32]
+ *   coef=<file>: coder-only mode (type 0).  The int32 plane in <file> (W_a*H_a values, Mallat layout) is fed to
+ *   BPCCuda<int>::Code in place of the DWT output and the result decoded with ::Decode; dumps <prefix>.stream and
+ *   <prefix>.q (the decoder's int32 plane).  Pins the rare coder branches (expansionFix, planes >= 16).
  */
 #include <chrono>
 #include <cstdio>
@@ -62,7 +65,7 @@ struct Stat { double sum = 0; double best = 1e30; int n = 0; void add(double v) 
 
 template <class T, class Y>
 static int run(int W, int H, int wl, bool lossy, float qs, const std::string& lutFolder, const std::string& input,
-               int frames, int iters, const std::string& prefix, const std::string& jsonOut) {
+               int frames, int iters, const std::string& prefix, const std::string& jsonOut, const std::string& coefFile = "") {
   Image img;
   img.setBitDepth(8); img.setBitsPerSample(8); img.setComponents(1); img.setEndianess(0);
   img.setHeight(H); img.setWidth(W); img.setIsRGB(false); img.setName(input); img.setSignedOrUnsigned(0);
@@ -118,12 +121,18 @@ static int run(int W, int H, int wl, bool lossy, float qs, const std::string& lu
   int bad = 0;
   for (int it = 0; it < iters; ++it) {
     for (int f = 0; f < nf; ++f) {
-      iomc.loadFrameCAdaptedSizes(&img, hPxPin, f); /* host mirror padding, IOManager.ipp:72-112 */
+      if (coefFile.empty()) iomc.loadFrameCAdaptedSizes(&img, hPxPin, f); /* host mirror padding, IOManager.ipp:72-112 */
       auto w0 = std::chrono::steady_clock::now();
       CK(cudaMemcpy(dPx, hPxPin, A, cudaMemcpyHostToDevice));
       CK(cudaEventRecord(e0));
-      h_offset<T><<<(A + 255) / 256, 256>>>(dPx, dIn, A);
-      {
+      if (!coefFile.empty()) { /* coder-only mode: the plane comes from the file */
+        std::vector<int> plane(A);
+        FILE* cf = fopen(coefFile.c_str(), "rb");
+        if (!cf || fread(plane.data(), sizeof(int), A, cf) != (size_t)A) { fprintf(stderr, "cannot read %s\n", coefFile.c_str()); exit(4); }
+        fclose(cf);
+        CK(cudaMemcpy(dCoef, plane.data(), (size_t)A * sizeof(int), cudaMemcpyHostToDevice));
+      } else {
+        h_offset<T><<<(A + 255) / 256, 256>>>(dPx, dIn, A);
         DWT<T, Y> dwt(&img, lossy, wl, 64, 18, qs);
         dwt.DWTEncode(dIn, dCoef, cudaStreamDefault);
       }
@@ -166,6 +175,14 @@ static int run(int W, int H, int wl, bool lossy, float qs, const std::string& lu
                     cudaStreamDefault, 256, dLUTBS, &td);
       }
       CK(cudaEventRecord(e1));
+      if (!coefFile.empty()) {
+        CK(cudaDeviceSynchronize());
+        std::vector<int> qh(A);
+        CK(cudaMemcpy(qh.data(), dQ, (size_t)A * sizeof(int), cudaMemcpyDeviceToHost));
+        if (prefix != "-") dump(prefix + ".q", qh.data(), (size_t)A * sizeof(int));
+        printf("{\"coef_mode\":1,\"stream_words\":%d}\n", total);
+        return 0;
+      }
       {
         DWT<T, Y> dwtd(&img, lossy, wl, 64, 18, qs);
         dwtd.DWTDecode(dQ, dIn, cudaStreamDefault);
@@ -225,8 +242,9 @@ int main(int argc, char** argv) {
   float qs = (float)atof(argv[5]);
   std::string lut = argv[6], input = argv[7];
   int frames = atoi(argv[8]), iters = atoi(argv[9]);
-  std::string prefix = argv[10], jsonOut = argc > 11 ? argv[11] : "";
+  std::string prefix = argv[10], jsonOut = argc > 11 ? argv[11] : "", coefFile;
+  if (argc > 12 && !strncmp(argv[12], "coef=", 5)) coefFile = argv[12] + 5;
   cudaDeviceSetCacheConfig(cudaFuncCachePreferL1); /* Launcher.cu:188 */
   if (type) return run<float, float2>(W, H, wl, true, qs, lut, input, frames, iters, prefix, jsonOut);
-  return run<int, int2>(W, H, wl, false, qs, lut, input, frames, iters, prefix, jsonOut);
+  return run<int, int2>(W, H, wl, false, qs, lut, input, frames, iters, prefix, jsonOut, coefFile);
 }
