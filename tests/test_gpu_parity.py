@@ -221,14 +221,18 @@ def test_full_size_properties(luts):
         dec = cd.decode_frames(stream, lens)[0]
         assert np.array_equal(dec, img)  # encode -> decode round trip is the identity
         cd.close()
-    # config 2 (lossy): stream length within a few words of the reference's, PSNR equal to the reference's
+    # config 2 (lossy, the round-1 headline configuration): byte-identical to the reference binary as well.  The reference is
+    # deterministic on this input (five runs per qs with one sha256 each: tests/golden/ref_runs/cfg2_determinism.json),
+    # and the forward 9/7 is matched bit for bit, so the sha256 of its stream is asserted; decoded pixels: PSNR equal
+    # to the reference's within 0.01 dB (its inverse uses -use_fast_math divisions).
     for name in ("cfg2_4096_wl5_q1", "cfg2_4096_wl5_q05", "cfg2_4096_wl5_q01"):
         e = man[name]
         _, plut = luts(e["lut"], e["wl"])
         cd = codec.Codec(codec.Params(e["W"], e["H"], e["wl"], True, e["qs"]), plut)
         img = synth.synth_frame(e["W"], e["H"])
         stream, lens = cd.encode_frames(img[None])
-        assert abs(stream.size * 2 - e["enc_len"]) <= 64, (name, stream.size * 2, e["enc_len"])
+        assert stream.size * 2 == e["enc_len"], (name, stream.size * 2, e["enc_len"])
+        assert hashlib.sha256(stream.tobytes()).hexdigest() == e["enc_sha256"], name
         dec = cd.decode_frames(stream, lens)[0]
         mse = np.mean((dec.astype(np.float64) - img) ** 2)
         psnr = 10 * np.log10(255.0 ** 2 / mse)

@@ -214,3 +214,28 @@ def test_oracle_rgb_matches_reference_binary(name, golden, lut_root):
             r = golden.decoded(name).reshape(max(F, 1), 3, H, W)[f]
             diff = np.abs(d.astype(np.int32) - r.astype(np.int32))
             assert diff.max() <= 1 and (diff != 0).mean() <= 1e-4
+
+
+def test_oracle_matches_reference_coder_on_rare_branches(lut_root):
+    """Expansion fallback (size 4096) and bit planes >= 16: the oracle's coder + bit-stream builder and its decoder against
+    the reference's own BPCCuda<int>::Code / ::Decode run on the synthetic planes of tests/coef_planes.py
+    (tests/golden/coef_planes.npz, made with `ref_harness ... coef=`, see tests/golden/ref_runs/README.md)."""
+    import os
+
+    import coef_planes
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "coef_planes.npz"))
+    lut = O.lut_load(f"{lut_root}/n1_lossless/", coef_planes.WL)
+    W, H, wl = coef_planes.W, coef_planes.H, coef_planes.WL
+    seen_expansion = seen_high = False
+    for name in coef_planes.CASES:
+        q = coef_planes.plane(name)
+        cs, sz = O.bpc_encode(q, wl, lut)
+        dq = O.bpc_decode(cs, sz, W, H, wl, lut)
+        if f"{name}.stream" not in g:      # every block expands: the reference itself fails on these (ref_runs/README.md)
+            assert (sz == 4096).all()
+            continue
+        assert np.array_equal(O.bsb_pack(cs, sz, O.header_pack(W, H, wl, 0, 1.0, 0)), g[f"{name}.stream"]), name
+        assert np.array_equal(dq, g[f"{name}.q"]), name
+        seen_expansion |= bool((sz == 4096).any())
+        seen_high |= bool(np.abs(q.astype(np.int64)).max() >= 1 << 16 and (sz < 4096).any())
+    assert seen_expansion and seen_high
