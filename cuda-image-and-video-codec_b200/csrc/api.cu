@@ -24,9 +24,8 @@ namespace pcs {
 unsigned long long g_launches = 0;
 
 size_t dwt_scratch_elems(int Wa, int Ha, int wl);
-int dwt_forward(const uint8_t*, void*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t, DwtAux*, void* qws);
-size_t dwt_queue_ws_bytes(int Wa, int Ha, int wl, int frames);
-int dwt_forward_planes(const void*, void*, void*, int, int, int, bool, float, bool, int, cudaStream_t, void* qws);
+int dwt_forward(const uint8_t*, void*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t);
+int dwt_forward_planes(const void*, void*, void*, int, int, int, bool, float, bool, int, cudaStream_t);
 bool dwt_forward_rgb_ok(const uint8_t*, const void*, const void*, int, int, int, int, int);
 int dwt_forward_rgb(const uint8_t*, void*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t);
 int dwt_inverse_planes(const int32_t*, void*, void*, int, int, int, bool, float, int, cudaStream_t);
@@ -34,7 +33,7 @@ int rgb_forward(const uint8_t*, void*, int, int, int, int, bool, int, cudaStream
 int rgb_inverse(const void*, uint8_t*, int, int, int, int, bool, bool, int, cudaStream_t);
 bool dwt_inverse_rgb_ok(const int32_t*, const uint8_t*, const void*, int, int, int, int, int);
 int dwt_inverse_rgb(const int32_t*, uint8_t*, void*, int, int, int, int, int, bool, float, int, cudaStream_t);
-int dwt_inverse(const int32_t*, uint8_t*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t, DwtAux*);
+int dwt_inverse(const int32_t*, uint8_t*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t);
 int bpc_encode(const void*, bool, uint16_t*, int32_t*, const BpcArgs&, cudaStream_t);
 int bpc_decode(const uint16_t*, const int32_t*, int32_t*, const BpcArgs&, cudaStream_t);
 int bpc_encode_k(const void*, bool, uint16_t*, int32_t*, const BpcKArgs&, cudaStream_t);
@@ -77,9 +76,6 @@ struct pcs_ctx {
   size_t status_bytes = 0;
   int32_t* d_lutk = nullptr;       // k > 0: flat tables of all bit-plane files, [ncomp][files][per]
   int lut_files = 1;               // table sets per component in `lut` (1 for k == 0)
-  void* d_dwtq = nullptr;          // [1 + kSlots] work-queue counter areas of the forward DWT
-  size_t dwtq_bytes = 0;
-  DwtAux* aux = nullptr;           // auxiliary streams of the batched DWT calls (device-buffer entry points)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool timing = false;
@@ -168,14 +164,13 @@ int build_prob_tables(pcs_ctx* c) {
 // ---- the stage chain on explicit workspace pointers (used by the device entry points and by the slots) ----
 struct Ws {
   void* scratch; void* status; void* tplanes; int32_t* coeff; uint16_t* cw; int32_t* sizes;
-  void* dwtq;  // counters of the forward DWT's work queue (one area per concurrent call)
 };
 
-int run_dwt_forward(pcs_ctx* c, const Ws& w, const uint8_t* d_px, void* d_coeff, bool out_int, int frames, cudaStream_t st, DwtAux* aux) {
+int run_dwt_forward(pcs_ctx* c, const Ws& w, const uint8_t* d_px, void* d_coeff, bool out_int, int frames, cudaStream_t st) {
   const pcs_params& p = c->p;
   if (c->ncomp == 1)
     return dwt_forward(d_px, d_coeff, w.scratch, p.width, p.height, c->Wa, c->Ha, p.wavelet_levels, p.lossy != 0, p.quant_size, out_int,
-                       frames, st, aux, w.dwtq);
+                       frames, st);
   // colour transform fused into the level-1 load where the streaming kernel applies ...
   static const bool fuse_rgb = [] { const char* e = std::getenv("PCS_RGB_FUSE"); return !e || std::atoi(e) != 0; }();
   if (fuse_rgb && dwt_forward_rgb_ok(d_px, d_coeff, w.scratch, p.width, p.height, c->Wa, c->Ha, p.wavelet_levels))
@@ -185,15 +180,15 @@ int run_dwt_forward(pcs_ctx* c, const Ws& w, const uint8_t* d_px, void* d_coeff,
   int rc = rgb_forward(d_px, w.tplanes, p.width, p.height, c->Wa, c->Ha, p.lossy != 0, frames, st);
   if (rc) return rc;
   return dwt_forward_planes(w.tplanes, d_coeff, w.scratch, c->Wa, c->Ha, p.wavelet_levels, p.lossy != 0, p.quant_size, out_int,
-                            frames * 3, st, w.dwtq);
+                            frames * 3, st);
 }
 
-int run_dwt_inverse(pcs_ctx* c, const Ws& w, const int32_t* d_q, uint8_t* d_px, int frames, cudaStream_t st, DwtAux* aux) {
+int run_dwt_inverse(pcs_ctx* c, const Ws& w, const int32_t* d_q, uint8_t* d_px, int frames, cudaStream_t st) {
   const pcs_params& p = c->p;
   const bool flat = (p.flags & PCS_F_REF_FLAT_CROP) != 0;
   if (c->ncomp == 1)
     return dwt_inverse(d_q, d_px, w.scratch, p.width, p.height, c->Wa, c->Ha, p.wavelet_levels, p.lossy != 0, p.quant_size, flat, frames,
-                       st, aux);
+                       st);
   static const bool fuse_rgb = [] { const char* e = std::getenv("PCS_RGB_FUSE"); return !e || std::atoi(e) != 0; }();
   if (fuse_rgb && dwt_inverse_rgb_ok(d_q, d_px, w.scratch, p.width, p.height, c->Wa, c->Ha, p.wavelet_levels))
     return dwt_inverse_rgb(d_q, d_px, w.scratch, p.width, p.height, c->Wa, c->Ha, p.wavelet_levels, p.lossy != 0, p.quant_size, frames * 3,
@@ -302,12 +297,9 @@ int32_t pcs_create(const pcs_params* params, pcs_ctx** out) {
   alloc((void**)&c->d_off, (PL + 1) * sizeof(long long));
   c->status_bytes = (bsb_status_bytes(c->ncb, (int)PL) + 255) / 256 * 256;
   alloc(&c->d_sstatus, pcs_ctx::kSlots * c->status_bytes);
-  c->dwtq_bytes = (dwt_queue_ws_bytes(Wa, Ha, p.wavelet_levels, (int)PL) + 255) / 256 * 256;
-  alloc(&c->d_dwtq, (1 + pcs_ctx::kSlots) * c->dwtq_bytes);
   alloc((void**)&c->d_soff, pcs_ctx::kSlots * (PL + 1) * sizeof(long long));
   if (e == cudaSuccess) e = cudaHostAlloc((void**)&c->h_off, pcs_ctx::kSlots * (PL + 1) * sizeof(long long), cudaHostAllocDefault);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) { c->aux = dwt_aux_create(); if (!c->aux) e = cudaErrorMemoryAllocation; }
   for (int i = 0; i < pcs_ctx::kSlots && e == cudaSuccess; ++i) {
     e = cudaStreamCreateWithFlags(&c->sstream[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->sev[i], cudaEventDisableTiming);
@@ -325,11 +317,10 @@ void pcs_destroy(pcs_ctx* c) {
   cudaFree(c->d_scratch); cudaFree(c->d_status); cudaFree(c->d_px); cudaFree(c->d_tplanes); cudaFree(c->d_coeff); cudaFree(c->d_cw);
   cudaFree(c->d_sizes); cudaFree(c->d_stream); cudaFree(c->d_off);
   if (c->h_off) cudaFreeHost(c->h_off);
-  cudaFree(c->d_sstatus); cudaFree(c->d_soff); cudaFree(c->d_dwtq); cudaFree(c->d_lutk);
+  cudaFree(c->d_sstatus); cudaFree(c->d_soff); cudaFree(c->d_lutk);
   for (auto& s2 : c->sstream) if (s2) cudaStreamDestroy(s2);
   for (auto& e2 : c->sev) if (e2) cudaEventDestroy(e2);
   for (auto& e2 : c->kev) if (e2) cudaEventDestroy(e2);
-  dwt_aux_destroy(c->aux);
   if (c->stream) cudaStreamDestroy(c->stream);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   delete c;
@@ -354,16 +345,16 @@ uint64_t pcs_kernel_launch_count(void) { return g_launches; }
 #define CHECK_BATCH(c, batch) \
   if (!(c)) return PCS_E_ARG; \
   if ((batch) < 1 || (batch) > (c)->p.max_batch) return fail((c), PCS_E_BATCH, "batch exceeds max_batch")
-#define FULL_WS(c) Ws{(c)->d_scratch, (c)->d_status, (c)->d_tplanes, (c)->d_coeff, (c)->d_cw, (c)->d_sizes, (c)->d_dwtq}
+#define FULL_WS(c) Ws{(c)->d_scratch, (c)->d_status, (c)->d_tplanes, (c)->d_coeff, (c)->d_cw, (c)->d_sizes}
 
 int32_t pcs_dwt_forward(pcs_ctx* c, const uint8_t* d_px, void* d_coeff, int32_t trunc, int32_t batch, void* st) {
   CHECK_BATCH(c, batch);
-  return run_dwt_forward(c, FULL_WS(c), d_px, d_coeff, trunc != 0, batch, (cudaStream_t)st, c->aux);
+  return run_dwt_forward(c, FULL_WS(c), d_px, d_coeff, trunc != 0, batch, (cudaStream_t)st);
 }
 
 int32_t pcs_dwt_inverse(pcs_ctx* c, const int32_t* d_q, uint8_t* d_px, int32_t batch, void* st) {
   CHECK_BATCH(c, batch);
-  return run_dwt_inverse(c, FULL_WS(c), d_q, d_px, batch, (cudaStream_t)st, c->aux);
+  return run_dwt_inverse(c, FULL_WS(c), d_q, d_px, batch, (cudaStream_t)st);
 }
 
 int32_t pcs_bpc_encode(pcs_ctx* c, const void* d_coeff, int32_t is_float, uint16_t* d_cw, int32_t* d_sizes, int32_t batch, void* st) {
@@ -442,7 +433,6 @@ Slot make_slot(pcs_ctx* c, int k, int sb) {
   Slot s;
   s.w.scratch = static_cast<char*>(c->d_scratch) + p0 * c->scratch_elems * 4;
   s.w.status = static_cast<char*>(c->d_sstatus) + (size_t)k * c->status_bytes;
-  s.w.dwtq = static_cast<char*>(c->d_dwtq) + (size_t)(1 + k) * c->dwtq_bytes;
   s.w.tplanes = c->d_tplanes ? static_cast<char*>(c->d_tplanes) + p0 * c->A * 4 : nullptr;
   s.w.coeff = c->d_coeff + p0 * c->A;
   s.w.cw = c->d_cw + p0 * c->A;
@@ -550,7 +540,7 @@ int32_t pcs_encode_frames(pcs_ctx* c, const uint8_t* h_px, int32_t nframes, int3
     const int f0 = plan[i].f0, b = plan[i].b;
     PCS_CUDA_TRY(cudaMemcpyAsync(s.px, h_px + (size_t)f0 * fpx, (size_t)b * fpx, cudaMemcpyDefault, s.st));
     if (i >= depth && depth < nslots) PCS_CUDA_TRY(cudaStreamWaitEvent(s.st, c->kev[(i - depth) % nslots], 0));
-    int rc = run_dwt_forward(c, s.w, s.px, s.w.coeff, true, b, s.st, nullptr);
+    int rc = run_dwt_forward(c, s.w, s.px, s.w.coeff, true, b, s.st);
     if (rc) return rc;
     rc = run_bpc_encode(c, s.w.coeff, false, s.w.cw, s.w.sizes, b, s.st);
     if (rc) return rc;
@@ -598,7 +588,7 @@ int32_t pcs_decode_frames(pcs_ctx* c, const uint16_t* h_stream, const int32_t* h
     if (rc) return rc;
     rc = run_bpc_decode(c, s.w.cw, s.w.sizes, s.w.coeff, b, s.st);
     if (rc) return rc;
-    rc = run_dwt_inverse(c, s.w, s.w.coeff, s.px, b, s.st, nullptr);
+    rc = run_dwt_inverse(c, s.w, s.w.coeff, s.px, b, s.st);
     if (rc) return rc;
     PCS_CUDA_TRY(cudaEventRecord(c->kev[i % nslots], s.st));
     PCS_CUDA_TRY(cudaMemcpyAsync(h_px + (size_t)f0 * fpx, s.px, (size_t)b * fpx, cudaMemcpyDefault, s.st));

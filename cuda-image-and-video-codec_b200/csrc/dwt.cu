@@ -533,16 +533,18 @@ int dwt_forward_fast(const void*, bool, long long, int, int, int, int, void*, lo
 bool dwt_inverse_fast_ok(const void*, const void*, const void*, bool, int, long long, int, long long, int, int);
 int dwt_inverse_fast(const int32_t*, long long, int, const void*, long long, int, bool, int, int, void*, bool, long long, int, int, int, bool,
                      float, int, cudaStream_t, bool rgb, long long comp_stride);
-int dwt_forward_queue(const void*, bool, int, int, int, int, void*, void*, int, bool, float, bool, int, void*, cudaStream_t, int*);
 
-// PCS_DWT_FUSE = 0: per-level kernels of this file only; 1: streaming kernel of dwt_fast.cu, one level per launch
-// (default); 2: the same with levels 1+2 fused in one launch
+bool dwt_forward_l12_ok(const void*, const void*, const void*, int, int, int, int, int);
+int dwt_forward_l12(const uint8_t*, int, int, int, int, void*, long long, void*, long long, int, bool, float, bool, int, cudaStream_t);
+
+// PCS_DWT_FUSE = 0: per-level kernels of this file only; 1: streaming kernels of dwt_fast.cu, one level per launch;
+// 2 (default): levels 1+2 of u8 frames in one launch (dwt_fused.cu), the deeper levels through the streaming kernels
 static int fuse_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("PCS_DWT_FUSE");
-    mode = e ? atoi(e) : 1;
-    if (mode < 0 || mode > 2) mode = 1;
+    mode = e ? atoi(e) : 2;
+    if (mode < 0 || mode > 2) mode = 2;
   }
   return mode;
 }
@@ -557,19 +559,25 @@ static int dwt_forward_levels(const uint8_t* d_px, void* d_coeff, void* d_scratc
                               const void* tplane = nullptr, bool rgb_px = false) {
   const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl);
   int first = lfirst;
-  // leading levels through the streaming kernel of dwt_fast.cu while the geometry allows it
+  // levels 1+2 of u8 frames in one launch: the LL1 plane stays on chip (dwt_fused.cu)
+  if (fuse_mode() == 2 && first == 1 && llast >= 2 && !tplane && !rgb_px && S % 4 == 0) {
+    void* ll2 = wl == 2 ? nullptr : static_cast<char*>(d_scratch) + ll_offset(Wa, Ha, 2) * 4;
+    if (dwt_forward_l12_ok(d_px, d_coeff, ll2, W, H, Wa, Ha, wl)) {
+      int rc = dwt_forward_l12(d_px, W, H, Wa, Ha, d_coeff, (long long)A, ll2, (long long)S, wl, lossy, qs, out_int, frames, st);
+      if (rc) return rc;
+      first = 3;
+    }
+  }
+  // (remaining) leading levels through the streaming kernel of dwt_fast.cu while the geometry allows it
   while (fuse_mode() > 0 && first <= llast) {
     const int l = first, Wc = Wa >> (l - 1), Hc = Ha >> (l - 1);
     const bool u8 = l == 1 && !tplane;
     const void* src = u8 ? static_cast<const void*>(d_px) : l == 1 ? tplane : static_cast<const char*>(d_scratch) + ll_offset(Wa, Ha, l - 1) * 4;
     const long long sfs = u8 ? (long long)W * H * (rgb_px ? 3 : 1) : l == 1 ? (long long)A : (long long)S;
     const int sp = u8 ? W : Wc;
-    int lv = (u8 && !rgb_px && fuse_mode() == 2 && llast >= 2) ? 2 : 1;
-    void* ll = (l + lv - 1 == wl) ? nullptr : static_cast<char*>(d_scratch) + ll_offset(Wa, Ha, l + lv - 1) * 4;
-    if (!dwt_forward_fast_ok(src, d_coeff, ll, u8, sp, sfs, H, Wc, Hc, lv)) {
-      if (lv == 2) { lv = 1; ll = (l == wl) ? nullptr : static_cast<char*>(d_scratch) + ll_offset(Wa, Ha, l) * 4; }
-      if (!dwt_forward_fast_ok(src, d_coeff, ll, u8, sp, sfs, H, Wc, Hc, lv)) break;
-    }
+    const int lv = 1;
+    void* ll = (l == wl) ? nullptr : static_cast<char*>(d_scratch) + ll_offset(Wa, Ha, l) * 4;
+    if (!dwt_forward_fast_ok(src, d_coeff, ll, u8, sp, sfs, H, Wc, Hc, lv)) break;
     if (S % 4) break;
     int rc = dwt_forward_fast(src, u8, sfs, sp, H, Wc, Hc, d_coeff, (long long)A, Wa, ll, (long long)S, Wa >> (l + lv - 1), l, lv, wl, lossy,
                               qs, out_int, frames, st, u8 && rgb_px, (long long)W * H);
@@ -676,130 +684,19 @@ static int dwt_inverse_levels(const int32_t* d_q, uint8_t* d_px, void* d_scratch
 
 
 // ---------------------------------------------------------------------------------------------
-// Batch drivers.  Level 1 moves 5 of the ~7 bytes per pixel; the deeper levels are small, latency-bound
-// launches.  With a batch of frames the two are overlapped: the batch is cut into groups of `gf` frames,
-// level 1 of group g runs on one auxiliary stream while levels 2..wl of group g-1 run on the other (and
-// find the LL planes group g-1 just wrote still in L2).  The caller's stream forks into / joins from the
-// two auxiliary streams with events; nothing synchronises the host.
+// Batch drivers: all frames of a call go through each launch together (one launch per level, or one launch for
+// levels 1+2 where the fused kernel of dwt_fused.cu applies); nothing synchronises the host.
 // ---------------------------------------------------------------------------------------------
-DwtAux* dwt_aux_create() {
-  DwtAux* x = new DwtAux();
-  bool ok = cudaStreamCreateWithFlags(&x->a, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaStreamCreateWithFlags(&x->b, cudaStreamNonBlocking) == cudaSuccess;
-  for (auto& e : x->ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
-  if (!ok) { dwt_aux_destroy(x); return nullptr; }
-  return x;
-}
-void dwt_aux_destroy(DwtAux* x) {
-  if (!x) return;
-  if (x->a) cudaStreamDestroy(x->a);
-  if (x->b) cudaStreamDestroy(x->b);
-  for (auto& e : x->ev) if (e) cudaEventDestroy(e);
-  delete x;
-}
-// Frames per sub-batch such that their LL1 planes (A/4 32-bit samples each) fit the part of the 126 MB L2 we
-// ask it to keep (PCS_DWT_L2_MB; default 0 = off: splitting the launches was measured to cost more than the L2 hits
-// gain, 0.240 vs 0.226 ms for 8 frames of 4096^2).
-static int l2_sub_batch(int Wa, int Ha, int frames, int wl) {
-  static long long mb = -1;
-  if (mb < 0) { const char* e = getenv("PCS_DWT_L2_MB"); mb = e ? atoll(e) : 0; }
-  if (wl < 2 || mb <= 0) return frames;
-  const long long ll1 = (long long)Wa * Ha;  // bytes of one frame's LL1 plane
-  return (int)std::max<long long>(1, std::min<long long>(frames, (mb << 20) / ll1));
-}
-static int group_frames(int frames, int wl) {  // PCS_DWT_GROUP: frames per group; default 0 = off (measured slower)
-  static int g = -1;
-  if (g < 0) { const char* e = getenv("PCS_DWT_GROUP"); g = e ? atoi(e) : 0; if (g < 0) g = 0; }
-  if (g == 0 || wl < 2 || frames < 2 * g) return 0;
-  return (frames + g - 1) / g <= DwtAux::kMaxGroups ? g : (frames + DwtAux::kMaxGroups - 1) / DwtAux::kMaxGroups;
-}
-
 int dwt_forward(const uint8_t* d_px, void* d_coeff, void* d_scratch, int W, int H, int Wa, int Ha, int wl, bool lossy, float qs,
-                bool out_int, int frames, cudaStream_t st, DwtAux* aux, void* qws) {
-  if (qws) {  // all levels the streaming kernel can take in one persistent launch (dwt_fast.cu), the rest level by level
-    int done = 0;
-    const int rc = dwt_forward_queue(d_px, true, W, H, Wa, Ha, d_coeff, d_scratch, wl, lossy, qs, out_int, frames, qws, st, &done);
-    if (rc || done == wl) return rc;
-    if (done > 0) return dwt_forward_levels(d_px, d_coeff, d_scratch, W, H, Wa, Ha, wl, lossy, qs, out_int, frames, done + 1, wl, st);
-  }
-  const int gf = aux ? group_frames(frames, wl) : 0;
-  if (!gf) {
-    // Levels 1 and 2 go sub-batch by sub-batch so that the LL1 planes level 1 writes (evict-last) are still in
-    // L2 when level 2 reads them; the remaining levels (LL2 and below are small) run over the whole batch.
-    const int sb = l2_sub_batch(Wa, Ha, frames, wl);
-    if (sb >= frames) return dwt_forward_levels(d_px, d_coeff, d_scratch, W, H, Wa, Ha, wl, lossy, qs, out_int, frames, 1, wl, st);
-    const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl), P = (size_t)W * H;
-    for (int f0 = 0; f0 < frames; f0 += sb) {
-      const int n = std::min(sb, frames - f0);
-      int rc = dwt_forward_levels(d_px + f0 * P, static_cast<char*>(d_coeff) + f0 * A * 4, static_cast<char*>(d_scratch) + f0 * S * 4, W, H,
-                                  Wa, Ha, wl, lossy, qs, out_int, n, 1, 2, st);
-      if (rc) return rc;
-    }
-    return wl > 2 ? dwt_forward_levels(d_px, d_coeff, d_scratch, W, H, Wa, Ha, wl, lossy, qs, out_int, frames, 3, wl, st) : 0;
-  }
-  const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl), P = (size_t)W * H;
-  const int ng = (frames + gf - 1) / gf;
-  PCS_CUDA_TRY(cudaEventRecord(aux->ev[0], st));
-  PCS_CUDA_TRY(cudaStreamWaitEvent(aux->a, aux->ev[0], 0));
-  PCS_CUDA_TRY(cudaStreamWaitEvent(aux->b, aux->ev[0], 0));
-  for (int g = 0; g < ng; ++g) {
-    const int f0 = g * gf, n = std::min(gf, frames - f0);
-    const uint8_t* px = d_px + f0 * P;
-    void* co = static_cast<char*>(d_coeff) + f0 * A * 4;
-    void* sc = static_cast<char*>(d_scratch) + f0 * S * 4;
-    int rc = dwt_forward_levels(px, co, sc, W, H, Wa, Ha, wl, lossy, qs, out_int, n, 1, 1, aux->a);
-    if (rc) return rc;
-    PCS_CUDA_TRY(cudaEventRecord(aux->ev[3 + g], aux->a));
-    PCS_CUDA_TRY(cudaStreamWaitEvent(aux->b, aux->ev[3 + g], 0));
-    rc = dwt_forward_levels(px, co, sc, W, H, Wa, Ha, wl, lossy, qs, out_int, n, 2, wl, aux->b);
-    if (rc) return rc;
-  }
-  PCS_CUDA_TRY(cudaEventRecord(aux->ev[1], aux->a));
-  PCS_CUDA_TRY(cudaEventRecord(aux->ev[2], aux->b));
-  PCS_CUDA_TRY(cudaStreamWaitEvent(st, aux->ev[1], 0));
-  PCS_CUDA_TRY(cudaStreamWaitEvent(st, aux->ev[2], 0));
-  return (int)cudaGetLastError();
+                bool out_int, int frames, cudaStream_t st) {
+  return dwt_forward_levels(d_px, d_coeff, d_scratch, W, H, Wa, Ha, wl, lossy, qs, out_int, frames, 1, wl, st);
 }
 
 int dwt_inverse(const int32_t* d_q, uint8_t* d_px, void* d_scratch, int W, int H, int Wa, int Ha, int wl, bool lossy, float qs,
-                bool flat_crop, int frames, cudaStream_t st, DwtAux* aux) {
-  const int gf = aux ? group_frames(frames, wl) : 0;
-  if (!gf) {
-    const int sb = l2_sub_batch(Wa, Ha, frames, wl);
-    if (sb >= frames) return dwt_inverse_levels(d_q, d_px, d_scratch, W, H, Wa, Ha, wl, lossy, qs, flat_crop, frames, wl, 1, st);
-    const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl), P = (size_t)W * H;
-    if (wl > 2) { int rc = dwt_inverse_levels(d_q, d_px, d_scratch, W, H, Wa, Ha, wl, lossy, qs, flat_crop, frames, wl, 3, st); if (rc) return rc; }
-    for (int f0 = 0; f0 < frames; f0 += sb) {  // level 2 writes LL1 (evict-last), level 1 reads it while it is still in L2
-      const int n = std::min(sb, frames - f0);
-      int rc = dwt_inverse_levels(d_q + f0 * A, d_px + f0 * P, static_cast<char*>(d_scratch) + f0 * S * 4, W, H, Wa, Ha, wl, lossy, qs,
-                                  flat_crop, n, 2, 1, st);
-      if (rc) return rc;
-    }
-    return 0;
-  }
-  const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl), P = (size_t)W * H;
-  const int ng = (frames + gf - 1) / gf;
-  PCS_CUDA_TRY(cudaEventRecord(aux->ev[0], st));
-  PCS_CUDA_TRY(cudaStreamWaitEvent(aux->a, aux->ev[0], 0));
-  PCS_CUDA_TRY(cudaStreamWaitEvent(aux->b, aux->ev[0], 0));
-  for (int g = 0; g < ng; ++g) {
-    const int f0 = g * gf, n = std::min(gf, frames - f0);
-    const int32_t* q = d_q + f0 * A;
-    uint8_t* px = d_px + f0 * P;
-    void* sc = static_cast<char*>(d_scratch) + f0 * S * 4;
-    int rc = dwt_inverse_levels(q, px, sc, W, H, Wa, Ha, wl, lossy, qs, flat_crop, n, wl, 2, aux->b);  // coarse levels
-    if (rc) return rc;
-    PCS_CUDA_TRY(cudaEventRecord(aux->ev[3 + g], aux->b));
-    PCS_CUDA_TRY(cudaStreamWaitEvent(aux->a, aux->ev[3 + g], 0));
-    rc = dwt_inverse_levels(q, px, sc, W, H, Wa, Ha, wl, lossy, qs, flat_crop, n, 1, 1, aux->a);        // finest level
-    if (rc) return rc;
-  }
-  PCS_CUDA_TRY(cudaEventRecord(aux->ev[1], aux->a));
-  PCS_CUDA_TRY(cudaEventRecord(aux->ev[2], aux->b));
-  PCS_CUDA_TRY(cudaStreamWaitEvent(st, aux->ev[1], 0));
-  PCS_CUDA_TRY(cudaStreamWaitEvent(st, aux->ev[2], 0));
-  return (int)cudaGetLastError();
+                bool flat_crop, int frames, cudaStream_t st) {
+  return dwt_inverse_levels(d_q, d_px, d_scratch, W, H, Wa, Ha, wl, lossy, qs, flat_crop, frames, wl, 1, st);
 }
+
 
 // RGB path, forward, colour transform fused into the level-1 load: possible when the streaming kernel takes level 1
 // of this geometry (no horizontal padding, 8-byte aligned colour planes).
@@ -816,13 +713,7 @@ int dwt_forward_rgb(const uint8_t* d_px, void* d_coeff, void* d_scratch, int W, 
 
 // RGB path: the same transforms on colour-transformed 32-bit planes (`planes` = frames x 3 components).
 int dwt_forward_planes(const void* d_tplanes, void* d_coeff, void* d_scratch, int Wa, int Ha, int wl, bool lossy, float qs, bool out_int,
-                       int planes, cudaStream_t st, void* qws) {
-  if (qws) {
-    int done = 0;
-    const int rc = dwt_forward_queue(d_tplanes, false, Wa, Ha, Wa, Ha, d_coeff, d_scratch, wl, lossy, qs, out_int, planes, qws, st, &done);
-    if (rc || done == wl) return rc;
-    if (done > 0) return dwt_forward_levels(nullptr, d_coeff, d_scratch, Wa, Ha, Wa, Ha, wl, lossy, qs, out_int, planes, done + 1, wl, st, d_tplanes);
-  }
+                       int planes, cudaStream_t st) {
   return dwt_forward_levels(nullptr, d_coeff, d_scratch, Wa, Ha, Wa, Ha, wl, lossy, qs, out_int, planes, 1, wl, st, d_tplanes);
 }
 // RGB path, inverse, colour transform fused into the level-1 store: possible when the streaming kernel produces level 1

@@ -57,16 +57,6 @@ struct BsbArgs {
   unsigned short hdr[9];
 };
 
-// Auxiliary streams / events with which a batched DWT call overlaps its level-1 launches with the
-// deeper levels of the previous group of frames (dwt.cu, "Batch drivers").
-struct DwtAux {
-  static constexpr int kMaxGroups = 16;
-  cudaStream_t a = nullptr, b = nullptr;
-  cudaEvent_t ev[3 + kMaxGroups] = {};
-};
-DwtAux* dwt_aux_create();
-void dwt_aux_destroy(DwtAux*);
-
 }  // namespace pcs
 
 #define PCS_CUDA_TRY(expr)                     \

@@ -18,13 +18,14 @@ import bench
 from picsong_b200 import codec
 
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
-W, H, wl, lossy, qs, lutname, B, desc = bench.WORKLOADS[name]
+cfg = bench.WORKLOADS[name]
+W, H, wl, lossy, qs, lutname, B, desc = cfg['W'], cfg['H'], cfg['wl'], cfg['lossy'], cfg['qs'], cfg['lut'], cfg['batch'], cfg['desc']
 if len(sys.argv) > 2:
     B = int(sys.argv[2])
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 20
 lroot = bench.materialize_luts()
 cd = codec.Codec(codec.Params(W, H, wl, bool(lossy), qs, max_batch=B), codec.load_lut(f"{lroot}/{lutname}/", wl))
-px = torch.from_numpy(bench.make_frames(W, H, B)).cuda()
+px = bench.gen_frames(cfg, range(B), torch.device('cuda'))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
 

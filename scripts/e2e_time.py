@@ -7,11 +7,13 @@ import numpy as np, torch
 import bench
 from picsong_b200 import codec
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
-W, H, wl, lossy, qs, lutname, B, desc = bench.WORKLOADS[name]
+cfg = bench.WORKLOADS[name]
+W, H, wl, lossy, qs, lutname, B, desc = cfg['W'], cfg['H'], cfg['wl'], cfg['lossy'], cfg['qs'], cfg['lut'], cfg['batch'], cfg['desc']
 if len(sys.argv) > 2: B = int(sys.argv[2])
 lroot = bench.materialize_luts()
 cd = codec.Codec(codec.Params(W, H, wl, bool(lossy), qs, max_batch=B), codec.load_lut(f"{lroot}/{lutname}/", wl))
-fr = bench.make_frames(W, H, B)
+import torch
+fr = bench.gen_frames(cfg, range(B), torch.device('cuda')).cpu().numpy()
 pin_px = torch.from_numpy(fr).pin_memory(); pin_out = torch.empty_like(pin_px).pin_memory()
 pin_stream = torch.empty(B * cd.max_words, dtype=torch.int16).pin_memory()
 hp, ho, hs = pin_px.numpy(), pin_out.numpy(), pin_stream.numpy().view(np.uint16)

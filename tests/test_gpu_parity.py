@@ -358,16 +358,19 @@ def test_decoder_survives_malformed_streams(luts):
     cd.close()
 
 
-_QUEUE_SNIPPET = r"""
+_FUSE_SNIPPET = r"""
 import hashlib, sys
 sys.path[:0] = [{root!r}, {pkg!r}]
+import numpy as np
 import torch
 from picsong_b200 import codec, synth
 out = []
-for (W, H, wl, lossy, B) in [(512, 384, 3, 0, 3), (1024, 512, 4, 1, 2), (256, 192, 2, 1, 1), (768, 320, 5, 0, 2)]:
+# W, H, wl, lossy, qs, frames: several CTAs across (W > 928), partial last CTA, padded heights, wl == 2 (LL2 is final), 5/3 and 9/7
+for (W, H, wl, lossy, qs, B) in [(512, 384, 3, 0, 1.0, 3), (1024, 512, 4, 1, 1.0, 2), (256, 192, 2, 1, 0.5, 1), (768, 320, 5, 0, 1.0, 2),
+                                 (1984, 200, 2, 0, 1.0, 1), (3840, 1100, 5, 1, 1.0, 1), (2048, 2048, 5, 1, 0.3, 1), (960, 1000, 3, 0, 1.0, 2),
+                                 (4096, 640, 5, 1, 1.0, 2), (64, 64, 2, 1, 1.0, 1), (128, 4096, 3, 0, 1.0, 1)]:
     folder = "video_lossy" if lossy else "video_lossless"
-    cd = codec.Codec(codec.Params(W, H, wl, bool(lossy), 1.0, max_batch=B), codec.load_lut({lut_root!r} + "/" + folder + "/", wl))
-    import numpy as np
+    cd = codec.Codec(codec.Params(W, H, wl, bool(lossy), qs, max_batch=B), codec.load_lut({lut_root!r} + "/" + folder + "/", wl))
     px = torch.from_numpy(np.stack([synth.synth_frame(W, H, f) for f in range(B)])).cuda()
     for trunc in (True, False):
         c = cd.dwt_forward(px, trunc_to_int=trunc)
@@ -378,21 +381,24 @@ print("HASHES " + " ".join(out))
 """
 
 
-def test_forward_dwt_work_queue_matches_per_level_launches(lut_root):
-    """PCS_DWT_QUEUE=1 (all levels in one persistent launch, dwt_fast.cu) is off by default; it must stay
-    bit-identical to the per-level launches.  The switch is read once per process, hence the subprocesses."""
+def test_fused_levels_match_per_level_launches(lut_root):
+    """Levels 1+2 in one launch (dwt_fused.cu: LL1 handed from producer to consumer warps through shared memory, TMA row
+    loads; the default) against one launch per level (PCS_DWT_FUSE=1): same coefficients bit for bit, also with short
+    chunks (PCS_FUSED_RP) so that chunk seams and the LL1 ring wrap many times.  The switches are read once per
+    process, hence the subprocesses."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = _QUEUE_SNIPPET.format(root=root, pkg=os.path.join(root, "cuda-image-and-video-codec_b200"), lut_root=str(lut_root))
+    code = _FUSE_SNIPPET.format(root=root, pkg=os.path.join(root, "cuda-image-and-video-codec_b200"), lut_root=str(lut_root))
     res = {}
-    for mode in ("0", "1"):
-        env = dict(os.environ, PCS_DWT_QUEUE=mode, PCS_DWTQ_MIN_MPIX="0")
-        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    for name, extra in (("per_level", {"PCS_DWT_FUSE": "1"}), ("fused", {}), ("fused_rp4", {"PCS_FUSED_RP": "4"}), ("fused_rp20", {"PCS_FUSED_RP": "20"})):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **extra), capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
-        res[mode] = [ln for ln in r.stdout.splitlines() if ln.startswith("HASHES ")][0]
-    assert res["0"] == res["1"]
+        res[name] = [ln for ln in r.stdout.splitlines() if ln.startswith("HASHES ")][0].split()
+    for name in ("fused", "fused_rp4", "fused_rp20"):
+        bad = [i for i, (x, y) in enumerate(zip(res["per_level"], res[name])) if x != y]
+        assert not bad, (name, bad)
 
 
 _PIPE_SNIPPET = r"""
