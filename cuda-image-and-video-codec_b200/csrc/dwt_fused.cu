@@ -9,7 +9,7 @@
 // Why: per-level launches move 7.4 B/px (the 4 B/px LL1 plane is written by level 1 and read back by level 2) where the
 // transform needs 5 B/px; both launches already run at ~86 % of the HBM peak, so only removing that round trip helps.
 //
-// Design (one CTA = 6 warps, a column strip of 928 pixels x a chunk of rows, streaming downwards):
+// Design (one CTA = 6 warps, a column strip of 912 pixels x a chunk of rows, streaming downwards):
 //   * warps 0-3, "producers": level 1.  A warp owns 256 pixel columns (8 per lane, lanes 0 / 31 are halo), keeps the
 //     vertical lifting state in registers and does the horizontal lifting with four shuffles per row pair -- the
 //     pipeline of dwt_fast.cu.  Its pixel rows arrive through a private ring of TMA tile loads
@@ -22,8 +22,9 @@
 //     lane).  Rows are handed over with mbarriers (producers arrive on ll_full[slot], consumers on ll_empty[slot]);
 //     there is no CTA-wide barrier in the loop.  HL2 / LH2 / HH2 go to the Mallat plane, LL2 to the scratch plane the
 //     per-level kernels continue from (or, quantised, to the Mallat plane when wl == 2).
-//   * CTA pitch 928 = 2 x 464 LL1 columns: producers deliver 4 x 120 = 480 valid LL1 columns, the consumers' 9/7
-//     lifting needs 8 of them as halo on either side.  At the right image edge only the warps that have columns run.
+//   * CTA pitch 912 = 2 x 456 LL1 columns: producers deliver 4 x 120 = 480 valid LL1 columns, the consumers' halo lanes
+//     take 8 on either side, and 912 keeps every TMA box start a multiple of 16 bytes (the unit rejects anything else).
+//     At the right image edge only the warps that have columns run.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -35,10 +36,10 @@ namespace pcs {
 namespace {
 
 constexpr int kProd = 4, kCons = 2, kThreads = 32 * (kProd + kCons);
-constexpr int kPitchLL = 464, kPitch = 2 * kPitchLL;  // effective LL1 / pixel columns per CTA
-constexpr int kDepth = 6;                             // steps (row pairs) a producer's TMA ring runs ahead
+constexpr int kPitchLL = 456, kPitch = 2 * kPitchLL;  // LL1 / pixel columns a CTA owns (912 = 16 * 57: TMA boxes start 16-byte aligned)
+constexpr int kStages = 4;                            // two-step stages (4 rows x 256 B) a producer's TMA ring runs ahead
 constexpr int kLLSlots = 8;                           // LL1 rows in the hand-over ring
-constexpr int kLLRow = 512;                           // 32-bit words per ring row (480 written, 496 read)
+constexpr int kLLRow = 512;                           // 32-bit words per ring row (480 written, 500 read)
 
 struct FusedArgs {
   const unsigned char* src; long long src_fstride; int src_pitch;  // u8 frames (for the one row each chunk starts from)
@@ -74,9 +75,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "}" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
-// one 256-byte row box of the u8 frames (x, y, frame) -> shared memory; `dep` ties the issue to data the warp has read
+// one box of the u8 frames at (x, y, frame) -> shared memory (256 columns x 4 rows or x 1 row, says the tensor map); `dep` ties the issue to data the warp has read
 // out of that very slot (the slot is private to the warp, so program order is the only hand-back it needs)
-__device__ __forceinline__ void tma_load_row(void* dst, const CUtensorMap* tmap, int x, int y, int z, unsigned long long* bar, unsigned dep) {
+__device__ __forceinline__ void tma_load_rows(void* dst, const CUtensorMap* tmap, int x, int y, int z, unsigned long long* bar, unsigned dep) {
   asm volatile(
       "{\n\t"
       ".reg .b32 t;\n\t"
@@ -101,25 +102,29 @@ __device__ __forceinline__ void lds8(const void* p, int (&v)[8]) {
 #ifndef PCS_FUSED_MINB
 #define PCS_FUSED_MINB 3
 #endif
+// tmap4: u8 frames with a 256 x 4 box (the four rows of a two-step stage in one copy); tmap1: 256 x 1 box, used row by
+// row where the rows of a stage are not four consecutive rows of the frame (mirror folds at the top / bottom / padding).
 template <bool LOSSY, typename OT, bool QS1>
-__global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kernel(const __grid_constant__ CUtensorMap tmap, const FusedArgs a) {
+__global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kernel(const __grid_constant__ CUtensorMap tmap4,
+                                                                                  const __grid_constant__ CUtensorMap tmap1, const FusedArgs a) {
   using T = typename VSel<LOSSY, 8>::T;
   using VP = typename VSel<LOSSY, 8>::type;
-  __shared__ __align__(128) unsigned char s_in[kProd][kDepth][2][256];
+  __shared__ __align__(128) unsigned char s_in[kProd][kStages][4][256];
   __shared__ __align__(16) unsigned s_ll[kLLSlots][kLLRow];
-  __shared__ __align__(8) unsigned long long s_full[kProd][kDepth], s_llfull[kLLSlots], s_llempty[kLLSlots];
+  __shared__ __align__(8) unsigned long long s_full[kProd][kStages], s_llfull[kLLSlots], s_llempty[kLLSlots];
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(kFullMask, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler: TMA operands stay in uniform registers
   const int ctax = blockIdx.x % a.nctax, chunk = blockIdx.x / a.nctax, frame = blockIdx.y;
   const int Wc = a.Wc, Hc = a.Hc, hw1 = Wc >> 1, hh1 = Hc >> 1, hw2 = Wc >> 2, hh2 = Hc >> 2;
   const int X0 = ctax * kPitch;                       // first pixel column this CTA owns
   const int remLL = min(kPitchLL, hw1 - (X0 >> 1));   // LL1 columns this CTA owns
   const int ncons = remLL > 240 ? 2 : 1;
-  const int nprod = min(kProd, (remLL + 16 + 119) / 120);
+  const int nprod = min(kProd, (remLL + 20 + 119) / 120);  // valid LL1 columns needed: 12 before the first owned one, 8 after the last
 
   if (threadIdx.x == 0) {
     for (int p = 0; p < kProd; ++p)
-      for (int d = 0; d < kDepth; ++d) mbar_init(&s_full[p][d], 1);
+      for (int d = 0; d < kStages; ++d) mbar_init(&s_full[p][d], 1);
     for (int s = 0; s < kLLSlots; ++s) { mbar_init(&s_llfull[s], nprod); mbar_init(&s_llempty[s], ncons); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
     // =============================== producer: level 1 on 256 pixel columns ===============================
     const int p = warp;
     if (p >= nprod) return;
-    const int xw = X0 - 24 + 240 * p;                 // first column of the warp's 256 (may be < 0 or reach past Wc)
+    const int xw = X0 - 32 + 240 * p;                 // first column of the warp's 256 (a multiple of 16; may be < 0 or reach past Wc)
     const int c0 = xw + 8 * lane;
     const bool inimg = c0 >= 0 && c0 < Wc;
     const bool wlane = lane >= 1 && lane <= 30 && inimg && c0 >= X0 && c0 < X0 + kPitch;  // stores: owned columns only
@@ -149,15 +154,21 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
       return ys < a.H ? ys : 2 * a.H - 1 - ys;
     };
     const int ms = P0 - VP::kWarm, mend = Plast + VP::kDelay;
-    auto issue = [&](int m, int slot, unsigned dep) {  // rows 2m+1, 2m+2 of step m -> ring slot
-      if (lane == 0 && m <= mend) {
-        mbar_expect_tx(&s_full[p][slot], 512);
-        tma_load_row(&s_in[p][slot][0][0], &tmap, xw, row_index(2 * m + 1), frame, &s_full[p][slot], dep);
-        tma_load_row(&s_in[p][slot][1][0], &tmap, xw, row_index(2 * m + 2), frame, &s_full[p][slot], dep);
+    const int nstages = (mend - ms + 2) >> 1;         // a stage = two steps = rows 2m+1 .. 2m+4 of its first step m
+    auto issue = [&](int j, int slot, unsigned dep) {
+      if (lane == 0 && j < nstages) {
+        const int y0 = 2 * (ms + 2 * j) + 1;
+        mbar_expect_tx(&s_full[p][slot], 1024);
+        if (y0 >= 0 && y0 + 3 < a.H) {
+          tma_load_rows(&s_in[p][slot][0][0], &tmap4, xw, y0, frame, &s_full[p][slot], dep);
+        } else {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) tma_load_rows(&s_in[p][slot][r][0], &tmap1, xw, row_index(y0 + r), frame, &s_full[p][slot], dep);
+        }
       }
     };
 #pragma unroll
-    for (int d = 0; d < kDepth; ++d) issue(ms + d, d, 0u);
+    for (int d = 0; d < kStages; ++d) issue(d, d, 0u);
     VP v1;
     {
       T r[8];
@@ -165,31 +176,25 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
       unpack8(__ldg(reinterpret_cast<const uint2*>(a.src + (size_t)frame * a.src_fstride + (size_t)row_index(2 * ms) * a.src_pitch + cl)), r);
       v1.init(r);
     }
-    int slot = 0; unsigned par = 0;
     int llk = 0;  // LL1 rows published so far
     const int oc1 = c0 >> 1;
-#pragma unroll 1
-    for (int m = ms; m <= mend; ++m) {
+    // one step: rows 2m+1 (ra) and 2m+2 (rb) enter, row pair m - kDelay leaves
+    auto step = [&](int m, uint2 ra, uint2 rb) {
       T xo[8], x2[8], lo[8], hi[8];
-      mbar_wait(&s_full[p][slot], par);
-      __syncwarp();  // converged: the two loads below are one warp instruction each, the re-arming lane cannot run ahead of a waiting one
-      const uint2 ra = *reinterpret_cast<const uint2*>(&s_in[p][slot][0][8 * lane]);
-      const uint2 rb = *reinterpret_cast<const uint2*>(&s_in[p][slot][1][8 * lane]);
       unpack8(ra, xo); unpack8(rb, x2);
-      issue(m + kDepth, slot, ra.x ^ rb.y);
-      if (++slot == kDepth) { slot = 0; par ^= 1u; }
       // borders of this level come from the folded loads, so no explicit rule here
       if constexpr (LOSSY) v97_step_packed<8>(v1, xo, x2, lo, hi);
       else v1.step(xo, x2, false, lo, hi);
-      const int pr = m - VP::kDelay;  // row pair leaving the vertical pipeline
-      if (pr < P0) continue;          // warm-up (warp-uniform)
+      const int pr = m - VP::kDelay;
+      // (the two or three warm-up steps of a chunk run the horizontal pass on unfinished rows rather than branch around it:
+      // a straight-line body lets the two steps of a stage share one register assignment for the lifting state)
       if constexpr (LOSSY) {
-        if (pair_variant(pr, a.nW1, a.ls1)) hfwd97_rows<8, true>(lo, hi, left, right);
-        else hfwd97_rows<8, false>(lo, hi, left, right);
+        hfwd97_rows_rt<8>(lo, hi, left, right, pair_variant(pr, a.nW1, a.ls1));
       } else {
         hfwd53<8>(lo, left, right);
         hfwd53<8>(hi, left, right);
       }
+      if (pr < P0) return;  // warm-up (warp-uniform): nothing to store or hand over yet
       if (wlane && pr >= n0 && pr < n1)
         emit_pair<LOSSY, QS1, OT, T, 8>(lo, hi, out + (size_t)pr * a.pitch + oc1, out + (size_t)(pr + hh1) * a.pitch + oc1, hw1, a.q1, qs,
                                         false, nullptr);
@@ -200,61 +205,84 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_llfull[ls]);
       ++llk;
+    };
+    int slot = 0; unsigned par = 0;
+#pragma unroll 1
+    for (int j = 0; j < nstages; ++j) {
+      mbar_wait(&s_full[p][slot], par);
+      __syncwarp();  // converged: each load below is one warp instruction, and the re-arming lane cannot run ahead of a waiting one
+      const unsigned char* const st = &s_in[p][slot][0][8 * lane];
+      const uint2 ra = *reinterpret_cast<const uint2*>(st), rb = *reinterpret_cast<const uint2*>(st + 256);
+      const uint2 rc = *reinterpret_cast<const uint2*>(st + 512), rd = *reinterpret_cast<const uint2*>(st + 768);
+      issue(j + kStages, slot, ra.x ^ rb.y ^ rc.x ^ rd.y);
+      if (++slot == kStages) { slot = 0; par ^= 1u; }
+      const int m = ms + 2 * j;
+      step(m, ra, rb);
+      if (m + 1 <= mend) step(m + 1, rc, rd);
     }
   } else {
     // =============================== consumer: level 2 on 256 LL1 columns ===============================
     const int c = warp - kProd;
     if (c >= ncons) return;
     const int cl0 = (X0 >> 1) - 8 + 240 * c + 8 * lane;  // first of the lane's 8 LL1 columns
-    const int ridx = 240 * c + 8 * lane;                 // ... and its position in a ring row
+    const int ridx = 4 + 240 * c + 8 * lane;             // ... and its position in a ring row (which starts at LL1 column X0/2 - 12)
     const bool inimg = cl0 >= 0 && cl0 < hw1;
     const bool wlane = lane >= 1 && lane <= 30 && inimg && cl0 >= (X0 >> 1) && cl0 < (X0 >> 1) + kPitchLL;
     const bool left = cl0 == 0, right = cl0 + 8 == hw1;
     T* const llbase = a.last ? nullptr : static_cast<T*>(a.ll) + (size_t)frame * a.ll_fstride;
     const int oc2 = cl0 >> 1;
-    VP v2;
-    T ll_odd[8] = {};
-    int k = 0;
-#pragma unroll 1
-    for (int R = P0; R <= Plast; ++R, ++k) {
+    int k = 0;  // LL1 rows taken from the ring so far: row P0 + k is next
+    auto take = [&](T (&row)[8]) {
       const int ls = k & (kLLSlots - 1);
       mbar_wait(&s_llfull[ls], (unsigned)(k / kLLSlots) & 1u);
-      T row[8];
       lds8(&s_ll[ls][ridx], row);
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_llempty[ls]);
-      if (R == P0) { v2.init(row); continue; }
-      const bool lastrow = R == hh1 - 1;  // bottom of the image: LL1 row hh1 does not exist
-      if (R & 1) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ll_odd[j] = row[j];
-        if (!lastrow) continue;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) row[j] = v2.xe[j];  // x[n] := x[n-2]
+      ++k;
+    };
+    // horizontal pass, quantiser and stores of level-2 row pair p2
+    auto finish = [&](int p2, T (&lo2)[8], T (&hi2)[8]) {
+      if (p2 < m2_0 || p2 >= m2_1) return;
+      if constexpr (LOSSY) {
+        hfwd97_rows_rt<8>(lo2, hi2, left, right, pair_variant(p2, a.nW2, a.ls2));
+      } else {
+        hfwd53<8>(lo2, left, right);
+        hfwd53<8>(hi2, left, right);
       }
-      // normally one step (M = R/2 - 1); at the bottom row the last step and, for 9/7, the flush step
-      const int Mfirst = lastrow ? (R - 1) >> 1 : (R >> 1) - 1;
-      const int Mlast = lastrow ? Mfirst + VP::kDelay : Mfirst;
-      for (int M = Mfirst; M <= Mlast; ++M) {
-        T lo2[8], hi2[8];
-        if constexpr (LOSSY) {
-          if (M >= 2 && M < hh2) v97_step_packed<8>(v2, ll_odd, row, lo2, hi2);   // interior: no border rule applies
-          else v2.step(ll_odd, row, M == 0, M == 1, M == hh2, lo2, hi2);
-        } else {
-          v2.step(ll_odd, row, M == 0, lo2, hi2);
-        }
-        const int p2 = M - VP::kDelay;
-        if (p2 < m2_0 || p2 >= m2_1) continue;
-        if constexpr (LOSSY) {
-          if (pair_variant(p2, a.nW2, a.ls2)) hfwd97_rows<8, true>(lo2, hi2, left, right);
-          else hfwd97_rows<8, false>(lo2, hi2, left, right);
-        } else {
-          hfwd53<8>(lo2, left, right);
-          hfwd53<8>(hi2, left, right);
-        }
-        if (!wlane) continue;
+      if (wlane)
         emit_pair<LOSSY, QS1, OT, T, 8>(lo2, hi2, out + (size_t)p2 * a.pitch + oc2, out + (size_t)(p2 + hh2) * a.pitch + oc2, hw2, a.q2, qs,
                                         a.last != 0, a.last ? nullptr : llbase + (size_t)p2 * a.ll_pitch + oc2);
+    };
+    VP v2;
+    {
+      T r[8];
+      take(r);
+      v2.init(r);
+    }
+    // steps whose two rows 2M+1, 2M+2 both exist; M < 2 only at the top of the image (explicit border rules)
+    const int Mreg = (Plast - 2) >> 1;
+#pragma unroll 2
+    for (int M = M0; M <= Mreg; ++M) {
+      T xo[8], x2[8], lo2[8], hi2[8];
+      take(xo); take(x2);
+      if constexpr (LOSSY) {
+        if (M >= 2) v97_step_packed<8>(v2, xo, x2, lo2, hi2);
+        else v2.step(xo, x2, M == 0, M == 1, false, lo2, hi2);
+      } else {
+        v2.step(xo, x2, M == 0, lo2, hi2);
+      }
+      finish(M - VP::kDelay, lo2, hi2);
+    }
+    if (Plast & 1) {
+      // bottom of the image (Plast == hh1 - 1): the last odd row has no even partner, x[n] := x[n-2]; 9/7: one flush step more
+      T xo[8], x2[8], lo2[8], hi2[8];
+      take(xo);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x2[j] = v2.xe[j];
+      for (int M = hh2 - 1; M <= hh2 - 1 + VP::kDelay; ++M) {
+        if constexpr (LOSSY) v2.step(xo, x2, M == 0, M == 1, M == hh2, lo2, hi2);
+        else v2.step(xo, x2, M == 0, lo2, hi2);
+        finish(M - VP::kDelay, lo2, hi2);
       }
     }
   }
@@ -273,7 +301,7 @@ EncodeTiledFn encode_tiled() {
 }
 
 template <bool LOSSY, typename OT, bool QS1>
-void launch_fused_k(const CUtensorMap& tmap, FusedArgs a, int frames, cudaStream_t st) {
+void launch_fused_k(const CUtensorMap& tmap4, const CUtensorMap& tmap1, FusedArgs a, int frames, cudaStream_t st) {
   static const long long slots = [] {  // CTAs the whole GPU holds at once
     int dev = 0, sms = 148, per_sm = PCS_FUSED_MINB;
     cudaGetDevice(&dev);
@@ -293,7 +321,7 @@ void launch_fused_k(const CUtensorMap& tmap, FusedArgs a, int frames, cudaStream
   a.rp = rp_env > 0 ? std::max(4, rp_env & ~3) : best;
   a.nchunks = (hh1 + a.rp - 1) / a.rp;
   dim3 grid(a.nctax * a.nchunks, frames);
-  dwt_forward_l12_kernel<LOSSY, OT, QS1><<<grid, kThreads, 0, st>>>(tmap, a);
+  dwt_forward_l12_kernel<LOSSY, OT, QS1><<<grid, kThreads, 0, st>>>(tmap4, tmap1, a);
 }
 
 }  // namespace
@@ -310,14 +338,16 @@ bool dwt_forward_l12_ok(const void* d_px, const void* d_coeff, const void* ll2, 
 // Levels 1 and 2 of `frames` u8 frames in one launch.  ll2: scratch plane that receives LL2 (ignored when wl == 2).
 int dwt_forward_l12(const uint8_t* d_px, int W, int H, int Wa, int Ha, void* d_coeff, long long out_fstride, void* ll2, long long ll_fstride,
                     int wl, bool lossy, float qs, bool out_int, int frames, cudaStream_t st) {
-  alignas(64) CUtensorMap tmap;
+  alignas(64) CUtensorMap tmap4, tmap1;
   const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)frames};
   const cuuint64_t gstride[2] = {(cuuint64_t)W, (cuuint64_t)W * H};
-  const cuuint32_t box[3] = {256, 1, 1}, estr[3] = {1, 1, 1};
-  const CUresult r = encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(d_px), gdim, gstride, box, estr,
-                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
+  const cuuint32_t box4[3] = {256, 4, 1}, box1[3] = {256, 1, 1}, estr[3] = {1, 1, 1};
+  for (int k = 0; k < 2; ++k) {
+    const CUresult r = encode_tiled()(k ? &tmap1 : &tmap4, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(d_px), gdim, gstride,
+                                      k ? box1 : box4, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
+  }
   FusedArgs a{};
   a.src = d_px; a.src_fstride = (long long)W * H; a.src_pitch = W;
   a.H = H; a.Wc = Wa; a.Hc = Ha;
@@ -330,9 +360,9 @@ int dwt_forward_l12(const uint8_t* d_px, int W, int H, int Wa, int Ha, void* d_c
   variant_params(Ha >> 1, &a.nW2, &a.ls2);
   a.nctax = (Wa + kPitch - 1) / kPitch;
   const bool qs1 = qs == 1.0f;
-  if (!lossy) launch_fused_k<false, int, true>(tmap, a, frames, st);
-  else if (out_int) { if (qs1) launch_fused_k<true, int, true>(tmap, a, frames, st); else launch_fused_k<true, int, false>(tmap, a, frames, st); }
-  else { if (qs1) launch_fused_k<true, float, true>(tmap, a, frames, st); else launch_fused_k<true, float, false>(tmap, a, frames, st); }
+  if (!lossy) launch_fused_k<false, int, true>(tmap4, tmap1, a, frames, st);
+  else if (out_int) { if (qs1) launch_fused_k<true, int, true>(tmap4, tmap1, a, frames, st); else launch_fused_k<true, int, false>(tmap4, tmap1, a, frames, st); }
+  else { if (qs1) launch_fused_k<true, float, true>(tmap4, tmap1, a, frames, st); else launch_fused_k<true, float, false>(tmap4, tmap1, a, frames, st); }
   ++g_launches;
   return (int)cudaGetLastError();
 }

@@ -145,6 +145,48 @@ __device__ __forceinline__ void hfwd97_rows(float (&lo)[N], float (&hi)[N], bool
   }
 }
 
+// hfwd97_rows with the row variant chosen at run time (warp-uniform): the two variants differ only in the first lifting
+// sum of each pair (FMA-contracted or not), so one copy of the code with a uniform branch around those N/2
+// instructions serves both -- half the instruction-cache footprint of calling the two template variants.
+template <int N>
+__device__ __forceinline__ void hfwd97_rows_rt(float (&lo)[N], float (&hi)[N], bool left, bool right, bool fused) {
+  constexpr int P = N / 2;
+  const f2 S = pk(kIK, kK), A2 = pk(kA, kA), B2 = pk(kB, kB), G2 = pk(kG, kG), D2 = pk(kD, kD), IK2 = pk(kIK, kIK), K2 = pk(kK, kK);
+  f2 x[N], e[P], o[P];
+#pragma unroll
+  for (int j = 0; j < N; ++j) x[j] = pk(lo[j], hi[j]);
+#pragma unroll
+  for (int k = 0; k < P; ++k) e[k] = mul2(x[2 * k], S);
+  f2 n0 = shfl_down2(e[0]);
+  if (right) n0 = e[P - 1];
+  if (fused) {
+#pragma unroll
+    for (int k = 0; k < P; ++k) o[k] = fma2(x[2 * k], S, k + 1 < P ? e[k + 1] : n0);
+  } else {
+#pragma unroll
+    for (int k = 0; k < P; ++k) o[k] = add2(e[k], k + 1 < P ? e[k + 1] : n0);
+  }
+#pragma unroll
+  for (int k = 0; k < P; ++k) o[k] = fma2(x[2 * k + 1], S, mul2(o[k], A2));
+  f2 p1 = shfl_up2(o[P - 1]);
+  if (left) p1 = o[0];
+#pragma unroll
+  for (int k = P - 1; k >= 0; --k) e[k] = fma2(add2(k ? o[k - 1] : p1, o[k]), B2, e[k]);
+  n0 = shfl_down2(e[0]);
+  if (right) n0 = e[P - 1];
+#pragma unroll
+  for (int k = 0; k < P; ++k) o[k] = fma2(add2(e[k], k + 1 < P ? e[k + 1] : n0), G2, o[k]);
+  p1 = shfl_up2(o[P - 1]);
+  if (left) p1 = o[0];
+#pragma unroll
+  for (int k = P - 1; k >= 0; --k) e[k] = mul2(fma2(add2(k ? o[k - 1] : p1, o[k]), D2, e[k]), IK2);
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    upk(e[k], lo[2 * k], hi[2 * k]);
+    upk(mul2(o[k], K2), lo[2 * k + 1], hi[2 * k + 1]);
+  }
+}
+
 // ---- vertical analysis pipelines (state per column) ------------------------------------------------
 // 5/3: step m consumes rows 2m+1, 2m+2 and produces row pair m.  d[n] = x[2n+1] - ((x[2n]+x[2n+2])>>1),
 // s[n] = x[2n] + ((d[n-1]+d[n]+2)>>2)  (DWTGenerator.cu:72-76,137-157).
