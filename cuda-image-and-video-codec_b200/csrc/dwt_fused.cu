@@ -38,7 +38,7 @@ namespace {
 constexpr int kProd = 4, kCons = 2, kThreads = 32 * (kProd + kCons);
 constexpr int kPitchLL = 456, kPitch = 2 * kPitchLL;  // LL1 / pixel columns a CTA owns (912 = 16 * 57: TMA boxes start 16-byte aligned)
 constexpr int kStages = 4;                            // two-step stages (4 rows x 256 B) a producer's TMA ring runs ahead
-constexpr int kLLSlots = 8;                           // LL1 rows in the hand-over ring
+constexpr int kLLSlots = 6;                           // LL1 rows in the hand-over ring (two named barriers each)
 constexpr int kLLRow = 512;                           // 32-bit words per ring row (480 written, 500 read)
 
 struct FusedArgs {
@@ -87,6 +87,24 @@ __device__ __forceinline__ void tma_load_rows(void* dst, const CUtensorMap* tmap
       : "memory");
 }
 
+// Named barriers for the LL1 hand-over (ids 1 .. 2 * kLLSlots): a waiting warp is parked by the hardware and spends no
+// issue slots, unlike a polled mbarrier -- the consumers wait about half of the time by design.
+__device__ __forceinline__ void bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// pair_variant() for 32 consecutive row pairs at once (lane i evaluates pair base + i), refreshed when n leaves the window:
+// two or three instructions per step instead of the dozen of the closed form
+struct VariantMask {
+  unsigned mask = 0; int base = -0x40000000;
+  __device__ __forceinline__ bool get(int n, int nW, int ls) {
+    if ((n >> 5) != base) {
+      base = n >> 5;
+      mask = __ballot_sync(kFullMask, pair_variant((base << 5) + (int)(threadIdx.x & 31), nW, ls));
+    }
+    return (mask >> (n & 31)) & 1u;
+  }
+};
+
 template <typename T> __device__ __forceinline__ void sts4(void* p, T a, T b, T c, T d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(bits(a)), "r"(bits(b)), "r"(bits(c)), "r"(bits(d)) : "memory");
 }
@@ -111,7 +129,7 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
   using VP = typename VSel<LOSSY, 8>::type;
   __shared__ __align__(128) unsigned char s_in[kProd][kStages][4][256];
   __shared__ __align__(16) unsigned s_ll[kLLSlots][kLLRow];
-  __shared__ __align__(8) unsigned long long s_full[kProd][kStages], s_llfull[kLLSlots], s_llempty[kLLSlots];
+  __shared__ __align__(8) unsigned long long s_full[kProd][kStages];
 
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(kFullMask, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler: TMA operands stay in uniform registers
@@ -125,7 +143,6 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
   if (threadIdx.x == 0) {
     for (int p = 0; p < kProd; ++p)
       for (int d = 0; d < kStages; ++d) mbar_init(&s_full[p][d], 1);
-    for (int s = 0; s < kLLSlots; ++s) { mbar_init(&s_llfull[s], nprod); mbar_init(&s_llempty[s], ncons); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -137,6 +154,7 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
   const int M0 = max(m2_0 - VP::kWarm, 0);            // first level-2 step; it starts from LL1 row 2 * M0
   const int P0 = 2 * M0;                              // first level-1 pair whose output is needed (<= n0)
   const int Plast = min(2 * (m2_1 - 1 + VP::kDelay) + 2, hh1 - 1);  // last one (level 2 reads one or three rows past n1)
+  const int hand = 32 * (nprod + ncons);  // threads that meet at a hand-over barrier
   const float qs = a.qs;
   OT* const out = static_cast<OT*>(a.out) + (size_t)frame * a.out_fstride;
 
@@ -176,20 +194,21 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
       unpack8(__ldg(reinterpret_cast<const uint2*>(a.src + (size_t)frame * a.src_fstride + (size_t)row_index(2 * ms) * a.src_pitch + cl)), r);
       v1.init(r);
     }
-    int llk = 0;  // LL1 rows published so far
+    int ls = 0; bool lap0 = true;  // ring slot of the next LL1 row; first lap: the slots are free
     const int oc1 = c0 >> 1;
+    VariantMask vm;
     // one step: rows 2m+1 (ra) and 2m+2 (rb) enter, row pair m - kDelay leaves
     auto step = [&](int m, uint2 ra, uint2 rb) {
       T xo[8], x2[8], lo[8], hi[8];
       unpack8(ra, xo); unpack8(rb, x2);
       // borders of this level come from the folded loads, so no explicit rule here
-      if constexpr (LOSSY) v97_step_packed<8>(v1, xo, x2, lo, hi);
+      if constexpr (LOSSY) v97_step_mixed<8>(v1, xo, x2, lo, hi);
       else v1.step(xo, x2, false, lo, hi);
       const int pr = m - VP::kDelay;
       // (the two or three warm-up steps of a chunk run the horizontal pass on unfinished rows rather than branch around it:
       // a straight-line body lets the two steps of a stage share one register assignment for the lifting state)
       if constexpr (LOSSY) {
-        hfwd97_rows_rt<8>(lo, hi, left, right, pair_variant(pr, a.nW1, a.ls1));
+        hfwd97_rows_rt<8>(lo, hi, left, right, vm.get(pr, a.nW1, a.ls1));
       } else {
         hfwd53<8>(lo, left, right);
         hfwd53<8>(hi, left, right);
@@ -199,12 +218,10 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
         emit_pair<LOSSY, QS1, OT, T, 8>(lo, hi, out + (size_t)pr * a.pitch + oc1, out + (size_t)(pr + hh1) * a.pitch + oc1, hw1, a.q1, qs,
                                         false, nullptr);
       // ---- hand the LL1 row to the consumers ----
-      const int ls = llk & (kLLSlots - 1);
-      if (llk >= kLLSlots) mbar_wait(&s_llempty[ls], ((unsigned)(llk / kLLSlots) - 1u) & 1u);
+      if (!lap0) bar_sync(1 + kLLSlots + ls, hand);  // the consumers have read what the slot held a lap ago
       if (lane >= 1 && lane <= 30) sts4<T>(&s_ll[ls][120 * p + 4 * (lane - 1)], lo[0], lo[2], lo[4], lo[6]);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_llfull[ls]);
-      ++llk;
+      bar_arrive(1 + ls, hand);
+      if (++ls == kLLSlots) { ls = 0; lap0 = false; }
     };
     int slot = 0; unsigned par = 0;
 #pragma unroll 1
@@ -231,20 +248,19 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
     const bool left = cl0 == 0, right = cl0 + 8 == hw1;
     T* const llbase = a.last ? nullptr : static_cast<T*>(a.ll) + (size_t)frame * a.ll_fstride;
     const int oc2 = cl0 >> 1;
-    int k = 0;  // LL1 rows taken from the ring so far: row P0 + k is next
+    VariantMask vm;
+    int ls = 0;  // ring slot of the next LL1 row
     auto take = [&](T (&row)[8]) {
-      const int ls = k & (kLLSlots - 1);
-      mbar_wait(&s_llfull[ls], (unsigned)(k / kLLSlots) & 1u);
+      bar_sync(1 + ls, hand);                  // every producer has stored its part of the row
       lds8(&s_ll[ls][ridx], row);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_llempty[ls]);
-      ++k;
+      bar_arrive(1 + kLLSlots + ls, hand);     // (the loaded values are consumed before the slot can be overwritten: see below)
+      if (++ls == kLLSlots) ls = 0;
     };
     // horizontal pass, quantiser and stores of level-2 row pair p2
     auto finish = [&](int p2, T (&lo2)[8], T (&hi2)[8]) {
       if (p2 < m2_0 || p2 >= m2_1) return;
       if constexpr (LOSSY) {
-        hfwd97_rows_rt<8>(lo2, hi2, left, right, pair_variant(p2, a.nW2, a.ls2));
+        hfwd97_rows_rt<8>(lo2, hi2, left, right, vm.get(p2, a.nW2, a.ls2));
       } else {
         hfwd53<8>(lo2, left, right);
         hfwd53<8>(hi2, left, right);
@@ -266,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
       T xo[8], x2[8], lo2[8], hi2[8];
       take(xo); take(x2);
       if constexpr (LOSSY) {
-        if (M >= 2) v97_step_packed<8>(v2, xo, x2, lo2, hi2);
+        if (M >= 2) v97_step_mixed<8>(v2, xo, x2, lo2, hi2);
         else v2.step(xo, x2, M == 0, M == 1, false, lo2, hi2);
       } else {
         v2.step(xo, x2, M == 0, lo2, hi2);
