@@ -9,6 +9,7 @@
 // Why: per-level launches move 7.4 B/px (the 4 B/px LL1 plane is written by level 1 and read back by level 2) where the
 // transform needs 5 B/px; both launches already run at ~86 % of the HBM peak, so only removing that round trip helps.
 //
+// (Measured steps of this design are in DESIGN.md 4.1.)
 // Design (one CTA = 6 warps, a column strip of 912 pixels x a chunk of rows, streaming downwards):
 //   * warps 0-3, "producers": level 1.  A warp owns 256 pixel columns (8 per lane, lanes 0 / 31 are halo), keeps the
 //     vertical lifting state in registers and does the horizontal lifting with four shuffles per row pair -- the
@@ -118,7 +119,7 @@ __device__ __forceinline__ void lds8(const void* p, int (&v)[8]) {
 }
 
 #ifndef PCS_FUSED_MINB
-#define PCS_FUSED_MINB 3
+#define PCS_FUSED_MINB 4
 #endif
 // tmap4: u8 frames with a 256 x 4 box (the four rows of a two-step stage in one copy); tmap1: 256 x 1 box, used row by
 // row where the rows of a stage are not four consecutive rows of the frame (mirror folds at the top / bottom / padding).
@@ -197,23 +198,9 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
     int ls = 0; bool lap0 = true;  // ring slot of the next LL1 row; first lap: the slots are free
     const int oc1 = c0 >> 1;
     VariantMask vm;
-    // one step: rows 2m+1 (ra) and 2m+2 (rb) enter, row pair m - kDelay leaves
-    auto step = [&](int m, uint2 ra, uint2 rb) {
-      T xo[8], x2[8], lo[8], hi[8];
-      unpack8(ra, xo); unpack8(rb, x2);
-      // borders of this level come from the folded loads, so no explicit rule here
-      if constexpr (LOSSY) v97_step_mixed<8>(v1, xo, x2, lo, hi);
-      else v1.step(xo, x2, false, lo, hi);
-      const int pr = m - VP::kDelay;
-      // (the two or three warm-up steps of a chunk run the horizontal pass on unfinished rows rather than branch around it:
-      // a straight-line body lets the two steps of a stage share one register assignment for the lifting state)
-      if constexpr (LOSSY) {
-        hfwd97_rows_rt<8>(lo, hi, left, right, vm.get(pr, a.nW1, a.ls1));
-      } else {
-        hfwd53<8>(lo, left, right);
-        hfwd53<8>(hi, left, right);
-      }
-      if (pr < P0) return;  // warm-up (warp-uniform): nothing to store or hand over yet
+    // stores and hand-over of row pair pr (after the horizontal pass)
+    auto finish = [&](int pr, T (&lo)[8], T (&hi)[8]) {
+      if (pr < P0 || pr > Plast) return;  // warm-up / the unused second half of the last stage (warp-uniform)
       if (wlane && pr >= n0 && pr < n1)
         emit_pair<LOSSY, QS1, OT, T, 8>(lo, hi, out + (size_t)pr * a.pitch + oc1, out + (size_t)(pr + hh1) * a.pitch + oc1, hw1, a.q1, qs,
                                         false, nullptr);
@@ -233,9 +220,25 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
       const uint2 rc = *reinterpret_cast<const uint2*>(st + 512), rd = *reinterpret_cast<const uint2*>(st + 768);
       issue(j + kStages, slot, ra.x ^ rb.y ^ rc.x ^ rd.y);
       if (++slot == kStages) { slot = 0; par ^= 1u; }
-      const int m = ms + 2 * j;
-      step(m, ra, rb);
-      if (m + 1 <= mend) step(m + 1, rc, rd);
+      // the two steps of the stage: rows 2m+1, 2m+2 (A) and 2m+3, 2m+4 (B) enter, row pairs prA and prA + 1 leave.  Both
+      // vertical steps first, then the two horizontal passes as one interleaved stream (borders of this level come from
+      // the folded loads, so no explicit rule in the vertical steps).
+      const int prA = ms + 2 * j - VP::kDelay;
+      T xo[8], x2[8], loA[8], hiA[8], loB[8], hiB[8];
+      unpack8(ra, xo); unpack8(rb, x2);
+      if constexpr (LOSSY) v97_step_mixed<8>(v1, xo, x2, loA, hiA);
+      else v1.step(xo, x2, false, loA, hiA);
+      unpack8(rc, xo); unpack8(rd, x2);
+      if constexpr (LOSSY) v97_step_mixed<8>(v1, xo, x2, loB, hiB);
+      else v1.step(xo, x2, false, loB, hiB);
+      if constexpr (LOSSY) {
+        hfwd97_rows2<8>(loA, hiA, loB, hiB, left, right, vm.get(prA, a.nW1, a.ls1), vm.get(prA + 1, a.nW1, a.ls1));
+      } else {
+        hfwd53<8>(loA, left, right); hfwd53<8>(hiA, left, right);
+        hfwd53<8>(loB, left, right); hfwd53<8>(hiB, left, right);
+      }
+      finish(prA, loA, hiA);
+      finish(prA + 1, loB, hiB);
     }
   } else {
     // =============================== consumer: level 2 on 256 LL1 columns ===============================

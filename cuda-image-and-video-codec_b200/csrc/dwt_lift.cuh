@@ -187,6 +187,59 @@ __device__ __forceinline__ void hfwd97_rows_rt(float (&lo)[N], float (&hi)[N], b
   }
 }
 
+// Two independent row pairs A and B through hfwd97_rows_rt in ONE instruction stream, stage by stage: the shuffle latency of
+// one pair (four dependent ~25-cycle exchanges) is covered by the arithmetic of the other.  At 3-4 eligible warps per
+// scheduler the lifting chains are latency-bound otherwise.
+template <int N>
+__device__ __forceinline__ void hfwd97_rows2(float (&loA)[N], float (&hiA)[N], float (&loB)[N], float (&hiB)[N], bool left, bool right,
+                                             bool fusedA, bool fusedB) {
+  constexpr int P = N / 2;
+  const f2 S = pk(kIK, kK), A2 = pk(kA, kA), B2 = pk(kB, kB), G2 = pk(kG, kG), D2 = pk(kD, kD), IK2 = pk(kIK, kIK), K2 = pk(kK, kK);
+  f2 xa[N], ea[P], oa[P], xb[N], eb[P], ob[P];
+#pragma unroll
+  for (int j = 0; j < N; ++j) { xa[j] = pk(loA[j], hiA[j]); xb[j] = pk(loB[j], hiB[j]); }
+#pragma unroll
+  for (int k = 0; k < P; ++k) { ea[k] = mul2(xa[2 * k], S); eb[k] = mul2(xb[2 * k], S); }
+  f2 na = shfl_down2(ea[0]), nb = shfl_down2(eb[0]);
+  if (right) { na = ea[P - 1]; nb = eb[P - 1]; }
+  if (fusedA) {
+#pragma unroll
+    for (int k = 0; k < P; ++k) oa[k] = fma2(xa[2 * k], S, k + 1 < P ? ea[k + 1] : na);
+  } else {
+#pragma unroll
+    for (int k = 0; k < P; ++k) oa[k] = add2(ea[k], k + 1 < P ? ea[k + 1] : na);
+  }
+  if (fusedB) {
+#pragma unroll
+    for (int k = 0; k < P; ++k) ob[k] = fma2(xb[2 * k], S, k + 1 < P ? eb[k + 1] : nb);
+  } else {
+#pragma unroll
+    for (int k = 0; k < P; ++k) ob[k] = add2(eb[k], k + 1 < P ? eb[k + 1] : nb);
+  }
+#pragma unroll
+  for (int k = 0; k < P; ++k) { oa[k] = fma2(xa[2 * k + 1], S, mul2(oa[k], A2)); ob[k] = fma2(xb[2 * k + 1], S, mul2(ob[k], A2)); }
+  f2 pa = shfl_up2(oa[P - 1]), pb = shfl_up2(ob[P - 1]);
+  if (left) { pa = oa[0]; pb = ob[0]; }
+#pragma unroll
+  for (int k = P - 1; k >= 0; --k) { ea[k] = fma2(add2(k ? oa[k - 1] : pa, oa[k]), B2, ea[k]); eb[k] = fma2(add2(k ? ob[k - 1] : pb, ob[k]), B2, eb[k]); }
+  na = shfl_down2(ea[0]); nb = shfl_down2(eb[0]);
+  if (right) { na = ea[P - 1]; nb = eb[P - 1]; }
+#pragma unroll
+  for (int k = 0; k < P; ++k) { oa[k] = fma2(add2(ea[k], k + 1 < P ? ea[k + 1] : na), G2, oa[k]); ob[k] = fma2(add2(eb[k], k + 1 < P ? eb[k + 1] : nb), G2, ob[k]); }
+  pa = shfl_up2(oa[P - 1]); pb = shfl_up2(ob[P - 1]);
+  if (left) { pa = oa[0]; pb = ob[0]; }
+#pragma unroll
+  for (int k = P - 1; k >= 0; --k) {
+    ea[k] = mul2(fma2(add2(k ? oa[k - 1] : pa, oa[k]), D2, ea[k]), IK2);
+    eb[k] = mul2(fma2(add2(k ? ob[k - 1] : pb, ob[k]), D2, eb[k]), IK2);
+  }
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    upk(ea[k], loA[2 * k], hiA[2 * k]); upk(mul2(oa[k], K2), loA[2 * k + 1], hiA[2 * k + 1]);
+    upk(eb[k], loB[2 * k], hiB[2 * k]); upk(mul2(ob[k], K2), loB[2 * k + 1], hiB[2 * k + 1]);
+  }
+}
+
 // ---- vertical analysis pipelines (state per column) ------------------------------------------------
 // 5/3: step m consumes rows 2m+1, 2m+2 and produces row pair m.  d[n] = x[2n+1] - ((x[2n]+x[2n+2])>>1),
 // s[n] = x[2n] + ((d[n-1]+d[n]+2)>>2)  (DWTGenerator.cu:72-76,137-157).
