@@ -104,3 +104,46 @@ def test_cli_k_factor(tmp_path):
     assert rc == 0, out
     blob = open(dec, "rb").read()
     assert np.array_equal(np.frombuffer(blob[len(b"P5\n256 256\n255\n"):], dtype=np.uint8), img.reshape(-1)) and e["rc_dec"] == 0
+
+
+def test_cli_many_batches_wrap_the_ring(tmp_path, lut_root):
+    """The command line's reader / GPU / writer pipeline circulates three page-locked buffers; PICSONG_BATCH forces small
+    batches so that a 13-frame video goes through 7 (encode) and 5 (decode) batches and every buffer is reused.  The
+    file must equal what ONE pcs_encode_frames call over all frames produces, and decode must return the input."""
+    from picsong_b200 import codec, synth
+    W, H, wl, n = 256, 192, 3, 13
+    frames = synth.synth_video(W, H, n)
+    raw, enc, dec = tmp_path / "m.raw", tmp_path / "m.pcs", tmp_path / "m.out"
+    frames.tofile(raw)
+    args = ["-cd", 0, "-wl", wl, "-cp", 2, "-type", 0, "-qs", 1, "-i", raw, "-o", enc, "-cbWidth", 64, "-cbHeight", 18, "-xSize", W, "-ySize", H,
+            "-video", 1, "-frames", n, "-LUTFolder", f"{lut_root}/video_lossless/"]
+    p = subprocess.run([CLI] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300,
+                       env=dict(os.environ, PICSONG_BATCH="2"))
+    assert p.returncode == 0, p.stdout
+    assert "Start-up (CUDA context" in p.stdout
+    cd = codec.Codec(codec.Params(W, H, wl, False, 1.0, frames=n, max_batch=16), codec.load_lut(f"{lut_root}/video_lossless/", wl))
+    s, lens = cd.encode_frames(frames)
+    cd.close()
+    assert np.array_equal(np.fromfile(enc, dtype=np.uint16), s)
+    assert open(str(enc) + "_SIZE").read() == ",".join(str(int(v)) for v in lens)
+    p = subprocess.run([CLI, "-cd", "1", "-i", str(enc), "-o", str(dec), "-LUTFolder", f"{lut_root}/video_lossless/", "-video", "1"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300, env=dict(os.environ, PICSONG_BATCH="3"))
+    assert p.returncode == 0, p.stdout
+    assert np.array_equal(np.fromfile(dec, dtype=np.uint8).reshape(n, H, W), frames)
+
+
+def test_cli_rgb_still_with_frames_flag(tmp_path, golden, lut_root):
+    """`-video 0 -isRGB 1 -frames N`: the reference codes the components of a still with iter = component, so only plane 0
+    carries the header whatever -frames says.  The stream must equal the plain RGB still's except for the
+    header's frame field."""
+    from picsong_b200 import synth
+    raw, enc0, enc5 = tmp_path / "c.raw", tmp_path / "c0.pcs", tmp_path / "c5.pcs"
+    synth.synth_rgb(256, 192).tofile(raw)
+    base = ["-cd", 0, "-wl", 3, "-cp", 2, "-type", 0, "-qs", 1, "-i", raw, "-cbWidth", 64, "-cbHeight", 18, "-xSize", 256, "-ySize", 192,
+            "-video", 0, "-isRGB", 1, "-LUTFolder", f"{lut_root}/n1_lossless/", "-k", 0]
+    rc, out = run(base + ["-o", enc0]); assert rc == 0, out
+    rc, out = run(base + ["-o", enc5, "-frames", 5]); assert rc == 0, out
+    a, b = np.fromfile(enc0, dtype=np.uint16), np.fromfile(enc5, dtype=np.uint16)
+    assert a.size == b.size and np.array_equal(a[9:], b[9:])          # planes 1 and 2 start with 0xFFFF x 9 in both
+    assert open(str(enc0) + "_SIZE").read() == open(str(enc5) + "_SIZE").read()
+    assert np.array_equal(a, golden.stream("rgb256x192_wl3_ll"))
