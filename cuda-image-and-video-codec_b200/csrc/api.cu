@@ -24,7 +24,7 @@ namespace pcs {
 unsigned long long g_launches = 0;
 
 size_t dwt_scratch_elems(int Wa, int Ha, int wl);
-int dwt_forward(const uint8_t*, void*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t);
+int dwt_forward(const uint8_t*, void*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t, int offset);
 int dwt_forward_planes(const void*, void*, void*, int, int, int, bool, float, bool, int, cudaStream_t);
 bool dwt_forward_rgb_ok(const uint8_t*, const void*, const void*, int, int, int, int, int);
 int dwt_forward_rgb(const uint8_t*, void*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t);
@@ -33,7 +33,7 @@ int rgb_forward(const uint8_t*, void*, int, int, int, int, bool, int, cudaStream
 int rgb_inverse(const void*, uint8_t*, int, int, int, int, bool, bool, int, cudaStream_t);
 bool dwt_inverse_rgb_ok(const int32_t*, const uint8_t*, const void*, int, int, int, int, int);
 int dwt_inverse_rgb(const int32_t*, uint8_t*, void*, int, int, int, int, int, bool, float, int, cudaStream_t);
-int dwt_inverse(const int32_t*, uint8_t*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t);
+int dwt_inverse(const int32_t*, uint8_t*, void*, int, int, int, int, int, bool, float, bool, int, cudaStream_t, int offset);
 int bpc_encode(const void*, bool, uint16_t*, int32_t*, const BpcArgs&, cudaStream_t);
 int bpc_decode(const uint16_t*, const int32_t*, int32_t*, const BpcArgs&, cudaStream_t);
 int bpc_encode_k(const void*, bool, uint16_t*, int32_t*, const BpcKArgs&, cudaStream_t);
@@ -50,6 +50,7 @@ using namespace pcs;
 struct pcs_ctx {
   pcs_params p;
   int Wa, Ha, ncb, ncomp;          // ncomp: planes per frame (1 grey, 3 RGB)
+  int offset = 128;                // level shift of the grey path: 2^(bit_depth - 1), 0 for signed samples
   size_t A, scratch_elems, max_words, frame_px;  // max_words: per PLANE; frame_px = ncomp * W * H
   std::vector<int32_t> lut;
   uint4* d_tab4 = nullptr; int nrows = 0;  // device: probability rows, [ncomp][nrows]
@@ -170,7 +171,7 @@ int run_dwt_forward(pcs_ctx* c, const Ws& w, const uint8_t* d_px, void* d_coeff,
   const pcs_params& p = c->p;
   if (c->ncomp == 1)
     return dwt_forward(d_px, d_coeff, w.scratch, p.width, p.height, c->Wa, c->Ha, p.wavelet_levels, p.lossy != 0, p.quant_size, out_int,
-                       frames, st);
+                       frames, st, c->offset);
   // colour transform fused into the level-1 load where the streaming kernel applies ...
   static const bool fuse_rgb = [] { const char* e = std::getenv("PCS_RGB_FUSE"); return !e || std::atoi(e) != 0; }();
   if (fuse_rgb && dwt_forward_rgb_ok(d_px, d_coeff, w.scratch, p.width, p.height, c->Wa, c->Ha, p.wavelet_levels))
@@ -188,7 +189,7 @@ int run_dwt_inverse(pcs_ctx* c, const Ws& w, const int32_t* d_q, uint8_t* d_px, 
   const bool flat = (p.flags & PCS_F_REF_FLAT_CROP) != 0;
   if (c->ncomp == 1)
     return dwt_inverse(d_q, d_px, w.scratch, p.width, p.height, c->Wa, c->Ha, p.wavelet_levels, p.lossy != 0, p.quant_size, flat, frames,
-                       st);
+                       st, c->offset);
   static const bool fuse_rgb = [] { const char* e = std::getenv("PCS_RGB_FUSE"); return !e || std::atoi(e) != 0; }();
   if (fuse_rgb && dwt_inverse_rgb_ok(d_q, d_px, w.scratch, p.width, p.height, c->Wa, c->Ha, p.wavelet_levels))
     return dwt_inverse_rgb(d_q, d_px, w.scratch, p.width, p.height, c->Wa, c->Ha, p.wavelet_levels, p.lossy != 0, p.quant_size, frames * 3,
@@ -255,7 +256,15 @@ int32_t pcs_create(const pcs_params* params, pcs_ctx** out) {
       p.coding_passes > 3 || p.k_factor < 0 || p.k_factor > 65.535f || p.max_batch < 1)
     return PCS_E_ARG;
   if (p.lossy && !(p.quant_size > 0)) return PCS_E_ARG;
-  if (p.coding_passes != 2 || p.is_signed || p.bit_depth != 8) return PCS_E_UNSUPPORTED;
+  if (p.coding_passes != 2) return PCS_E_UNSUPPORTED;  // the 3-pass variant needs LUT files the reference does not ship
+  // -bps / -signedOrUnsigned: samples stay BYTES (IO/IOManager.ipp:72-112 reads unsigned char whatever -bps
+  // says), only the level shift changes: 2^(bps-1), or 0 for signed input (Engines/CodingEngine.cu:581-588,644-656); the
+  // decoder clamps to [0, 255] either way (Engines/DecodingEngine.cu:706-729).  Grey only; bounded so that the shifted
+  // samples stay exact in fp32 and the LL indices inside the de-quantiser's 2^21 range.
+  if (p.bit_depth < 1 || p.bit_depth > 16) return PCS_E_ARG;
+  const int offset = p.is_signed ? 0 : 1 << (p.bit_depth - 1);
+  if (offset != 128 && p.is_rgb) return PCS_E_UNSUPPORTED;
+  if (p.lossy && (double)(offset + 128) * 1.1 * (double)(1 << p.wavelet_levels) >= 2097152.0) return PCS_E_UNSUPPORTED;
   // RGB: `-isRGB 1` with the default `-components 1` is what the reference's own examples use (README.md:105-115);
   // `-components 3` is accepted as well.  Grey: one component.
   if (p.is_rgb ? (p.components != 1 && p.components != 3) : p.components != 1) return PCS_E_UNSUPPORTED;
@@ -272,6 +281,7 @@ int32_t pcs_create(const pcs_params* params, pcs_ctx** out) {
   c->lut.assign(p.lut, p.lut + p.lut_len);
   c->p.lut = c->lut.data();
   c->ncomp = p.is_rgb ? 3 : 1;
+  c->offset = offset;
   c->Wa = Wa; c->Ha = Ha; c->A = (size_t)Wa * Ha; c->ncb = (Wa / kCB) * (Ha / kCB);
   c->max_words = c->A + c->ncb + 10;
   c->frame_px = (size_t)c->ncomp * p.width * p.height;

@@ -44,7 +44,7 @@ pcs_ctx* Engine::makeContext(int maxBatch, unsigned flags) {
   pcs_ctx* ctx = nullptr;
   const int rc = pcs_create(&p, &ctx);
   if (rc == PCS_E_ARG) die("Incorrect parameters. Please choose valid values.", -1);
-  if (rc == PCS_E_UNSUPPORTED) die("This build covers the 8-bit unsigned 2-coding-pass paths, grey and RGB, k >= 0 (cp=3 and signed input are out of scope).", -1);
+  if (rc == PCS_E_UNSUPPORTED) die("This build covers the 2-coding-pass paths: grey (any -bps up to 16, signed or unsigned byte samples) and 8-bit RGB, k >= 0 (-cp 3 is out of scope: the reference ships no LUT files for it).", -1);
   if (rc != 0) die("pcs_create failed with code " + std::to_string(rc) + (rc > 0 ? " (CUDA error: is a GPU present? there is no CPU fallback)" : ""));
   return ctx;
 }

@@ -42,6 +42,7 @@ struct FwdArgs {
   int last, src_vec, out_vec;
   float q_ll, q_hl, q_lh, q_hh, qs;
   int rp, nstrips, nchunks;
+  int offset;                                            // u8 level: level shift 2^(bps-1), 0 for signed samples
 };
 
 struct InvArgs {
@@ -54,6 +55,7 @@ struct InvArgs {
   int in_vec, dst_vec;
   float r_ll, r_hl, r_lh, r_hh, rqs;                     // reciprocal quantiser steps
   int rp, nstrips, nchunks;
+  int offset;                                            // u8 output: level shift added back before the clamp
 };
 
 template <typename T> struct Vec4;
@@ -70,7 +72,7 @@ template <> struct Vec2<float> { using type = float2; };
 template <typename T, bool SRC_U8>
 struct RowLoader {
   const unsigned char* base8; const T* baseT;
-  int pitch, Hc, H, c0; int col[4]; bool vec;
+  int pitch, Hc, H, c0; int col[4]; bool vec; int offset;
   __device__ __forceinline__ void load(int y, T v[4]) const {
     int ys = fold_ws(y, Hc);
     if (SRC_U8) {
@@ -78,10 +80,10 @@ struct RowLoader {
       const unsigned char* r = base8 + (size_t)ys * pitch;
       if (vec) {
         uchar4 p = __ldg(reinterpret_cast<const uchar4*>(r + c0));
-        v[0] = (T)((int)p.x - 128); v[1] = (T)((int)p.y - 128); v[2] = (T)((int)p.z - 128); v[3] = (T)((int)p.w - 128);
+        v[0] = (T)((int)p.x - offset); v[1] = (T)((int)p.y - offset); v[2] = (T)((int)p.z - offset); v[3] = (T)((int)p.w - offset);
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = (T)((int)__ldg(r + col[j]) - 128);
+        for (int j = 0; j < 4; ++j) v[j] = (T)((int)__ldg(r + col[j]) - offset);
       }
     } else {
       const T* r = baseT + (size_t)ys * pitch;
@@ -192,6 +194,7 @@ __global__ void __launch_bounds__(128) dwt_forward_level(const FwdArgs a) {
     ld.col[j] = SRC_U8 ? pad_src(c, a.W) : c;
   }
   ld.vec = a.src_vec && ld.c0 >= 0 && ld.c0 + 3 < (SRC_U8 ? min(Wc, a.W) : Wc);
+  ld.offset = a.offset;
 
   const bool wlane = lane >= 1 && lane <= 30;
   const bool v0 = wlane && ld.c0 < Wc, v1 = wlane && ld.c0 + 2 < Wc;
@@ -411,8 +414,8 @@ __global__ void __launch_bounds__(128) dwt_inverse_level(const InvArgs a) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         int r;
-        if (LOSSY) r = __float2int_rn(__fadd_rn(__fadd_rn((float)v[j], 128.0f), 0.01f));  // DecodingEngine.cu:714
-        else r = (int)v[j] + 128;                                                          // :728
+        if (LOSSY) r = __float2int_rn(__fadd_rn(__fadd_rn((float)v[j], (float)a.offset), 0.01f));  // DecodingEngine.cu:714
+        else r = (int)v[j] + a.offset;                                                          // :728
         px[j] = (unsigned char)min(max(r, 0), 255);
       }
       unsigned char* d = static_cast<unsigned char*>(a.dst) + (size_t)frame * a.dst_fstride;
@@ -528,14 +531,14 @@ static size_t ll_offset(int Wa, int Ha, int l) {
 
 bool dwt_forward_fast_ok(const void*, const void*, const void*, bool, int, long long, int, int, int, int);
 int dwt_forward_fast(const void*, bool, long long, int, int, int, int, void*, long long, int, void*, long long, int, int, int, int, bool, float,
-                     bool, int, cudaStream_t, bool rgb, long long comp_stride);
+                     bool, int, cudaStream_t, bool rgb, long long comp_stride, int offset);
 
 bool dwt_inverse_fast_ok(const void*, const void*, const void*, bool, int, long long, int, long long, int, int);
 int dwt_inverse_fast(const int32_t*, long long, int, const void*, long long, int, bool, int, int, void*, bool, long long, int, int, int, bool,
-                     float, int, cudaStream_t, bool rgb, long long comp_stride);
+                     float, int, cudaStream_t, bool rgb, long long comp_stride, int offset);
 
 bool dwt_forward_l12_ok(const void*, const void*, const void*, int, int, int, int, int);
-int dwt_forward_l12(const uint8_t*, int, int, int, int, void*, long long, void*, long long, int, bool, float, bool, int, cudaStream_t);
+int dwt_forward_l12(const uint8_t*, int, int, int, int, void*, long long, void*, long long, int, bool, float, bool, int, cudaStream_t, int offset);
 
 // PCS_DWT_FUSE = 0: per-level kernels of this file only; 1: streaming kernels of dwt_fast.cu, one level per launch;
 // 2 (default): levels 1+2 of u8 frames in one launch (dwt_fused.cu), the deeper levels through the streaming kernels
@@ -556,14 +559,14 @@ static int fuse_mode() {
 // colour transform in its load (streaming kernel only: the caller checks dwt_forward_rgb_ok first).
 static int dwt_forward_levels(const uint8_t* d_px, void* d_coeff, void* d_scratch, int W, int H, int Wa, int Ha, int wl,
                               bool lossy, float qs, bool out_int, int frames, int lfirst, int llast, cudaStream_t st,
-                              const void* tplane = nullptr, bool rgb_px = false) {
+                              const void* tplane = nullptr, bool rgb_px = false, int offset = 128) {
   const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl);
   int first = lfirst;
   // levels 1+2 of u8 frames in one launch: the LL1 plane stays on chip (dwt_fused.cu)
   if (fuse_mode() == 2 && first == 1 && llast >= 2 && !tplane && !rgb_px && S % 4 == 0) {
     void* ll2 = wl == 2 ? nullptr : static_cast<char*>(d_scratch) + ll_offset(Wa, Ha, 2) * 4;
     if (dwt_forward_l12_ok(d_px, d_coeff, ll2, W, H, Wa, Ha, wl)) {
-      int rc = dwt_forward_l12(d_px, W, H, Wa, Ha, d_coeff, (long long)A, ll2, (long long)S, wl, lossy, qs, out_int, frames, st);
+      int rc = dwt_forward_l12(d_px, W, H, Wa, Ha, d_coeff, (long long)A, ll2, (long long)S, wl, lossy, qs, out_int, frames, st, offset);
       if (rc) return rc;
       first = 3;
     }
@@ -580,7 +583,7 @@ static int dwt_forward_levels(const uint8_t* d_px, void* d_coeff, void* d_scratc
     if (!dwt_forward_fast_ok(src, d_coeff, ll, u8, sp, sfs, H, Wc, Hc, lv)) break;
     if (S % 4) break;
     int rc = dwt_forward_fast(src, u8, sfs, sp, H, Wc, Hc, d_coeff, (long long)A, Wa, ll, (long long)S, Wa >> (l + lv - 1), l, lv, wl, lossy,
-                              qs, out_int, frames, st, u8 && rgb_px, (long long)W * H);
+                              qs, out_int, frames, st, u8 && rgb_px, (long long)W * H, offset);
     if (rc) return rc;
     first = l + lv;
   }
@@ -605,7 +608,7 @@ static int dwt_forward_levels(const uint8_t* d_px, void* d_coeff, void* d_scratc
     a.ll_fstride = a.last ? (long long)A : (long long)S; a.ll_pitch = a.last ? Wa : (a.Wc >> 1);
     a.out_vec = (a.Wc % 4 == 0) && (S % 2 == 0) && (ll_offset(Wa, Ha, l) % 2 == 0);
     a.q_ll = kQStep[l - 1][0]; a.q_hl = kQStep[l - 1][1]; a.q_lh = kQStep[l - 1][2]; a.q_hh = kQStep[l - 1][3];
-    a.qs = qs;
+    a.qs = qs; a.offset = offset;
     a.nstrips = (a.Wc + kStrip - 1) / kStrip;
     a.rp = rows_per_warp(a.Hc >> 1, a.nstrips, frames);
     a.nchunks = ((a.Hc >> 1) + a.rp - 1) / a.rp;
@@ -632,7 +635,7 @@ static int dwt_forward_levels(const uint8_t* d_px, void* d_coeff, void* d_scratc
 // inverse colour transform in its store (streaming kernel only: the caller checks dwt_inverse_rgb_ok first).
 static int dwt_inverse_levels(const int32_t* d_q, uint8_t* d_px, void* d_scratch, int W, int H, int Wa, int Ha, int wl, bool lossy,
                               float qs, bool flat_crop, int frames, int lhigh, int llow, cudaStream_t st, void* tplane = nullptr,
-                              bool rgb_px = false) {
+                              bool rgb_px = false, int offset = 128) {
   const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl);
   for (int l = lhigh; l >= llow; --l) {
     InvArgs a{};
@@ -657,12 +660,12 @@ static int dwt_inverse_levels(const int32_t* d_q, uint8_t* d_px, void* d_scratch
     }
     a.r_ll = 1.0f / kQStep[l - 1][0]; a.r_hl = 1.0f / kQStep[l - 1][1];
     a.r_lh = 1.0f / kQStep[l - 1][2]; a.r_hh = 1.0f / kQStep[l - 1][3];
-    a.rqs = 1.0f / qs;
+    a.rqs = 1.0f / qs; a.offset = offset;
     if (fuse_mode() > 0 && S % 4 == 0 && !(px_out && flat_crop && W != Wa) &&
         dwt_inverse_fast_ok(d_q, a.first ? nullptr : a.ll, a.dst, px_out, a.dst_pitch, a.dst_fstride, a.ll_pitch, a.ll_fstride, a.Wc, a.Hc)) {
       const bool rgb = px_out && rgb_px;
       int rc = dwt_inverse_fast(d_q, (long long)A, Wa, a.first ? nullptr : a.ll, a.ll_fstride, a.ll_pitch, a.first != 0, a.Wc, a.Hc, a.dst, px_out,
-                                a.dst_fstride, a.dst_pitch, H, l, lossy, qs, rgb ? frames / 3 : frames, st, rgb, (long long)W * H);
+                                a.dst_fstride, a.dst_pitch, H, l, lossy, qs, rgb ? frames / 3 : frames, st, rgb, (long long)W * H, offset);
       if (rc) return rc;
       continue;
     }
@@ -688,13 +691,13 @@ static int dwt_inverse_levels(const int32_t* d_q, uint8_t* d_px, void* d_scratch
 // levels 1+2 where the fused kernel of dwt_fused.cu applies); nothing synchronises the host.
 // ---------------------------------------------------------------------------------------------
 int dwt_forward(const uint8_t* d_px, void* d_coeff, void* d_scratch, int W, int H, int Wa, int Ha, int wl, bool lossy, float qs,
-                bool out_int, int frames, cudaStream_t st) {
-  return dwt_forward_levels(d_px, d_coeff, d_scratch, W, H, Wa, Ha, wl, lossy, qs, out_int, frames, 1, wl, st);
+                bool out_int, int frames, cudaStream_t st, int offset) {
+  return dwt_forward_levels(d_px, d_coeff, d_scratch, W, H, Wa, Ha, wl, lossy, qs, out_int, frames, 1, wl, st, nullptr, false, offset);
 }
 
 int dwt_inverse(const int32_t* d_q, uint8_t* d_px, void* d_scratch, int W, int H, int Wa, int Ha, int wl, bool lossy, float qs,
-                bool flat_crop, int frames, cudaStream_t st) {
-  return dwt_inverse_levels(d_q, d_px, d_scratch, W, H, Wa, Ha, wl, lossy, qs, flat_crop, frames, wl, 1, st);
+                bool flat_crop, int frames, cudaStream_t st, int offset) {
+  return dwt_inverse_levels(d_q, d_px, d_scratch, W, H, Wa, Ha, wl, lossy, qs, flat_crop, frames, wl, 1, st, nullptr, false, offset);
 }
 
 

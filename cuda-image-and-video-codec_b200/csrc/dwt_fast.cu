@@ -39,6 +39,7 @@ struct FastFwdArgs {
   int nW1, ls1, nW2, ls2;                                   // row-variant tiling of the reference, per level (9/7 only)
   int nstrips, nchunks, rp;                                 // rp: row pairs per chunk (multiple of 4)
   long long comp_stride;                                    // RGB input: bytes between the R, G and B planes of a frame
+  int offset;                                               // u8 input: level shift 2^(bps-1), 0 for signed samples
 };
 
 
@@ -144,7 +145,7 @@ __device__ __forceinline__ void fwd_item(const FastFwdArgs& a, const int strip, 
       unpack8(*reinterpret_cast<const uint2*>(&ringp[2][slot][r][lane][0]), cb);
       rgb_component(comp, cr, cg, cb, v);
     } else {
-      unpack8(*reinterpret_cast<const uint2*>(&ring[slot][r][lane][0]), v);
+      unpack8(*reinterpret_cast<const uint2*>(&ring[slot][r][lane][0]), v, a.offset);
     }
   };
   auto load_row = [&](int y) -> RowT {
@@ -182,7 +183,8 @@ __device__ __forceinline__ void fwd_item(const FastFwdArgs& a, const int strip, 
       unpack8(__ldg(reinterpret_cast<const uint2*>(p + 2 * a.comp_stride)), cb);
       rgb_component(comp, cr, cg, cb, r);
     } else {
-      unpack8(load_row(2 * ms), r);
+      if constexpr (SRC_U8) unpack8(load_row(2 * ms), r, a.offset);
+      else unpack8(load_row(2 * ms), r);
     }
     v1.init(r);
   }
@@ -302,6 +304,7 @@ struct FastInvArgs {
   void* dst; long long dst_fstride; int dst_pitch;         // scratch plane (T) or the u8 frame
   int H;                                                   // u8 output: rows >= H are padding and are not stored
   float r[4], rqs;                                         // reciprocal quantiser steps LL, HL, LH, HH and 1/qs
+  int offset;                                              // u8 output: level shift added back before the clamp
   int nstrips, nchunks, rp;
 };
 
@@ -412,16 +415,17 @@ __global__ void __launch_bounds__(128, PCS_INV_MINB) dwt_inverse_fast_kernel(con
     if constexpr (DST_U8) {
       if (y >= a.H) return;
       unsigned b[8];
-      if constexpr (LOSSY) {  // clamp(rn((v + 128) + 0.01)), DecodingEngine.cu:714
+      if constexpr (LOSSY) {  // clamp(rn((v + offset) + 0.01)), DecodingEngine.cu:714
+        const float foff = (float)a.offset;
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
           float t0, t1;
-          upk(add2(add2(pk(v[j], v[j + 1]), pk(128.0f, 128.0f)), pk(0.01f, 0.01f)), t0, t1);
+          upk(add2(add2(pk(v[j], v[j + 1]), pk(foff, foff)), pk(0.01f, 0.01f)), t0, t1);
           b[j] = sat_u8(t0); b[j + 1] = sat_u8(t1);
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) b[j] = (unsigned)min(max(v[j] + 128, 0), 255);  // :728
+        for (int j = 0; j < 8; ++j) b[j] = (unsigned)min(max(v[j] + a.offset, 0), 255);  // :728
       }
       uint2 w;
       w.x = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
@@ -571,11 +575,11 @@ bool dwt_forward_fast_ok(const void* src, const void* d_coeff, const void* ll, b
 // `levels` (1 or 2) levels of the forward transform, starting at 1-based level `level`, in one launch.
 int dwt_forward_fast(const void* src, bool src_u8, long long src_fstride, int src_pitch, int H, int Wc, int Hc, void* d_coeff,
                      long long out_fstride, int pitch, void* d_ll, long long ll_fstride, int ll_pitch, int level, int levels, int wl,
-                     bool lossy, float qs, bool out_int, int frames, cudaStream_t st, bool rgb, long long comp_stride) {
+                     bool lossy, float qs, bool out_int, int frames, cudaStream_t st, bool rgb, long long comp_stride, int offset) {
   // rgb: src = planar u8 RGB frames (src_fstride per FRAME, comp_stride between colour planes), `frames` counts
   // component planes (3 per frame) and the colour transform is fused into the load (one level only)
   FastFwdArgs a{};
-  a.comp_stride = comp_stride;
+  a.comp_stride = comp_stride; a.offset = offset;
   a.src = src; a.src_fstride = src_fstride; a.src_pitch = src_pitch; a.H = src_u8 ? H : Hc; a.Wc = Wc; a.Hc = Hc;
   a.out = d_coeff; a.out_fstride = out_fstride; a.pitch = pitch;
   a.ll = d_ll; a.ll_fstride = ll_fstride; a.ll_pitch = ll_pitch;
@@ -622,11 +626,11 @@ bool dwt_inverse_fast_ok(const void* q, const void* ll, const void* dst, bool ds
 
 int dwt_inverse_fast(const int32_t* d_q, long long q_fstride, int pitch, const void* ll, long long ll_fstride, int ll_pitch, bool first,
                      int Wc, int Hc, void* dst, bool dst_u8, long long dst_fstride, int dst_pitch, int H, int level, bool lossy, float qs,
-                     int frames, cudaStream_t st, bool rgb, long long comp_stride) {
+                     int frames, cudaStream_t st, bool rgb, long long comp_stride, int offset) {
   // rgb (dst_u8 only): dst = planar u8 RGB frames (dst_fstride per FRAME, comp_stride between colour planes), `frames`
   // counts frames, d_q / ll hold three component planes per frame
   FastInvArgs a{};
-  a.comp_stride = comp_stride;
+  a.comp_stride = comp_stride; a.offset = offset;
   a.q = d_q; a.q_fstride = q_fstride; a.pitch = pitch;
   a.ll = ll; a.ll_fstride = ll_fstride; a.ll_pitch = ll_pitch; a.first = first;
   a.Wc = Wc; a.Hc = Hc; a.dst = dst; a.dst_fstride = dst_fstride; a.dst_pitch = dst_pitch; a.H = dst_u8 ? H : Hc;

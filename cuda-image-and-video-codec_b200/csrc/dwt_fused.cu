@@ -51,6 +51,7 @@ struct FusedArgs {
   float q1[4], q2[4], qs;                             // quantiser steps of levels 1 / 2: LL, HL, LH, HH
   int nW1, ls1, nW2, ls2;                             // row-variant tiling of the reference per level (9/7 only)
   int nctax, nchunks, rp;                             // rp: level-1 row pairs per chunk (multiple of 4)
+  int offset;                                         // level shift 2^(bps-1), 0 for signed samples
 };
 
 // ---- mbarrier / TMA (PTX; SASS: SYNCS.*, UTMALDG) ----------------------------------------------------------------
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
     {
       T r[8];
       const int cl = min(max(c0, 0), Wc - 8);  // lanes outside the image read inside it; their values are never used
-      unpack8(__ldg(reinterpret_cast<const uint2*>(a.src + (size_t)frame * a.src_fstride + (size_t)row_index(2 * ms) * a.src_pitch + cl)), r);
+      unpack8(__ldg(reinterpret_cast<const uint2*>(a.src + (size_t)frame * a.src_fstride + (size_t)row_index(2 * ms) * a.src_pitch + cl)), r, a.offset);
       v1.init(r);
     }
     int ls = 0; bool lap0 = true;  // ring slot of the next LL1 row; first lap: the slots are free
@@ -225,10 +226,10 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
       // the folded loads, so no explicit rule in the vertical steps).
       const int prA = ms + 2 * j - VP::kDelay;
       T xo[8], x2[8], loA[8], hiA[8], loB[8], hiB[8];
-      unpack8(ra, xo); unpack8(rb, x2);
+      unpack8(ra, xo, a.offset); unpack8(rb, x2, a.offset);
       if constexpr (LOSSY) v97_step_mixed<8>(v1, xo, x2, loA, hiA);
       else v1.step(xo, x2, false, loA, hiA);
-      unpack8(rc, xo); unpack8(rd, x2);
+      unpack8(rc, xo, a.offset); unpack8(rd, x2, a.offset);
       if constexpr (LOSSY) v97_step_mixed<8>(v1, xo, x2, loB, hiB);
       else v1.step(xo, x2, false, loB, hiB);
       if constexpr (LOSSY) {
@@ -356,7 +357,7 @@ bool dwt_forward_l12_ok(const void* d_px, const void* d_coeff, const void* ll2, 
 
 // Levels 1 and 2 of `frames` u8 frames in one launch.  ll2: scratch plane that receives LL2 (ignored when wl == 2).
 int dwt_forward_l12(const uint8_t* d_px, int W, int H, int Wa, int Ha, void* d_coeff, long long out_fstride, void* ll2, long long ll_fstride,
-                    int wl, bool lossy, float qs, bool out_int, int frames, cudaStream_t st) {
+                    int wl, bool lossy, float qs, bool out_int, int frames, cudaStream_t st, int offset) {
   alignas(64) CUtensorMap tmap4, tmap1;
   const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)frames};
   const cuuint64_t gstride[2] = {(cuuint64_t)W, (cuuint64_t)W * H};
@@ -369,7 +370,7 @@ int dwt_forward_l12(const uint8_t* d_px, int W, int H, int Wa, int Ha, void* d_c
   }
   FusedArgs a{};
   a.src = d_px; a.src_fstride = (long long)W * H; a.src_pitch = W;
-  a.H = H; a.Wc = Wa; a.Hc = Ha;
+  a.H = H; a.Wc = Wa; a.Hc = Ha; a.offset = offset;
   a.out = d_coeff; a.out_fstride = out_fstride; a.pitch = Wa;
   a.ll = ll2; a.ll_fstride = ll_fstride; a.ll_pitch = Wa >> 2;
   a.last = wl == 2;

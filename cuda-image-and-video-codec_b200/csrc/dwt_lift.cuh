@@ -341,8 +341,10 @@ template <int N> struct VSel<true, N> { using type = V97<N>; using T = float; };
 
 // 8 pixels of a u8 row -> T (px - 128; for 5/3 the shift is applied to the LL output instead, which is
 // exact because every high-pass step is shift-invariant and the low-pass steps carry the offset through)
-__device__ __forceinline__ void unpack8(uint2 p, float (&v)[8]) {
-  const f2 C2 = pk(-8388736.0f, -8388736.0f);  // 2^23 + b - (2^23 + 128), exact
+// `offset` = the level shift 2^(bps-1) (128 for 8-bit samples, 0 for signed input; Engines/CodingEngine.cu:581-588)
+__device__ __forceinline__ void unpack8(uint2 p, float (&v)[8], int offset = 128) {
+  const float c = -(8388608.0f + (float)offset);  // (2^23 + b) - (2^23 + offset), exact for offset <= 2^15
+  const f2 C2 = pk(c, c);
 #pragma unroll
   for (int j = 0; j < 4; j += 2) {
     upk(add2(pk(__uint_as_float(__byte_perm(p.x, 0x4B000000u, 0x7540u + j)), __uint_as_float(__byte_perm(p.x, 0x4B000000u, 0x7541u + j))), C2),
@@ -351,11 +353,11 @@ __device__ __forceinline__ void unpack8(uint2 p, float (&v)[8]) {
         v[4 + j], v[5 + j]);
   }
 }
-__device__ __forceinline__ void unpack8(uint2 p, int (&v)[8]) {
+__device__ __forceinline__ void unpack8(uint2 p, int (&v)[8], int offset = 128) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    v[j] = (int)__byte_perm(p.x, 0u, 0x4440u + j) - 128;
-    v[4 + j] = (int)__byte_perm(p.y, 0u, 0x4440u + j) - 128;
+    v[j] = (int)__byte_perm(p.x, 0u, 0x4440u + j) - offset;
+    v[4 + j] = (int)__byte_perm(p.y, 0u, 0x4440u + j) - offset;
   }
 }
 

@@ -35,6 +35,11 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
+def set_sample_offset(offset: int = 128):
+    """Level shift of the grey path: 2^(bps-1) (default 128), or 0 for -signedOrUnsigned 1."""
+    lib().pcso_set_sample_offset(int(offset))
+
+
 def adapted_dims(W, H):
     wa, ha = C.c_int(), C.c_int()
     lib().pcso_adapted_dims(W, H, C.byref(wa), C.byref(ha))
@@ -198,6 +203,15 @@ def encode_frame(img: np.ndarray, wl: int, lossy: bool, qs: float, lut: Lut, fir
     cs, sizes = bpc_encode(q, wl, lut, k=k)
     hdr = header_pack(W, H, wl, lossy, qs, frames, k=k) if first else None
     return bsb_pack(cs, sizes, hdr)
+
+
+def encode_frame_params(img: np.ndarray, wl: int, lossy: bool, qs: float, lut: Lut, **hdr) -> np.ndarray:
+    """encode_frame with extra header fields (bitDepth, bps, isSigned ...); the level shift itself is set_sample_offset()."""
+    H, W = img.shape
+    px = pad_mirror(img)
+    q = truncate(dwt97_forward(px, wl, qs)) if lossy else dwt53_forward(px, wl)
+    cs, sizes = bpc_encode(q, wl, lut)
+    return bsb_pack(cs, sizes, header_pack(W, H, wl, lossy, qs, 0, **hdr))
 
 
 def decode_frame(stream: np.ndarray, Wa: int, Ha: int, wl: int, lossy: bool, qs: float, lut: Lut, k: float = 0.0) -> np.ndarray:

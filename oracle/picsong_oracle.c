@@ -169,10 +169,15 @@ static const float QSTEP[10][4] = {
 
 /* Forward 5/3: u8 pixels (W_a x H_a, already padded) -> int32 Mallat plane out[0..A).
  * Level shift Engines/CodingEngine.cu:581-588 (px - 2^(bps-1)); host loop DWTGenerator.cu:1268-1342. */
+/* Level shift of the grey path: 2^(bps-1) for unsigned samples (-bps, default 8), 0 for -signedOrUnsigned 1
+ * (Engines/CodingEngine.cu:581-588,644-656; Engines/DecodingEngine.cu:706-729).  Samples are bytes whatever -bps says
+ * (IO/IOManager.ipp:72-112 reads unsigned char), and the decoder clamps to [0, 255] in either case. */
+static int g_sample_offset = 128;
+void pcso_set_sample_offset(int offset) { g_sample_offset = offset; }
 static int dwt53_forward_core(int Wa, int Ha, int wl, int32_t* out);
 int pcso_dwt53_forward(const uint8_t* px, int Wa, int Ha, int wl, int32_t* out) {
   size_t A = (size_t)Wa * Ha;
-  for (size_t i = 0; i < A; i++) out[i] = (int32_t)px[i] - 128;
+  for (size_t i = 0; i < A; i++) out[i] = (int32_t)px[i] - g_sample_offset;
   return dwt53_forward_core(Wa, Ha, wl, out);
 }
 /* RGB path: the plane is already level-shifted and colour-transformed (Engines/CodingEngine.cu:613) */
@@ -228,7 +233,7 @@ static int dwt53_inverse_core(const int32_t* q, int Wa, int Ha, int wl, uint8_t*
   for (size_t i = 0; i < A; i++) {
     if (iout) iout[i] = w[i];
     if (px) {
-      int32_t v = w[i] + 128;
+      int32_t v = w[i] + g_sample_offset;
       px[i] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
     }
   }
@@ -242,7 +247,7 @@ static int dwt53_inverse_core(const int32_t* q, int Wa, int Ha, int wl, uint8_t*
 static int dwt97_forward_core(int Wa, int Ha, int wl, float qs, float* out);
 int pcso_dwt97_forward(const uint8_t* px, int Wa, int Ha, int wl, float qs, float* out) {
   size_t A = (size_t)Wa * Ha;
-  for (size_t i = 0; i < A; i++) out[i] = (float)((int)px[i] - 128);
+  for (size_t i = 0; i < A; i++) out[i] = (float)((int)px[i] - g_sample_offset);
   return dwt97_forward_core(Wa, Ha, wl, qs, out);
 }
 /* RGB path: colour-transformed float plane in (Engines/CodingEngine.cu:693) */
@@ -309,7 +314,7 @@ int pcso_dwt97_inverse(const int32_t* q, int Wa, int Ha, int wl, float qs, uint8
   for (size_t i = 0; i < A; i++) {
     if (fout) fout[i] = w[i];
     if (!px) continue;
-    float r = nearbyintf((w[i] + 128.0f) + 0.01f); /* __float2int_rn: round half to even */
+    float r = nearbyintf((w[i] + (float)g_sample_offset) + 0.01f); /* __float2int_rn: round half to even */
     r = r > 255.0f ? 255.0f : r;
     r = r < 0.0f ? 0.0f : r;
     px[i] = (uint8_t)r;

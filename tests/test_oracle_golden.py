@@ -239,3 +239,44 @@ def test_oracle_matches_reference_coder_on_rare_branches(lut_root):
         seen_expansion |= bool((sz == 4096).any())
         seen_high |= bool(np.abs(q.astype(np.int64)).max() >= 1 << 16 and (sz < 4096).any())
     assert seen_expansion and seen_high
+
+
+F4_CASES = [("bps16_ll", 0, 16, 0), ("bps12_ll", 0, 12, 0), ("signed_ll", 0, 8, 1), ("signed_q1", 1, 8, 1), ("bps16_q1", 1, 16, 0)]
+
+
+def test_oracle_bit_depth_and_signed_input_match_reference(lut_root):
+    """-bps 16 / 12 and -signedOrUnsigned 1: only the level shift changes (2^(bps-1), or 0 for signed
+    samples).  Oracle == the reference executable's streams and decoded pixels (tests/golden/f4_ref.npz); for the lossy
+    -bps 16 run within the 9/7 tolerance (see tests/golden/ref_runs/README.md)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "f4_ref.npz"))
+    img = g["input"]
+    H, W = img.shape
+    try:
+        for name, lossy, bps, signed in F4_CASES:
+            lut = O.lut_load(f"{lut_root}/{'n1_lossy' if lossy else 'n1_lossless'}/", 3)
+            O.set_sample_offset(0 if signed else 1 << (bps - 1))
+            px = O.pad_mirror(img)
+            q = O.truncate(O.dwt97_forward(px, 3, 1.0)) if lossy else O.dwt53_forward(px, 3)
+            cs, sz = O.bpc_encode(q, 3, lut)
+            st = O.bsb_pack(cs, sz, O.header_pack(W, H, 3, lossy, 1.0, 0, bitDepth=bps, bps=bps, isSigned=signed))
+            ref = g[name + ".stream"]
+            assert np.array_equal(st[:9], ref[:9]), name                      # header words carry bps / signedness
+            if name != "bps16_q1":
+                assert np.array_equal(st, ref), name
+                assert np.array_equal(O.decode_frame(ref, W, H, 3, bool(lossy), 1.0, lut), g[name + ".dec"]), name
+            else:
+                rcs, rsz, _ = O.bsb_unpack(ref, (W // 64) * (H // 64))
+                rq = O.bpc_decode(rcs, rsz, W, H, 3, lut)
+                assert np.abs(rq - q).max() <= 1 and (rq != q).mean() <= 1e-4
+                # pixels: the reference's -use_fast_math divisions at magnitude 32768 (one fp32 ulp = 0.004) move ~0.7 % of the
+                # roundings by one grey level; PSNR against the input is the north_star criterion (within 0.01 dB)
+                mine, theirs = O.decode_frame(ref, W, H, 3, True, 1.0, lut), g[name + ".dec"]
+                d = np.abs(mine.astype(int) - theirs.astype(int))
+                assert d.max() <= 1 and (d != 0).mean() <= 1e-2
+                psnr = lambda a: 10 * np.log10(255.0 ** 2 / np.mean((a.astype(np.float64) - img) ** 2))  # noqa: E731
+                assert abs(psnr(mine) - psnr(theirs)) <= 0.01
+            if not lossy:
+                assert np.array_equal(g[name + ".dec"], img)
+    finally:
+        O.set_sample_offset(128)
