@@ -226,7 +226,12 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    cfg = WORKLOADS[args.workload]
+    cfg = dict(WORKLOADS[args.workload])
+    if args.wl:
+        cfg["wl"] = args.wl
+        cfg["desc"] += f" [wl={args.wl}]"
+    if args.cb_length == 32:
+        cfg["desc"] += " [64x32 codeblocks]"
     W, H, wl, lossy, qs, B = cfg["W"], cfg["H"], cfg["wl"], cfg["lossy"], cfg["qs"], cfg["batch"]
     strong = cfg["scaling"] == "strong"
     rgb = bool(cfg.get("rgb"))
@@ -235,7 +240,13 @@ def run_ours(args):
     lroot = materialize_luts()
     lut = codec.load_lut(f"{lroot}/{cfg['lut']}/", wl, rgb=rgb)
     os.environ["PCS_STAGE_TIMING"] = "1"
-    cd = codec.Codec(codec.Params(W, H, wl, bool(lossy), qs, frames=hdr_frames, max_batch=B, rgb=rgb), lut)
+    try:
+        cd = codec.Codec(codec.Params(W, H, wl, bool(lossy), qs, frames=hdr_frames, max_batch=B, rgb=rgb,
+                                      flags=codec.PCS_F_CB_LENGTH_32 if args.cb_length == 32 else 0), lut)
+    except codec.PcsError as e:  # e.g. 64x32 codeblocks at a depth where a level of the (32-row padded) frame has odd height
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "unit": "Mpix/s", "n_gpus": world, "config": {"workload": cfg["desc"]}, "unavailable": str(e)}))
+        return
     first, count = sharding.partition(total, world, rank)            # this rank's frames of the device-resident leg
     if count == 0:
         raise SystemExit(f"rank {rank}: no frames to code ({total} frames over {world} ranks)")
@@ -567,11 +578,17 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    cfg = WORKLOADS[args.workload]
+    cfg = dict(WORKLOADS[args.workload])
+    if args.wl:
+        cfg["wl"] = args.wl
+        cfg["desc"] += f" [wl={args.wl}]"
+    if args.cb_length == 32:
+        cfg["desc"] += " [64x32 codeblocks]"
     W, H, wl, lossy, qs = cfg["W"], cfg["H"], cfg["wl"], cfg["lossy"], cfg["qs"]
     video = args.workload == "cfg4"
     total = cfg["frames"]
-    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    # 64x32 codeblocks: the reference rebuilt with -DCBLOCK_LENGTH=32 (oracle/build_ref.sh with REF_SUFFIX=_cb32)
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness" + ("_cb32" if args.cb_length == 32 else ""))
     base = {"metric": METRIC, "unit": "Mpix/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
             "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32" if lossy else "int32", "data": "synthetic", "impl": "reference",
             "config": {"workload": cfg["desc"], "frames_total": total}}
@@ -599,6 +616,8 @@ def run_reference(args):
         print(json.dumps({**base, "unavailable": f"ref_harness failed rc={p.returncode}: {p.stdout[-200:]}"}))
         return
     r = json.load(open(js))
+    if r.get("roundtrip_bad"):
+        base["reference_roundtrip_bad_pixels"] = r["roundtrip_bad"]  # the reference itself does not reproduce its input here
     ms = r["enc_dev_ms"] + r["dec_dev_ms"]  # per frame
     e2e_ms = r["enc_e2e_ms"] + r["dec_e2e_ms"]
     v = W * H / 1e6 / (ms * 1e-3)
@@ -611,7 +630,7 @@ def run_reference(args):
             "stage_ms_per_frame": {"enc_dwt": r["enc_dwt_ms"], "enc_bpc_bsb": r["enc_bpc_bsb_ms"], "dec_bpc_bsb": r["dec_bpc_bsb_ms"], "dec_dwt": r["dec_dwt_ms"]},
             "harness": {"value": v, "e2e": e2e_v, "sample": f"{sample} frames x {iters - 1} timed passes, one frame per call, default stream"}}
     # (2) video: the reference executable with its own worker-stream concurrency on the whole video
-    cli = reference_cli_sweep(cfg, lutdir, raw, total, tmp) if video else None
+    cli = reference_cli_sweep(cfg, lutdir, raw, total, tmp) if (video and args.cb_length != 32) else None
     if cli:
         line["cli"] = cli
         if cli["best"]:
@@ -683,6 +702,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--rounds", type=int, default=4, help="multi-GPU e2e: rounds the frames are dealt in (sharding.encode_rounds)")
+    ap.add_argument("--cb-length", type=int, default=64, choices=[64, 32],
+                    help="codeblock length: 64, or 32 = the reference's -DCBLOCK_LENGTH=32 build (BASELINE configs[2] sweep)")
+    ap.add_argument("--wl", type=int, default=0, help="override the workload's wavelet levels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-continuity", action="store_true", help="skip the extra configs[1] measurement of the default run")
     args = ap.parse_args()

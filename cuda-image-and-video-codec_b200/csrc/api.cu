@@ -38,7 +38,7 @@ int bpc_encode(const void*, bool, uint16_t*, int32_t*, const BpcArgs&, cudaStrea
 int bpc_decode(const uint16_t*, const int32_t*, int32_t*, const BpcArgs&, cudaStream_t);
 int bpc_encode_k(const void*, bool, uint16_t*, int32_t*, const BpcKArgs&, cudaStream_t);
 int bpc_decode_k(const uint16_t*, const int32_t*, int32_t*, const BpcKArgs&, cudaStream_t);
-int export_ref_codestream(const uint16_t*, const int32_t*, int32_t*, long long, cudaStream_t);
+int export_ref_codestream(const uint16_t*, const int32_t*, int32_t*, long long, int, cudaStream_t);
 int bsb_pack(const uint16_t*, const int32_t*, uint16_t*, long long*, void*, const BsbArgs&, cudaStream_t);
 int bsb_unpack(const uint16_t*, const long long*, uint16_t*, int32_t*, void*, const BsbArgs&, cudaStream_t);
 size_t bsb_status_bytes(int ncb, int batch);
@@ -50,6 +50,7 @@ using namespace pcs;
 struct pcs_ctx {
   pcs_params p;
   int Wa, Ha, ncb, ncomp;          // ncomp: planes per frame (1 grey, 3 RGB)
+  int cb_rows = 64;                // codeblock length: 64, or 32 with PCS_F_CB_LENGTH_32
   int offset = 128;                // level shift of the grey path: 2^(bit_depth - 1), 0 for signed samples
   size_t A, scratch_elems, max_words, frame_px;  // max_words: per PLANE; frame_px = ncomp * W * H
   std::vector<int32_t> lut;
@@ -95,7 +96,7 @@ BpcArgs bpc_args(const pcs_ctx* c, int frames, int comp) {
   a.Wa = c->Wa; a.Ha = c->Ha; a.nbx = c->Wa / kCB; a.ncb = c->ncb; a.wl = c->p.wavelet_levels;
   a.nBp = c->p.lut_header[0]; a.nSub = c->p.lut_header[1]; a.nrows = c->nrows; a.prec = c->p.lut_header[5];
   a.total_cb = c->ncb * frames; a.A = (long long)c->A;
-  a.pstep = c->ncomp; a.pfirst = comp;
+  a.pstep = c->ncomp; a.pfirst = comp; a.cb_rows = c->cb_rows;
   a.tab4 = c->d_tab4 + (size_t)comp * c->nrows;
   return a;
 }
@@ -103,7 +104,7 @@ BpcArgs bpc_args(const pcs_ctx* c, int frames, int comp) {
 // `planes` consecutive planes starting at global plane index `first_plane`
 BsbArgs bsb_args(const pcs_ctx* c, int planes, int first_plane) {
   BsbArgs a{};
-  a.ncb = c->ncb; a.batch = planes; a.first_frame_index = first_plane;
+  a.ncb = c->ncb; a.batch = planes; a.first_frame_index = first_plane; a.cbw = kCB * c->cb_rows;
   // stills: component i is coded with iter = i, video: every component of frame f with iter = f
   // (CodingEngine.cu:620,700 vs :790,902) -> the three planes of video frame 0 all carry the header
   // (PCS_F_STILLS: the caller codes stills although `frames`, a header-only value, is > 0)
@@ -269,8 +270,12 @@ int32_t pcs_create(const pcs_params* params, pcs_ctx** out) {
   // `-components 3` is accepted as well.  Grey: one component.
   if (p.is_rgb ? (p.components != 1 && p.components != 3) : p.components != 1) return PCS_E_UNSUPPORTED;
   if (!p.lut || p.lut_len <= 0) return PCS_E_LUT;
+  // codeblock length 32 = the reference rebuilt with -DCBLOCK_LENGTH=32 (BPC/BPCEngine.cuh:33-36): the frame is padded to a
+  // multiple of 32 rows instead of 64 (fixImageProportions is called with CBLOCK_LENGTH).  k = 0 coder only.
+  const int cb_rows = (p.flags & PCS_F_CB_LENGTH_32) ? 32 : 64;
+  if (cb_rows == 32 && p.k_factor > 0) return PCS_E_UNSUPPORTED;
   int Wa, Ha;
-  pcs_adapted_dims(p.width, p.height, &Wa, &Ha);
+  pcs_adapted_dims_cb(p.width, p.height, cb_rows, &Wa, &Ha);
   // every level input must have even size
   if (((Wa >> (p.wavelet_levels - 1)) & 1) || ((Ha >> (p.wavelet_levels - 1)) & 1) || (Wa >> p.wavelet_levels) < 1 ||
       (Ha >> p.wavelet_levels) < 1)
@@ -282,7 +287,8 @@ int32_t pcs_create(const pcs_params* params, pcs_ctx** out) {
   c->p.lut = c->lut.data();
   c->ncomp = p.is_rgb ? 3 : 1;
   c->offset = offset;
-  c->Wa = Wa; c->Ha = Ha; c->A = (size_t)Wa * Ha; c->ncb = (Wa / kCB) * (Ha / kCB);
+  c->cb_rows = cb_rows;
+  c->Wa = Wa; c->Ha = Ha; c->A = (size_t)Wa * Ha; c->ncb = (Wa / kCB) * (Ha / cb_rows);
   c->max_words = c->A + c->ncb + 10;
   c->frame_px = (size_t)c->ncomp * p.width * p.height;
   c->scratch_elems = dwt_scratch_elems(Wa, Ha, p.wavelet_levels);
@@ -392,7 +398,7 @@ int32_t pcs_bsb_unpack(pcs_ctx* c, const uint16_t* d_in, const int64_t* d_off, u
 
 int32_t pcs_export_ref_codestream(pcs_ctx* c, const uint16_t* d_cw, const int32_t* d_sizes, int32_t* d_ref, int32_t batch, void* st) {
   CHECK_BATCH(c, batch);
-  return export_ref_codestream(d_cw, d_sizes, d_ref, (long long)c->A * batch * c->ncomp, (cudaStream_t)st);
+  return export_ref_codestream(d_cw, d_sizes, d_ref, (long long)c->A * batch * c->ncomp, kCB * c->cb_rows, (cudaStream_t)st);
 }
 
 int32_t pcs_encode_device(pcs_ctx* c, const uint8_t* d_px, int32_t batch, int32_t first, uint16_t* d_stream, int64_t* d_off, void* stv) {

@@ -137,6 +137,7 @@ struct EncState { unsigned lower, size, slot, count, lt; };
 #ifndef PCS_ENC_PTX
 #define PCS_ENC_PTX 1
 #endif
+template <int WORDS>  // words a codeblock owns (64 x rows): slots are clamped to WORDS - 2 (BPCEngine.cu:382 for 64 rows)
 __device__ __forceinline__ void enc_step(unsigned abw, unsigned anbw, unsigned bitm, unsigned p, EncState& c,
                                          unsigned short* out1, unsigned prec) {
 #if PCS_ENC_PTX
@@ -166,12 +167,12 @@ __device__ __forceinline__ void enc_step(unsigned abw, unsigned anbw, unsigned b
       "@pab add.u32 %0, %0, r;\n\t"
       "@panb mov.u32 %1, q;\n\t"
       "setp.eq.and.u32 pst, %1, 0, pact;\n\t"
-      "min.u32 sl, %2, 4094;\n\t"
+      "min.u32 sl, %2, %11;\n\t"
       "mad.wide.u32 ad, sl, 2, %10;\n\t"
       "@pst st.global.u16 [ad], %0;\n\t"
       "}"
       : "+r"(c.lower), "+r"(c.size), "+r"(c.slot), "+r"(c.count)
-      : "r"(abw), "r"(anbw), "r"(bitm), "r"(c.lt), "r"(p), "r"(prec), "l"(out1)
+      : "r"(abw), "r"(anbw), "r"(bitm), "r"(c.lt), "r"(p), "r"(prec), "l"(out1), "n"(WORDS - 2)
       : "memory");
 #else
   const bool ab = (abw & bitm) != 0, anb = (anbw & bitm) != 0;
@@ -184,7 +185,7 @@ __device__ __forceinline__ void enc_step(unsigned abw, unsigned anbw, unsigned b
   const unsigned q = (c.size * p) >> prec;
   if (ab) { c.size = c.size - q - 1u; c.lower = c.lower + q + 1u; }
   if (anb) c.size = q;
-  if (act && c.size == 0) out1[min(c.slot, 4094u)] = (unsigned short)c.lower;
+  if (act && c.size == 0) out1[min(c.slot, (unsigned)(WORDS - 2))] = (unsigned short)c.lower;
 #endif
 }
 
@@ -196,7 +197,7 @@ constexpr int kSppUnroll = PCS_SPP_UNROLL;
 #ifndef PCS_ENC_MINB
 #define PCS_ENC_MINB 5
 #endif
-template <typename T>
+template <typename T, int ROWS>  // ROWS: codeblock length, 64 or 32 (the reference's CBLOCK_LENGTH, BPC/BPCEngine.cuh:33-36)
 __global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* __restrict__ coeff, unsigned short* __restrict__ cw,
                                                         int* __restrict__ sizes, const BpcArgs p) {
   // transposed magnitude bits of the warp's codeblock: word [32*half + k][lane], k < 16: plane k of the
@@ -206,17 +207,18 @@ __global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* 
   const int w = blockIdx.x * (blockDim.x >> 5) + wib;
   if (w >= p.total_cb) return;
   const int frame = (w / p.ncb) * p.pstep + p.pfirst, cb = w % p.ncb;
+  constexpr int kHalves = ROWS / 32, kWords = kCB * ROWS;  // 32-row halves of a block; words a block owns
   const int bx = cb % p.nbx, by = cb / p.nbx;
-  const T* src = coeff + (size_t)frame * p.A + (size_t)(by * kCB) * p.Wa + bx * kCB + 2 * lane;
+  const T* src = coeff + (size_t)frame * p.A + (size_t)(by * ROWS) * p.Wa + bx * kCB + 2 * lane;
   const size_t blk = (size_t)frame * p.ncb + cb;  // index of this block in the codeword / size arrays
-  unsigned short* out = cw + blk * kCBWords;
+  unsigned short* out = cw + blk * kWords;
   unsigned (*pl)[32] = s_pl[wib];
 
   // pass 0: MSB of the block, sign masks (BPCEngine.cu:41-63,176-192), bit-plane transposition
   u64 g0 = 0, g1 = 0;
   unsigned ormag = 0;
 #pragma unroll 1
-  for (int h = 0; h < 2; ++h) {
+  for (int h = 0; h < kHalves; ++h) {
     unsigned wv[32], sg0 = 0, sg1 = 0;
 #pragma unroll
     for (int i = 31; i >= 0; --i) {
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* 
     return;
   }
   __syncwarp();
-  int row = lane_group(bx * kCB + 2 * lane, by * kCB, p) * p.nBp + MSB;  // initializeLUTPointers :329-350
+  int row = lane_group(bx * kCB + 2 * lane, by * ROWS, p) * p.nBp + MSB;  // initializeLUTPointers :329-350
   const u64 Lg = shfl_up64(g1, lane), Rg = shfl_down64(g0, lane);       // neighbour lanes' signs
   unsigned short* const out1 = out + 1;
   const unsigned prec = (unsigned)p.prec;
@@ -249,12 +251,12 @@ __global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* 
   for (int bp = MSB; bp >= 0; --bp, --row) {
     u64 B0, B1;
     if (bp < 16) {
-      B0 = (u64)pl[bp][lane] | ((u64)pl[32 + bp][lane] << 32);
-      B1 = (u64)pl[16 + bp][lane] | ((u64)pl[48 + bp][lane] << 32);
+      B0 = (u64)pl[bp][lane]; B1 = (u64)pl[16 + bp][lane];
+      if constexpr (kHalves == 2) { B0 |= (u64)pl[32 + bp][lane] << 32; B1 |= (u64)pl[48 + bp][lane] << 32; }
     } else {  // |q| >= 2^16: not reachable from 8-bit images with the shipped quantiser; generic slow path
       B0 = 0; B1 = 0;
 #pragma unroll 4
-      for (int i = 0; i < kCB; ++i) {
+      for (int i = 0; i < ROWS; ++i) {
         int a, b; load2<T>(src + (size_t)i * p.Wa, a, b);
         B0 |= (u64)((umag(a) >> bp) & 1u) << i; B1 |= (u64)((umag(b) >> bp) & 1u) << i;
       }
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* 
 
     // ---- significance propagation pass: rows in order, column 0 then column 1 (BPCEngine.cu:770-843) ----
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < kHalves; ++h) {
       const int sh = 32 * h;
       const unsigned A0 = ~(unsigned)(s0 >> sh), A1 = ~(unsigned)(s1 >> sh);
       const unsigned anyact = __reduce_or_sync(kFull, A0 | A1);  // rows of this half in which some lane codes a symbol
@@ -337,10 +339,10 @@ __global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* 
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const unsigned bitm = 1u << (4 * t + q);
-            enc_step(ab0, an0, bitm, byte_of(P0[q], t), ac, out1, prec);
-            if (new0 & bitm) enc_step(gp0, gn0, bitm, byte_of(S0[q], t), ac, out1, prec);
-            enc_step(ab1, an1, bitm, byte_of(P1[q], t), ac, out1, prec);
-            if (new1 & bitm) enc_step(gp1, gn1, bitm, byte_of(S1[q], t), ac, out1, prec);
+            enc_step<kWords>(ab0, an0, bitm, byte_of(P0[q], t), ac, out1, prec);
+            if (new0 & bitm) enc_step<kWords>(gp0, gn0, bitm, byte_of(S0[q], t), ac, out1, prec);
+            enc_step<kWords>(ab1, an1, bitm, byte_of(P1[q], t), ac, out1, prec);
+            if (new1 & bitm) enc_step<kWords>(gp1, gn1, bitm, byte_of(S1[q], t), ac, out1, prec);
           }
         }
       }
@@ -348,7 +350,7 @@ __global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* 
     // ---- magnitude refinement pass: samples significant before this plane (BPCEngine.cu:726-736,1249-1261);
     //      only rows in which some lane refines are visited ----
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < kHalves; ++h) {
       const int sh = 32 * h;
       const unsigned r0m = (unsigned)(s0 >> sh), r1m = (unsigned)(s1 >> sh), b0 = (unsigned)(B0 >> sh), b1 = (unsigned)(B1 >> sh);
       const unsigned r0b = r0m & b0, r0n = r0m & ~b0, r1b = r1m & b1, r1n = r1m & ~b1;
@@ -356,22 +358,22 @@ __global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* 
       while (U) {
         const unsigned bitm = U & (0u - U);  // lowest row in which some lane refines
         U ^= bitm;
-        enc_step(r0b, r0n, bitm, pref, ac, out1, prec);
-        enc_step(r1b, r1n, bitm, pref, ac, out1, prec);
+        enc_step<kWords>(r0b, r0n, bitm, pref, ac, out1, prec);
+        enc_step<kWords>(r1b, r1n, bitm, pref, ac, out1, prec);
       }
     }
     s0 = a0; s1 = a1;
   }
-  out1[min(ac.slot, 4094u)] = (unsigned short)ac.lower;  // flush (BPCEngine.cu:1719)
-  const int size = (int)min(ac.count, 4095u) + 1;         // :2010
+  out1[min(ac.slot, (unsigned)(kWords - 2))] = (unsigned short)ac.lower;  // flush (BPCEngine.cu:1719)
+  const int size = (int)min(ac.count, (unsigned)(kWords - 1)) + 1;         // :2010
   __syncwarp();
-  if (size == kCBWords) {
+  if (size == kWords) {
     // expansion fallback (BPCEngine.cu:2015-2024,1904-1912): raw low 16 bits of (|q|<<1 | sign), lane-major
     __threadfence_block();
-    for (int i = 0; i < kCB; ++i) {
+    for (int i = 0; i < ROWS; ++i) {
       int a, b; load2<T>(src + (size_t)i * p.Wa, a, b);
-      out[lane * 2 * kCB + 2 * i] = (unsigned short)(((umag(a) << 1) | (a < 0 ? 1u : 0u)) & 0xFFFFu);
-      out[lane * 2 * kCB + 2 * i + 1] = (unsigned short)(((umag(b) << 1) | (b < 0 ? 1u : 0u)) & 0xFFFFu);
+      out[lane * 2 * ROWS + 2 * i] = (unsigned short)(((umag(a) << 1) | (a < 0 ? 1u : 0u)) & 0xFFFFu);
+      out[lane * 2 * ROWS + 2 * i + 1] = (unsigned short)(((umag(b) << 1) | (b < 0 ? 1u : 0u)) & 0xFFFFu);
     }
   } else if (lane == 0) {
     out[0] = (unsigned short)MSB;
@@ -422,7 +424,7 @@ struct DecState { unsigned lower, size, slot, count, code, lt; };
       "popc.b32 pm, m;\n\t"                                      \
       "@pneed add.u32 %2, %3, pre;\n\t"                          \
       "add.u32 %3, %3, pm;\n\t"                                  \
-      "min.u32 sl, %2, 4094;\n\t"                                \
+      "min.u32 sl, %2, %12;\n\t"                                 \
       "mad.wide.u32 ad, sl, 2, %11;\n\t"                         \
       "@pneed ld.global.nc.u16 %4, [ad];\n\t"                    \
       "@pneed mov.u32 %1, 0xFFFF;\n\t"                           \
@@ -437,20 +439,20 @@ struct DecState { unsigned lower, size, slot, count, code, lt; };
       "@pnb mov.u32 %1, q;\n\t"                                  \
       "selp.u32 %5, 1, 0, pb;\n\t"                               \
       "}"
-template <int PREC>
+template <int PREC, int WORDS>
 __device__ __forceinline__ unsigned dec_step(unsigned actw, unsigned bitm, unsigned p, DecState& c,
                                              const unsigned short* in1, unsigned prec) {
   unsigned b;
   if constexpr (PREC == 7) {
     asm volatile(PCS_DEC_STEP_ASM("shr.u32 q, r, 7;\n\t")
                  : "+r"(c.lower), "+r"(c.size), "+r"(c.slot), "+r"(c.count), "+r"(c.code), "=r"(b)
-                 : "r"(actw), "r"(bitm), "r"(c.lt), "r"(p), "r"(prec), "l"(in1)
+                 : "r"(actw), "r"(bitm), "r"(c.lt), "r"(p), "r"(prec), "l"(in1), "n"(WORDS - 2)
                  : "memory");
     return b;
   }
   asm volatile(PCS_DEC_STEP_ASM("shr.u32 q, r, %10;\n\t")
                : "+r"(c.lower), "+r"(c.size), "+r"(c.slot), "+r"(c.count), "+r"(c.code), "=r"(b)
-               : "r"(actw), "r"(bitm), "r"(c.lt), "r"(p), "r"(prec), "l"(in1)
+               : "r"(actw), "r"(bitm), "r"(c.lt), "r"(p), "r"(prec), "l"(in1), "n"(WORDS - 2)
                : "memory");
   return b;
 }
@@ -465,7 +467,7 @@ __device__ __forceinline__ unsigned lds_u8(unsigned addr) {
   return v;
 }
 
-template <int PREC>
+template <int PREC, int ROWS>
 __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const unsigned short* __restrict__ cw, const int* __restrict__ sizes,
                                                                       int* __restrict__ q, const BpcArgs p) {
   // decoded magnitude bit planes, same layout as the encoder's: word [32*half + k][lane], k < 16: plane k of
@@ -492,33 +494,34 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
   const int w = blockIdx.x * (blockDim.x >> 5) + wib;
   if (w >= p.total_cb) return;
   const int frame = (w / p.ncb) * p.pstep + p.pfirst, cb = w % p.ncb;
+  constexpr int kHalves = ROWS / 32, kWords = kCB * ROWS;
   const int bx = cb % p.nbx, by = cb / p.nbx;
-  int* dst = q + (size_t)frame * p.A + (size_t)(by * kCB) * p.Wa + bx * kCB + 2 * lane;
+  int* dst = q + (size_t)frame * p.A + (size_t)(by * ROWS) * p.Wa + bx * kCB + 2 * lane;
   const size_t blk = (size_t)frame * p.ncb + cb;
-  const unsigned short* in = cw + blk * kCBWords;
+  const unsigned short* in = cw + blk * kWords;
   const int size = sizes[blk];
   const int MSB = in[0];
   unsigned (*pl)[32] = s_pl[wib];
 
-  if (size == kCBWords) {  // raw block (BPCEngine.cu:2197-2200,1914-1922,94-111)
-    for (int i = 0; i < kCB; ++i) {
-      const unsigned a = in[lane * 2 * kCB + 2 * i], b = in[lane * 2 * kCB + 2 * i + 1];
+  if (size == kWords) {  // raw block (BPCEngine.cu:2197-2200,1914-1922,94-111)
+    for (int i = 0; i < ROWS; ++i) {
+      const unsigned a = in[lane * 2 * ROWS + 2 * i], b = in[lane * 2 * ROWS + 2 * i + 1];
       const int va = (int)(a >> 1), vb = (int)(b >> 1);
       *reinterpret_cast<int2*>(dst + (size_t)i * p.Wa) = make_int2((a & 1u) ? -va : va, (b & 1u) ? -vb : vb);
     }
     return;
   }
   if (MSB >= 23) {  // 32 = all-zero block; 23..31 cannot be produced by the coder (|q| < 2^23, Annex B.2) -> zeros
-    for (int i = 0; i < kCB; ++i) *reinterpret_cast<int2*>(dst + (size_t)i * p.Wa) = make_int2(0, 0);
+    for (int i = 0; i < ROWS; ++i) *reinterpret_cast<int2*>(dst + (size_t)i * p.Wa) = make_int2(0, 0);
     return;
   }
   const bool hi_planes = MSB >= 16;  // rare: planes >= 16 are accumulated in the output directly
   if (hi_planes)
-    for (int i = 0; i < kCB; ++i) *reinterpret_cast<int2*>(dst + (size_t)i * p.Wa) = make_int2(0, 0);
+    for (int i = 0; i < ROWS; ++i) *reinterpret_cast<int2*>(dst + (size_t)i * p.Wa) = make_int2(0, 0);
 #pragma unroll
   for (int k = 0; k < 64; ++k) pl[k][lane] = 0u;
 
-  int row = lane_group(bx * kCB + 2 * lane, by * kCB, p) * p.nBp + MSB;
+  int row = lane_group(bx * kCB + 2 * lane, by * ROWS, p) * p.nBp + MSB;
   const unsigned short* const in1 = in + 1;
   const unsigned prec = (unsigned)p.prec;
   DecState ac; ac.lower = 0; ac.size = 0; ac.slot = 0; ac.count = 0; ac.code = 0; ac.lt = (1u << lane) - 1u;
@@ -545,7 +548,7 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
     // of row i-1, kept pre-shifted to their position in the sign-table index (<< 4 / << 6)
     unsigned pns = 0, pnl = 0, pnr = 0, u0 = 0, u1 = 0;
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < kHalves; ++h) {
       const int sh = 32 * h;
       const unsigned S0 = (unsigned)(s0 >> sh), S1 = (unsigned)(s1 >> sh), G0 = (unsigned)(g0 >> sh), G1 = (unsigned)(g1 >> sh);
       const unsigned A0 = ~S0, A1 = ~S1;
@@ -576,12 +579,12 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
             const unsigned bitm = 1u << qq;
             // ---- column 0 ----
             unsigned ctx = (n0[qq] >> r0) + pnl + pns;  // bits above the nibble are masked at the look-up
-            const unsigned cn0 = dec_step<PREC>(a40, bitm, prob[ctx & 15u], ac, in1, prec);
+            const unsigned cn0 = dec_step<PREC, kWords>(a40, bitm, prob[ctx & 15u], ac, in1, prec);
             unsigned neg0 = (g40 >> qq) & 1u;
             if (__any_sync(kFull, cn0)) {
               // horizontal: static (sign of the static sum), up: row i-1 now, down: static
               const unsigned sc = lds_u8(sgn0 + (((c0[qq] >> r0) & 15u) | u0));
-              const unsigned sym = dec_step<PREC>(cn0, 1u, prob[12u + (sc >> 1)], ac, in1, prec);
+              const unsigned sym = dec_step<PREC, kWords>(cn0, 1u, prob[12u + (sc >> 1)], ac, in1, prec);
               if (cn0) neg0 = (sym ^ sc) & 1u;  // BPCEngine.cu:583-589
             }
             nb0 = __funnelshift_r(nb0, cn0, 1); ng0 = __funnelshift_r(ng0, cn0 & neg0, 1);
@@ -592,11 +595,11 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
             const unsigned cnr = rv >> 2;
             // ---- column 1 ----
             ctx = (n1[qq] >> r0) + pns + pnr + cn0 + cnr;
-            const unsigned cn1 = dec_step<PREC>(a41, bitm, prob[ctx & 15u], ac, in1, prec);
+            const unsigned cn1 = dec_step<PREC, kWords>(a41, bitm, prob[ctx & 15u], ac, in1, prec);
             unsigned neg1 = (g41 >> qq) & 1u;
             if (__any_sync(kFull, cn1)) {
               const unsigned sc = lds_u8(sgn0 + 64u + (((c1[qq] >> r0) & 3u) | (cur0 << 2) | ((rv & 3u) << 4) | u1));
-              const unsigned sym = dec_step<PREC>(cn1, 1u, prob[12u + (sc >> 1)], ac, in1, prec);
+              const unsigned sym = dec_step<PREC, kWords>(cn1, 1u, prob[12u + (sc >> 1)], ac, in1, prec);
               if (cn1) neg1 = (sym ^ sc) & 1u;
             }
             nb1 = __funnelshift_r(nb1, cn1, 1); ng1 = __funnelshift_r(ng1, cn1 & neg1, 1);
@@ -618,7 +621,7 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
     }
     // ---- magnitude refinement pass (BPCEngine.cu:742-762,1267-1279): only rows in which some lane refines ----
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < kHalves; ++h) {
       const int sh = 32 * h;
       const unsigned r0m = (unsigned)(s0 >> sh), r1m = (unsigned)(s1 >> sh);
       unsigned nb0 = 0, nb1 = 0;
@@ -626,8 +629,8 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
       while (U) {
         const unsigned bitm = U & (0u - U);  // lowest row in which some lane refines
         U ^= bitm;
-        nb0 |= (0u - dec_step<PREC>(r0m, bitm, pref, ac, in1, prec)) & bitm;
-        nb1 |= (0u - dec_step<PREC>(r1m, bitm, pref, ac, in1, prec)) & bitm;
+        nb0 |= (0u - dec_step<PREC, kWords>(r0m, bitm, pref, ac, in1, prec)) & bitm;
+        nb1 |= (0u - dec_step<PREC, kWords>(r1m, bitm, pref, ac, in1, prec)) & bitm;
       }
       B0 |= (u64)nb0 << sh; B1 |= (u64)nb1 << sh;
     }
@@ -636,7 +639,7 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
       pl[bp][lane] = (unsigned)B0; pl[32 + bp][lane] = (unsigned)(B0 >> 32);
       pl[16 + bp][lane] = (unsigned)B1; pl[48 + bp][lane] = (unsigned)(B1 >> 32);
     } else {
-      for (int i = 0; i < kCB; ++i) {
+      for (int i = 0; i < ROWS; ++i) {
         int2* d = reinterpret_cast<int2*>(dst + (size_t)i * p.Wa);
         int2 v = *d;
         v.x |= (int)((B0 >> i) & 1ull) << bp; v.y |= (int)((B1 >> i) & 1ull) << bp;
@@ -647,7 +650,7 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
   __syncwarp();
   // assemble magnitudes from the bit planes (transpose back), apply signs and write (BPCEngine.cu:94-111)
 #pragma unroll 1
-  for (int h = 0; h < 2; ++h) {
+  for (int h = 0; h < kHalves; ++h) {
     unsigned wv[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) wv[k] = pl[32 * h + k][lane];
@@ -978,10 +981,10 @@ __global__ void __launch_bounds__(32 * kKWarps) bpc_decode_k_kernel(const unsign
 }
 
 // Debug/parity export: the reference's int32 sparse `DCodeStreamValues` layout, -1 filled.
-__global__ void export_ref_cs_kernel(const unsigned short* cw, const int* sizes, int* ref, long long n) {
+__global__ void export_ref_cs_kernel(const unsigned short* cw, const int* sizes, int* ref, long long n, int cbw) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int cb = (int)(i / kCBWords), j = (int)(i % kCBWords);
+  const int cb = (int)(i / cbw), j = (int)(i % cbw);
   ref[i] = j < sizes[cb] ? (int)cw[i] : -1;
 }
 
@@ -989,16 +992,26 @@ __global__ void export_ref_cs_kernel(const unsigned short* cw, const int* sizes,
 
 int bpc_encode(const void* d_coeff, bool is_float, uint16_t* d_cw, int32_t* d_sizes, const BpcArgs& a, cudaStream_t st) {
   const int blocks = (a.total_cb + 3) / 4;
-  if (is_float) bpc_encode_kernel<float><<<blocks, 128, 0, st>>>(static_cast<const float*>(d_coeff), d_cw, d_sizes, a);
-  else bpc_encode_kernel<int><<<blocks, 128, 0, st>>>(static_cast<const int*>(d_coeff), d_cw, d_sizes, a);
+  if (a.cb_rows == 32) {
+    if (is_float) bpc_encode_kernel<float, 32><<<blocks, 128, 0, st>>>(static_cast<const float*>(d_coeff), d_cw, d_sizes, a);
+    else bpc_encode_kernel<int, 32><<<blocks, 128, 0, st>>>(static_cast<const int*>(d_coeff), d_cw, d_sizes, a);
+  } else {
+    if (is_float) bpc_encode_kernel<float, 64><<<blocks, 128, 0, st>>>(static_cast<const float*>(d_coeff), d_cw, d_sizes, a);
+    else bpc_encode_kernel<int, 64><<<blocks, 128, 0, st>>>(static_cast<const int*>(d_coeff), d_cw, d_sizes, a);
+  }
   ++g_launches;
   return (int)cudaGetLastError();
 }
 
 int bpc_decode(const uint16_t* d_cw, const int32_t* d_sizes, int32_t* d_q, const BpcArgs& a, cudaStream_t st) {
   const int blocks = (a.total_cb + 3) / 4;
-  if (a.prec == 7) bpc_decode_kernel<7><<<blocks, 128, 0, st>>>(d_cw, d_sizes, d_q, a);
-  else bpc_decode_kernel<0><<<blocks, 128, 0, st>>>(d_cw, d_sizes, d_q, a);
+  if (a.cb_rows == 32) {
+    if (a.prec == 7) bpc_decode_kernel<7, 32><<<blocks, 128, 0, st>>>(d_cw, d_sizes, d_q, a);
+    else bpc_decode_kernel<0, 32><<<blocks, 128, 0, st>>>(d_cw, d_sizes, d_q, a);
+  } else {
+    if (a.prec == 7) bpc_decode_kernel<7, 64><<<blocks, 128, 0, st>>>(d_cw, d_sizes, d_q, a);
+    else bpc_decode_kernel<0, 64><<<blocks, 128, 0, st>>>(d_cw, d_sizes, d_q, a);
+  }
   ++g_launches;
   return (int)cudaGetLastError();
 }
@@ -1018,8 +1031,8 @@ int bpc_decode_k(const uint16_t* d_cw, const int32_t* d_sizes, int32_t* d_q, con
   return (int)cudaGetLastError();
 }
 
-int export_ref_codestream(const uint16_t* d_cw, const int32_t* d_sizes, int32_t* d_ref, long long n, cudaStream_t st) {
-  export_ref_cs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_cw, d_sizes, d_ref, n);
+int export_ref_codestream(const uint16_t* d_cw, const int32_t* d_sizes, int32_t* d_ref, long long n, int cbw, cudaStream_t st) {
+  export_ref_cs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_cw, d_sizes, d_ref, n, cbw);
   ++g_launches;
   return (int)cudaGetLastError();
 }

@@ -111,9 +111,9 @@ __global__ void __launch_bounds__(256) bsb_pack_kernel(const unsigned short* __r
     const int f = (int)(g / n), cb = (int)(g - (long long)f * n);
     const int sz = sizes[g];
     const long long data = s_excl[k] + (long long)f * (n + 10) + 9 + 2LL * n - cb;
-    const unsigned short* src = cw + (size_t)g * kCBWords;
-    // src[sz] is readable: sz <= 4095 leaves it inside the block, and a block of 4096 words ends on a 32-bit boundary
-    warp_copy_u16(out + data, src + 1, sz - 1, sz < kCBWords, lane);
+    const unsigned short* src = cw + (size_t)g * a.cbw;
+    // src[sz] is readable: sz < cbw leaves it inside the block, and a block of cbw words ends on a 32-bit boundary
+    warp_copy_u16(out + data, src + 1, sz - 1, sz < a.cbw, lane);
   }
   // The tile holding block 0 of frame f knows S_f: it writes that frame's 9-word header, all n
   // (MSB, size) pairs (BitStreamBuilder.cu:122-127) and the previous frame's trailing 0xFFFF.
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) bsb_pack_kernel(const unsigned short* __r
     if (threadIdx.x == 0) { frame_off[f] = S; if (f > 0) out[S - 1] = 0xFFFFu; }
     if (threadIdx.x < 9) out[S + threadIdx.x] = (a.first_frame_index + f < a.hdr_count) ? a.hdr[threadIdx.x] : (unsigned short)0xFFFFu;
     for (int cb = threadIdx.x; cb < n; cb += blockDim.x) {
-      out[S + 9 + 2 * cb] = cw[(size_t)(g + cb) * kCBWords];
+      out[S + 9 + 2 * cb] = cw[(size_t)(g + cb) * a.cbw];
       out[S + 10 + 2 * cb] = (unsigned short)sizes[g + cb];
     }
   }
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) bsb_unpack_kernel(const unsigned short* _
   if (warp == 0) {
     const int cb = cb0 + lane;
     int sz = cb < n ? (int)fin[10 + 2 * cb] : 0;
-    if (cb < n) sz = min(max(sz, 1), kCBWords);  // malformed streams cannot index outside a block
+    if (cb < n) sz = min(max(sz, 1), a.cbw);  // malformed streams cannot index outside a block
     int incl = sz;
     for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
     const long long base = lookback(status, tile, f * tpf, __shfl_sync(0xffffffffu, incl, 31), lane);
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) bsb_unpack_kernel(const unsigned short* _
     const int sz = s_sz[k];
     const long long g = (long long)f * n + cb;
     const long long data = 9 + 2LL * n + s_excl[k] - cb;
-    unsigned short* dst = cw + (size_t)g * kCBWords;
+    unsigned short* dst = cw + (size_t)g * a.cbw;
     if (lane == 0) { dst[0] = fin[9 + 2 * cb]; sizes[g] = sz; }
     // words the (possibly malformed) frame really holds; the rest of the block reads as 0xFFFF
     const int have = (int)min((long long)(sz - 1), max(0LL, E - S - data));

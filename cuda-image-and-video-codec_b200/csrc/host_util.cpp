@@ -19,6 +19,14 @@ void pcs_adapted_dims(int32_t width, int32_t height, int32_t* adapted_w, int32_t
   *adapted_h = (height + PCS_CB - 1) / PCS_CB * PCS_CB;
 }
 
+// The same with the codeblock length the reference was built with (CBLOCK_LENGTH, BPC/BPCEngine.cuh:33-36): the height
+// is padded to a multiple of the block length, the width always to 64.
+void pcs_adapted_dims_cb(int32_t width, int32_t height, int32_t cb_rows, int32_t* adapted_w, int32_t* adapted_h) {
+  const int r = cb_rows == 32 ? 32 : PCS_CB;
+  *adapted_w = (width + PCS_CB - 1) / PCS_CB * PCS_CB;
+  *adapted_h = (height + r - 1) / r * r;
+}
+
 int32_t pcs_lut_size(const int32_t h[8], int32_t wl) {
   const int nBp = h[0], nSub = h[1], cR = h[2], cG = h[3], cS = h[4];
   return (nSub * wl + 1) * nBp * (cR + cS + cG);

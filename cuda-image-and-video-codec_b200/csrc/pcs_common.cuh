@@ -35,6 +35,7 @@ extern unsigned long long g_launches;  // host-side counter of kernel launches (
 struct BpcArgs {
   int Wa, Ha, nbx, ncb, wl, nBp, nSub, nrows, prec, total_cb;
   int pstep, pfirst;               // plane of the launch's frame f = f * pstep + pfirst (RGB: one launch per component, pstep = 3)
+  int cb_rows;                     // codeblock length: 64, or 32 (PCS_F_CB_LENGTH_32)
   long long A;
   const uint4* tab4;               // [nrows] probability rows of this launch's component, as bytes: x = sig ctx 0..3, y = sig ctx 4..7, z = sig ctx 8 | ref << 8, w = sign ctx 0..3
 };
@@ -54,6 +55,7 @@ struct BsbArgs {
   int batch;              // frames
   int first_frame_index;  // global index of frame 0 of this batch
   int hdr_count;          // global frames 0 .. hdr_count-1 carry the header (1; RGB video: 3, BitStreamBuilder.cpp:104 with iter = frame)
+  int cbw;                // words a codeblock owns in the sparse layout: 64 x codeblock length
   unsigned short hdr[9];
 };
 

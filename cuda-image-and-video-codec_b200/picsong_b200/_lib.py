@@ -25,6 +25,7 @@ class PcsParams(C.Structure):
 _VP, _I32, _I64, _U16P = C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_uint16)
 SYMBOLS = {
     "pcs_adapted_dims": (None, [_I32, _I32, C.POINTER(_I32), C.POINTER(_I32)]),
+    "pcs_adapted_dims_cb": (None, [_I32, _I32, _I32, C.POINTER(_I32), C.POINTER(_I32)]),
     "pcs_lut_load": (_I32, [C.c_char_p, _I32, C.POINTER(_I32), C.POINTER(_I32), _I32]),
     "pcs_lut_size": (_I32, [C.POINTER(_I32), _I32]),
     "pcs_lut_load_component": (_I32, [C.c_char_p, _I32, _I32, C.POINTER(_I32), C.POINTER(_I32), _I32]),

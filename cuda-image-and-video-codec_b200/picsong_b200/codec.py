@@ -14,6 +14,8 @@ import numpy as np
 from . import _lib
 
 PCS_F_REF_FLAT_CROP = 1
+PCS_F_STILLS = 2
+PCS_F_CB_LENGTH_32 = 4
 
 
 class PcsError(RuntimeError):
@@ -29,9 +31,9 @@ def _check(rc: int, what: str, ctx=None):
         raise PcsError(f"{what}: {kind} {rc} {msg}")
 
 
-def adapted_dims(width: int, height: int):
+def adapted_dims(width: int, height: int, cb_rows: int = 64):
     wa, ha = C.c_int32(), C.c_int32()
-    _lib.load().pcs_adapted_dims(width, height, C.byref(wa), C.byref(ha))
+    _lib.load().pcs_adapted_dims_cb(width, height, cb_rows, C.byref(wa), C.byref(ha))
     return wa.value, ha.value
 
 
@@ -124,7 +126,9 @@ class Codec:
         self.ncb = int(self.lib.pcs_frame_codeblocks(ctx))
         self.max_words = int(self.lib.pcs_frame_max_stream_words(ctx))  # per frame (all its planes)
         self.planes = int(self.lib.pcs_frame_planes(ctx))               # 1 grey, 3 RGB
-        self.Wa, self.Ha = adapted_dims(params.width, params.height)
+        self.cb_rows = 32 if (params.flags & PCS_F_CB_LENGTH_32) else 64
+        self.Wa, self.Ha = adapted_dims(params.width, params.height, self.cb_rows)
+        self.cbw = 64 * self.cb_rows                                    # words a codeblock owns in the sparse layout
 
     def close(self):
         if getattr(self, "ctx", None):
@@ -171,7 +175,7 @@ class Codec:
     def bpc_encode(self, coeff):
         t = self.torch
         B = coeff.shape[0] // self.planes
-        cw = t.empty((B * self.planes, self.ncb, 4096), dtype=t.int16, device=coeff.device)
+        cw = t.empty((B * self.planes, self.ncb, self.cbw), dtype=t.int16, device=coeff.device)
         sizes = t.empty((B * self.planes, self.ncb), dtype=t.int32, device=coeff.device)
         _check(self.lib.pcs_bpc_encode(self.ctx, self._p(coeff), int(coeff.dtype == t.float32), self._p(cw), self._p(sizes),
                                        B, self._stream()), "pcs_bpc_encode", self.ctx)
@@ -197,7 +201,7 @@ class Codec:
     def bsb_unpack(self, stream, off):
         t = self.torch
         B = (off.numel() - 1) // self.planes
-        cw = t.empty((B * self.planes, self.ncb, 4096), dtype=t.int16, device=stream.device)
+        cw = t.empty((B * self.planes, self.ncb, self.cbw), dtype=t.int16, device=stream.device)
         sizes = t.empty((B * self.planes, self.ncb), dtype=t.int32, device=stream.device)
         _check(self.lib.pcs_bsb_unpack(self.ctx, self._p(stream), self._p(off), self._p(cw), self._p(sizes), B, self._stream()),
                "pcs_bsb_unpack", self.ctx)

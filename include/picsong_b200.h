@@ -47,6 +47,12 @@ enum {
                                   plane 0 carries the header; without the flag frames > 0 means video, where the three
                                   planes of frame 0 all do (CodingEngine.cu:790,902). */
 
+#define PCS_F_CB_LENGTH_32 4u  /* 64 x 32 codeblocks: the reference rebuilt with -DCBLOCK_LENGTH=32 (BPC/BPCEngine.cuh:33-36;
+                                  BASELINE configs[2]'s sweep point).  The frame is padded to a multiple of 32 rows, a block
+                                  owns 2048 words.  k = 0 only.  (The reference build keeps its 4094 / 4095 codeword clamps,
+                                  so it is only defined while no block needs more than 2046 codewords; this library clamps
+                                  at 2046 / 2047 and falls back to the raw dump at 2048 like the 64-row coder does at 4096.) */
+
 typedef struct pcs_ctx pcs_ctx;
 
 /* Mirrors the Engine setters (Engines/Engine.cuh:28-44) + Image fields (Image/Image.hpp:52-62). */
@@ -71,6 +77,8 @@ typedef struct pcs_params {
 
 /* SupportFunctions/AuxiliarFunctions.cpp:22-26 fixImageProportions */
 void pcs_adapted_dims(int32_t width, int32_t height, int32_t* adapted_w, int32_t* adapted_h);
+/* ... with the codeblock length (64 or 32) the height is padded to (see PCS_F_CB_LENGTH_32) */
+void pcs_adapted_dims_cb(int32_t width, int32_t height, int32_t cb_rows, int32_t* adapted_w, int32_t* adapted_h);
 
 /* Engine::initLUT grey/k==0/cp==2 branch (Engines/Engine.cu:101-141) + IOManager::loadLUTHeaders
  * (IO/IOManager.ipp:363-386) + loadLUTUpgraded (:404-612).  `folder` is used as the reference

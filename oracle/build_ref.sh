@@ -19,7 +19,8 @@ if [ ! -d "$SRC" ]; then
   echo "build_ref: $SRC not present (GPU box?) -- keeping prebuilt $OUT" >&2
   exit 0
 fi
-mkdir -p "$OUT/obj"
+OBJ="$OUT/obj${REF_SUFFIX:-}"   # REF_SUFFIX=_cb32 REF_EXTRA_FLAGS=-DCBLOCK_LENGTH=32: the 64x32-codeblock build (BASELINE configs[2] sweep)
+mkdir -p "$OBJ"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-std=c++17 "-gencode=arch=compute_100,code=[sm_100,compute_100]" -rdc=true
        -use_fast_math -lineinfo -w -Xcompiler -fpermissive
@@ -30,7 +31,7 @@ TUS=(Launcher.cu Engines/Engine.cu Engines/CodingEngine.cu Engines/DecodingEngin
 pids=()
 objs=()
 for tu in "${TUS[@]}"; do
-  o="$OUT/obj/$(echo "$tu" | tr '/.' '__').o"
+  o="$OBJ/$(echo "$tu" | tr '/.' '__').o"
   objs+=("$o")
   if [ ! -f "$o" ] || [ "$SRC/$tu" -nt "$o" ] || [ "$HERE/shims/cub_shim.cuh" -nt "$o" ]; then
     "$NVCC" "${FLAGS[@]}" -x cu -dc "$SRC/$tu" -o "$o" &
@@ -41,10 +42,10 @@ for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
 "$NVCC" "-gencode=arch=compute_100,code=[sm_100,compute_100]" -rdc=true "${objs[@]}" -o "$OUT/PICSONG_ref${REF_SUFFIX:-}"
 # Stage-level driver (oracle/ref_harness.cu: our code, includes the reference's headers in place,
 # links the reference's own objects minus Launcher.cu's main).
-"$NVCC" "${FLAGS[@]}" -I "$SRC" -x cu -dc "$HERE/ref_harness.cu" -o "$OUT/obj/ref_harness.o"
+"$NVCC" "${FLAGS[@]}" -I "$SRC" -x cu -dc "$HERE/ref_harness.cu" -o "$OBJ/ref_harness.o"
 hobjs=()
 for o in "${objs[@]}"; do case "$o" in *Launcher_cu.o) ;; *) hobjs+=("$o");; esac; done
-"$NVCC" "-gencode=arch=compute_100,code=[sm_100,compute_100]" -rdc=true "$OUT/obj/ref_harness.o" "${hobjs[@]}" -o "$OUT/ref_harness${REF_SUFFIX:-}"
+"$NVCC" "-gencode=arch=compute_100,code=[sm_100,compute_100]" -rdc=true "$OBJ/ref_harness.o" "${hobjs[@]}" -o "$OUT/ref_harness${REF_SUFFIX:-}"
 # The reference binary needs its probability tables at run time (-LUTFolder); stage the k=0
 # tables beside it (data, git-ignored, travels with oracle/_ref like the binary).
 for d in n1_lossless n1_lossy video_lossless video_lossy; do

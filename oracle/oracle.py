@@ -12,6 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libpicsong_oracle.so")
 CBSZ = 4096
+_cb_rows = 64
 
 
 def build(force: bool = False) -> str:
@@ -33,6 +34,14 @@ def lib():
 
 def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
+
+
+def set_cb_rows(rows: int = 64):
+    """Codeblock length: 64 (default) or 32 = the reference rebuilt with -DCBLOCK_LENGTH=32 (BASELINE configs[2] sweep)."""
+    global CBSZ, _cb_rows
+    lib().pcso_set_cb_rows(int(rows))
+    _cb_rows = 32 if rows == 32 else 64
+    CBSZ = 64 * _cb_rows
 
 
 def set_sample_offset(offset: int = 128):
@@ -129,7 +138,7 @@ def bpc_encode(q: np.ndarray, wl: int, lut: Lut, cb0: int = 0, cb1: int = 0, k: 
     """k > 0: complexity-scalable mode (ENCODER only, lut from lut_load_k); exact for blocks inside one subband."""
     Ha, Wa = q.shape
     q = np.ascontiguousarray(q, dtype=np.int32)
-    ncb = (Wa // 64) * (Ha // 64)
+    ncb = (Wa // 64) * (Ha // _cb_rows)
     cs = np.full(ncb * CBSZ, -1, dtype=np.int32)
     sizes = np.zeros(ncb, dtype=np.int32)
     if k > 0:
@@ -216,7 +225,7 @@ def encode_frame_params(img: np.ndarray, wl: int, lossy: bool, qs: float, lut: L
 
 def decode_frame(stream: np.ndarray, Wa: int, Ha: int, wl: int, lossy: bool, qs: float, lut: Lut, k: float = 0.0) -> np.ndarray:
     """Engines/DecodingEngine.cu:765-859 (grey): unpack -> BPC decode -> inverse DWT -> clamp."""
-    ncb = (Wa // 64) * (Ha // 64)
+    ncb = (Wa // 64) * (Ha // _cb_rows)
     cs, sizes, _ = bsb_unpack(stream, ncb)
     q = bpc_decode(cs, sizes, Wa, Ha, wl, lut, k=k)
     return dwt97_inverse(q, wl, qs) if lossy else dwt53_inverse(q, wl)
@@ -270,7 +279,7 @@ def encode_rgb_frame(rgb: np.ndarray, wl: int, lossy: bool, qs: float, luts, hea
 
 def decode_rgb_frame(streams, Wa: int, Ha: int, wl: int, lossy: bool, qs: float, luts) -> np.ndarray:
     """Engines/DecodingEngine.cu:738-770 + :599-650: three component streams -> u8 (3, Ha, Wa)."""
-    ncb = (Wa // 64) * (Ha // 64)
+    ncb = (Wa // 64) * (Ha // _cb_rows)
     comps = []
     for c in range(3):
         cs, sizes, _ = bsb_unpack(streams[c], ncb)

@@ -20,8 +20,14 @@
 #include <stdlib.h>
 #include <string.h>
 
-#define CB 64            /* BPC/BPCEngine.cuh:29-36  CBLOCK_WIDTH = CBLOCK_LENGTH = 64 */
-#define CBSZ (CB * CB)   /* 4096 words reserved per codeblock in the sparse codestream */
+#define CB 64            /* BPC/BPCEngine.cuh:29-36  CBLOCK_WIDTH = 64 (two columns x 32 lanes: fixed) */
+/* CBLOCK_LENGTH: 64 rows, or 32 when the reference is rebuilt with -DCBLOCK_LENGTH=32 (BPCEngine.cuh:33-36; BASELINE
+ * configs[2]'s sweep point).  With 32 rows the reference still clamps its codeword counter at 4094 / 4095 while a block
+ * owns only 2048 words, so it is only defined while no block needs more than 2046 codewords; tests stay inside that. */
+static int g_cb_rows = 64;
+void pcso_set_cb_rows(int rows) { g_cb_rows = rows == 32 ? 32 : 64; }
+#define CBR g_cb_rows
+#define CBSZ (CB * CBR)  /* words reserved per codeblock in the sparse codestream */
 
 /* ------------------------------------------------------------------------------------------
  * Geometry and padding
@@ -30,7 +36,7 @@
 /* SupportFunctions/AuxiliarFunctions.cpp:22-26 fixImageProportions: pad both dims to x64. */
 void pcso_adapted_dims(int W, int H, int* Wa, int* Ha) {
   *Wa = (int)ceilf((float)W / CB) * CB;
-  *Ha = (int)ceilf((float)H / CB) * CB;
+  *Ha = (int)ceilf((float)H / CBR) * CBR;
 }
 
 /* IO/IOManager.ipp:72-112 loadFrameCAdaptedSizes: edge-inclusive mirror, columns then rows:
@@ -590,7 +596,7 @@ static inline uint32_t ac_decode(cbstate* s, int l, int p) {
  * n[0..7] = up-left, up, up-right, left, right, bottom-left, bottom, bottom-right. */
 static void neighbours(const cbstate* s, int l, int i, int c, uint32_t n[8]) {
   const uint32_t(*S)[2 * CB + 4] = s->S;
-#define AT(lane, row, col) (((row) < 0 || (row) >= CB || (lane) < 0 || (lane) > 31) ? 0u : S[lane][2 * (row) + (col)])
+#define AT(lane, row, col) (((row) < 0 || (row) >= CBR || (lane) < 0 || (lane) > 31) ? 0u : S[lane][2 * (row) + (col)])
   if (c == 0) {
     n[0] = AT(l - 1, i - 1, 1); n[1] = AT(l, i - 1, 0); n[2] = AT(l, i - 1, 1);
     n[3] = AT(l - 1, i, 1);                              n[4] = AT(l, i, 1);
@@ -632,12 +638,12 @@ static int sign_ctx_bulk(uint32_t up, uint32_t left, uint32_t right, uint32_t do
  * :490-516; MRP :1249-1261 + :726-736.  q = coefficient plane (already (int)-truncated for the
  * lossy path), words = this block's 4096-word slot (pre-filled with -1 by the caller, :2431-2440). */
 static int encode_block(const bpc_cfg* cfg, const int32_t* q, int Wa, int Ha, int cb, int32_t* words) {
-  int nbx = Wa / CB, X = (cb % nbx) * CB, Y = (cb / nbx) * CB;
+  int nbx = Wa / CB, X = (cb % nbx) * CB, Y = (cb / nbx) * CBR;
   cbstate* s = (cbstate*)calloc(1, sizeof(cbstate));
   s->words = words; s->prec = cfg->prec;
   uint32_t ormag = 0;
   for (int l = 0; l < 32; l++)
-    for (int i = 0; i < CB; i++)
+    for (int i = 0; i < CBR; i++)
       for (int c = 0; c < 2; c++) {
         int32_t v = q[(size_t)(Y + i) * Wa + X + 2 * l + c];
         uint32_t mag = (uint32_t)(v < 0 ? -(int64_t)v : v);
@@ -667,7 +673,7 @@ static int encode_block(const bpc_cfg* cfg, const int32_t* q, int Wa, int Ha, in
     int bp;
     for (bp = MSB; bp >= consec; bp--) {
       /* ---- SPP ---- */
-      for (int i = 0; i < CB; i++)
+      for (int i = 0; i < CBR; i++)
         for (int c = 0; c < 2; c++) {
           uint32_t act = 0, one = 0, need;
           for (int l = 0; l < 32; l++) {
@@ -698,7 +704,7 @@ static int encode_block(const bpc_cfg* cfg, const int32_t* q, int Wa, int Ha, in
             }
         }
       /* ---- MRP ---- */
-      for (int i = 0; i < CB; i++)
+      for (int i = 0; i < CBR; i++)
         for (int c = 0; c < 2; c++) {
           uint32_t act = 0, need = 0;
           for (int l = 0; l < 32; l++) {
@@ -717,7 +723,7 @@ static int encode_block(const bpc_cfg* cfg, const int32_t* q, int Wa, int Ha, in
       /* ---- bulk pass from plane B = bp down to 0, one coefficient at a time (:1285-1420, :1640-1650): rows in order,
        * column 0 then column 1; context and neighbour snapshot are taken ONCE per coefficient, before its planes ---- */
       const int B = bp;
-      for (int i = 0; i < CB; i++)
+      for (int i = 0; i < CBR; i++)
         for (int c = 0; c < 2; c++) {
           int ctx[32];
           uint32_t any = 0;
@@ -765,7 +771,7 @@ static int encode_block(const bpc_cfg* cfg, const int32_t* q, int Wa, int Ha, in
   int size = s->count + 1; /* :2010 */
   if (size == CBSZ) {      /* expansion fallback :2015-2024, :1904-1912 */
     for (int l = 0; l < 32; l++)
-      for (int k = 0; k < 2 * CB; k++) words[l * 2 * CB + k] = (int32_t)(s->S[l][k] & 0xFFFF);
+      for (int k = 0; k < 2 * CBR; k++) words[l * 2 * CBR + k] = (int32_t)(s->S[l][k] & 0xFFFF);
   }
   free(s);
   return size;
@@ -774,13 +780,13 @@ static int encode_block(const bpc_cfg* cfg, const int32_t* q, int Wa, int Ha, in
 /* One codeblock, decode.  Kernel BPCEngine.cu:2173-2213; Decode :1776-1837; SPP :930-1003 +
  * :558-594; MRP :1267-1279 + :742-762; output :94-111. */
 static void decode_block(const bpc_cfg* cfg, const int32_t* words, int size, int Wa, int Ha, int cb, int32_t* q) {
-  int nbx = Wa / CB, X = (cb % nbx) * CB, Y = (cb / nbx) * CB;
+  int nbx = Wa / CB, X = (cb % nbx) * CB, Y = (cb / nbx) * CBR;
   cbstate* s = (cbstate*)calloc(1, sizeof(cbstate));
   s->words = (int32_t*)words; s->prec = cfg->prec;
   int MSB = words[0];
   if (size == CBSZ) { /* :2197-2200, :1914-1922 copyEntireCodeblock */
     for (int l = 0; l < 32; l++)
-      for (int k = 0; k < 2 * CB; k++) s->S[l][k] = (uint32_t)words[l * 2 * CB + k];
+      for (int k = 0; k < 2 * CBR; k++) s->S[l][k] = (uint32_t)words[l * 2 * CBR + k];
   } else if (MSB != 32) {
     int refP[32], sigP[32], sgnP[32];
     lane_pointers(cfg, X, Y, Wa, Ha, MSB, refP, sigP, sgnP);
@@ -798,7 +804,7 @@ static void decode_block(const bpc_cfg* cfg, const int32_t* words, int size, int
     }
     int bp;
     for (bp = MSB; bp >= consec; bp--) {
-      for (int i = 0; i < CB; i++)
+      for (int i = 0; i < CBR; i++)
         for (int c = 0; c < 2; c++) {
           uint32_t act = 0, one = 0, need = 0;
           for (int l = 0; l < 32; l++) {
@@ -825,7 +831,7 @@ static void decode_block(const bpc_cfg* cfg, const int32_t* words, int size, int
               *w |= sym;
             }
         }
-      for (int i = 0; i < CB; i++)
+      for (int i = 0; i < CBR; i++)
         for (int c = 0; c < 2; c++) {
           uint32_t act = 0, need = 0;
           for (int l = 0; l < 32; l++) {
@@ -850,7 +856,7 @@ static void decode_block(const bpc_cfg* cfg, const int32_t* words, int size, int
     if (bp >= 0) { /* bulk pass, inverse of the one in encode_block (:1487-1530, :1535-1650) */
       const int B = bp;
       const uint32_t mask0 = mask;
-      for (int i = 0; i < CB; i++)
+      for (int i = 0; i < CBR; i++)
         for (int c = 0; c < 2; c++) {
           int ctx[32];
           uint32_t any = 0;
@@ -900,7 +906,7 @@ static void decode_block(const bpc_cfg* cfg, const int32_t* words, int size, int
     }
   }
   for (int l = 0; l < 32; l++)
-    for (int i = 0; i < CB; i++)
+    for (int i = 0; i < CBR; i++)
       for (int c = 0; c < 2; c++) {
         uint32_t w = s->S[l][2 * i + c];
         int32_t v = (int32_t)((w & 0xFFFFFF) >> 1);
@@ -920,7 +926,7 @@ static void mkcfg(bpc_cfg* c, const int hdr[8], int wl, const int32_t* lut, int 
 int pcso_bpc_encode(const int32_t* q, int Wa, int Ha, int wl, const int hdr[8], const int32_t* lut,
                     int lutN, int32_t* cs, int32_t* sizes, int cb0, int cb1) {
   bpc_cfg cfg; mkcfg(&cfg, hdr, wl, lut, lutN);
-  int nCB = (Wa / CB) * (Ha / CB);
+  int nCB = (Wa / CB) * (Ha / CBR);
   if (cb1 <= 0 || cb1 > nCB) cb1 = nCB;
   for (int cb = cb0; cb < cb1; cb++) {
     int32_t* w = cs + (size_t)cb * CBSZ;
@@ -935,7 +941,7 @@ int pcso_bpc_encode_k(const int32_t* q, int Wa, int Ha, int wl, const int hdr[8]
                       int lutN, float k, int32_t* cs, int32_t* sizes, int cb0, int cb1) {
   bpc_cfg cfg; mkcfg(&cfg, hdr, wl, lut, lutN);
   cfg.k = k;
-  int nCB = (Wa / CB) * (Ha / CB);
+  int nCB = (Wa / CB) * (Ha / CBR);
   if (cb1 <= 0 || cb1 > nCB) cb1 = nCB;
   for (int cb = cb0; cb < cb1; cb++) {
     int32_t* w = cs + (size_t)cb * CBSZ;
@@ -949,7 +955,7 @@ int pcso_bpc_decode_k(const int32_t* cs, const int32_t* sizes, int Wa, int Ha, i
                       const int32_t* lut, int lutN, float k, int32_t* q, int cb0, int cb1) {
   bpc_cfg cfg; mkcfg(&cfg, hdr, wl, lut, lutN);
   cfg.k = k;
-  int nCB = (Wa / CB) * (Ha / CB);
+  int nCB = (Wa / CB) * (Ha / CBR);
   if (cb1 <= 0 || cb1 > nCB) cb1 = nCB;
   for (int cb = cb0; cb < cb1; cb++) decode_block(&cfg, cs + (size_t)cb * CBSZ, sizes[cb], Wa, Ha, cb, q);
   return 0;
@@ -958,7 +964,7 @@ int pcso_bpc_decode_k(const int32_t* cs, const int32_t* sizes, int Wa, int Ha, i
 int pcso_bpc_decode(const int32_t* cs, const int32_t* sizes, int Wa, int Ha, int wl, const int hdr[8],
                     const int32_t* lut, int lutN, int32_t* q, int cb0, int cb1) {
   bpc_cfg cfg; mkcfg(&cfg, hdr, wl, lut, lutN);
-  int nCB = (Wa / CB) * (Ha / CB);
+  int nCB = (Wa / CB) * (Ha / CBR);
   if (cb1 <= 0 || cb1 > nCB) cb1 = nCB;
   for (int cb = cb0; cb < cb1; cb++) decode_block(&cfg, cs + (size_t)cb * CBSZ, sizes[cb], Wa, Ha, cb, q);
   return 0;
