@@ -445,9 +445,10 @@ def bpc_decisions(cd, px, enc_ms, dec_ms):
     import torch
     q = cd.dwt_forward(px, trunc_to_int=True)                              # [n, Ha, Wa] int32 indices
     n, Ha, Wa = q.shape
-    blk = q.abs().reshape(n, Ha // 64, 64, Wa // 64, 64).amax(dim=(2, 4)).to(torch.int64)
+    r = cd.cb_rows
+    blk = q.abs().reshape(n, Ha // r, r, Wa // 64, 64).amax(dim=(2, 4)).to(torch.int64)
     msb1 = torch.where(blk > 0, torch.floor(torch.log2(blk.clamp(min=1).double())).long() + 1, torch.zeros_like(blk))
-    D = int((msb1 * 4096).sum().item() + (q != 0).sum().item())
+    D = int((msb1 * 64 * r).sum().item() + (q != 0).sum().item())
     return {"decisions_per_batch": D, "decisions_per_pixel": D / float(n * Ha * Wa),
             "encode_mdecisions_s": D / 1e6 / (enc_ms * 1e-3), "decode_mdecisions_s": D / 1e6 / (dec_ms * 1e-3)}
 

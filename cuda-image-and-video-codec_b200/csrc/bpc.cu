@@ -194,8 +194,11 @@ __device__ __forceinline__ void enc_step(unsigned abw, unsigned anbw, unsigned b
 #endif
 constexpr int kSppUnroll = PCS_SPP_UNROLL;
 
+// CTAs per SM the encoder is register-bounded for.  4 (128 registers): no spills at all -- smsp__inst_executed_op_local_ld/st
+// = 0.  5 (96 registers) spills 92 bytes: 9.2 M local loads + 4.0 M local stores in 3.13 G warp instructions per
+// 32 4K frames (0.4 %), and measures the same within noise (3.81 vs 3.83 ms; profiles/r2h_bpc_metrics.md).
 #ifndef PCS_ENC_MINB
-#define PCS_ENC_MINB 5
+#define PCS_ENC_MINB 4
 #endif
 template <typename T, int ROWS>  // ROWS: codeblock length, 64 or 32 (the reference's CBLOCK_LENGTH, BPC/BPCEngine.cuh:33-36)
 __global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* __restrict__ coeff, unsigned short* __restrict__ cw,
@@ -458,6 +461,8 @@ __device__ __forceinline__ unsigned dec_step(unsigned actw, unsigned bitm, unsig
 }
 
 
+// The decoder keeps 5 CTAs per SM (96 registers, 8-16 bytes of spill: 0.88 M local loads + 0.47 M local stores in 4.67 G warp
+// instructions, 0.03 %): 4 CTAs per SM is spill-free but 1.8 % slower (6.08 vs 5.98 ms per 32 4K frames).
 #ifndef PCS_DEC_MINB
 #define PCS_DEC_MINB 5
 #endif

@@ -66,3 +66,21 @@ def test_cb32_against_oracle(case, lut_root):
     finally:
         O.set_cb_rows(64)
         cd.close()
+
+
+def test_cb32_full_size_config3_matches_reference_build(lut_root):
+    """BASELINE configs[2] at its 64 x 32 sweep point: 7680x4320 lossless, wl = 5 (the deepest the reference's own 64x32
+    build round-trips at: its wl = 6 run does not reproduce the input, tests/golden/ref_manifest.json).  sha256 of the
+    reference build's stream, and the identity round trip."""
+    import hashlib
+    import json
+    e = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_manifest.json")))["cfg3_8k_wl5_ll_cb32"]
+    plut = codec.load_lut(f"{lut_root}/{e['lut']}/", e["wl"])
+    cd = codec.Codec(codec.Params(e["W"], e["H"], e["wl"], False, 1.0, flags=codec.PCS_F_CB_LENGTH_32), plut)
+    assert (cd.Wa, cd.Ha) == (7680, 4320)          # no padding rows with 32-row blocks (4352 with 64-row blocks)
+    img = synth.synth_frame(e["W"], e["H"])
+    stream, lens = cd.encode_frames(img[None])
+    assert stream.size * 2 == e["enc_len"]
+    assert hashlib.sha256(stream.tobytes()).hexdigest() == e["enc_sha256"]
+    assert np.array_equal(cd.decode_frames(stream, lens)[0], img)
+    cd.close()

@@ -280,3 +280,32 @@ def test_oracle_bit_depth_and_signed_input_match_reference(lut_root):
                 assert np.array_equal(g[name + ".dec"], img)
     finally:
         O.set_sample_offset(128)
+
+
+def test_oracle_64x32_codeblocks_match_reference_build(lut_root):
+    """64 x 32 codeblocks (the reference rebuilt with -DCBLOCK_LENGTH=32, BASELINE configs[2]'s sweep point): oracle ==
+    that build's streams byte for byte (tests/golden/cb32_ref.npz, scripts/r2_gpu_i.sh)."""
+    import os
+
+    from picsong_b200 import synth
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cb32_ref.npz"))
+    cases = [("cb32_s256x160_wl3_ll", "synth", 256, 160, 3, 0, 1.0), ("cb32_s512x288_wl3_q1", "synth", 512, 288, 3, 1, 1.0),
+             ("cb32_pad200x150_wl2_ll", "synth", 200, 150, 2, 0, 1.0), ("cb32_noise128x96_wl2_ll", "noise", 128, 96, 2, 0, 1.0),
+             ("cb32_s1024x544_wl4_q05", "synth", 1024, 544, 4, 1, 0.5)]
+    try:
+        O.set_cb_rows(32)
+        for name, kind, W, H, wl, lossy, qs in cases:
+            lut = O.lut_load(f"{lut_root}/{'n1_lossy' if lossy else 'n1_lossless'}/", wl)
+            img = synth.synth_frame(W, H) if kind == "synth" else synth.noise_frame(W, H)
+            assert O.adapted_dims(W, H) == (-(-W // 64) * 64, -(-H // 32) * 32)
+            s = O.encode_frame(img, wl, bool(lossy), qs, lut)
+            assert np.array_equal(s, g[name + ".stream"]), name
+            Wa, Ha = O.adapted_dims(W, H)
+            dec = O.decode_frame(s, Wa, Ha, wl, bool(lossy), qs, lut)[:H, :W]
+            if not lossy:
+                assert np.array_equal(dec, img), name
+            elif name + ".dec" in g:
+                d = np.abs(dec.astype(int) - g[name + ".dec"].reshape(H, W).astype(int))
+                assert d.max() <= 1 and (d != 0).mean() <= 1e-4
+    finally:
+        O.set_cb_rows(64)
