@@ -238,11 +238,15 @@ def run_ours(args):
     total = cfg["frames"] if strong else cfg["frames"] * world      # frames of the whole job
     hdr_frames = total if (strong or args.workload == "cfg4") else 0  # value of the header's frame field
     lroot = materialize_luts()
-    lut = codec.load_lut(f"{lroot}/{cfg['lut']}/", wl, rgb=rgb)
+    if args.k > 0:  # complexity-scalable mode: needs every bit-plane file of the LUT folder (oracle/_ref/LUT_all)
+        cfg["desc"] += f" [k={args.k}]"
+        lut = codec.load_lut(k_lut_dir(cfg["lut"]), wl, rgb=rgb, k=True)
+    else:
+        lut = codec.load_lut(f"{lroot}/{cfg['lut']}/", wl, rgb=rgb)
     os.environ["PCS_STAGE_TIMING"] = "1"
     try:
         cd = codec.Codec(codec.Params(W, H, wl, bool(lossy), qs, frames=hdr_frames, max_batch=B, rgb=rgb,
-                                      flags=codec.PCS_F_CB_LENGTH_32 if args.cb_length == 32 else 0), lut)
+                                      flags=codec.PCS_F_CB_LENGTH_32 if args.cb_length == 32 else 0, k=args.k), lut)
     except codec.PcsError as e:  # e.g. 64x32 codeblocks at a depth where a level of the (32-row padded) frame has odd height
         if rank == 0:
             print(json.dumps({"metric": METRIC, "unit": "Mpix/s", "n_gpus": world, "config": {"workload": cfg["desc"]}, "unavailable": str(e)}))
@@ -425,7 +429,7 @@ def run_ours(args):
     res["bpc"] = {"bound": "integer issue rate", "encode_mpix_s": W * H * nb0 / 1e6 / (m[1] * 1e-3), "decode_mpix_s": W * H * nb0 / 1e6 / (m[4] * 1e-3),
                   "share_of_step": float((m[1] + m[4]) / m.sum())}
     res["bpc"].update(bpc_decisions(cd, px[:nb0], m[1], m[4]))
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.k == 0 and args.cb_length == 64:
         res["cpu_baseline"] = cpu_baseline(W, H, wl, lossy, qs, f"{lroot}/{cfg['lut']}/") if not rgb else None
     cd.close()
     del px, out, stream
@@ -501,6 +505,52 @@ def continuity_cfg2(dev, lroot, steps=5):
     cd.close()
     return {"workload": cfg["desc"], "frames": B, "value": mpix / (float(np.mean(ts)) * 1e-3), "e2e": mpix / float(np.mean(te)),
             "unit": "Mpix/s", "dwt_forward_ms": float(np.mean(dw)), "dwt_forward_frac": gbs / hbm}
+
+
+def k_lut_dir(name):
+    d = os.path.join(ROOT, "oracle", "_ref", "LUT_all", name) + "/"
+    if not os.path.isdir(d):
+        raise SystemExit(f"--k needs the reference's complete LUT folder (all bit-plane files) at {d}: run oracle/build_ref.sh where /root/reference exists")
+    return d
+
+
+def run_reference_k(args, base, cfg):
+    """Complexity-scalable mode on the reference arm: its stage wrappers are only driven with k = 0 by the harness, so this
+    is the reference EXECUTABLE (-k K, video mode, a bounded sample of the frames, files in /dev/shm) and its own "time
+    ... without considering allocation periods" lines.  Its decoder aborts on streams whose codeblocks straddle subbands
+    (tests/golden/k_factor/README.md); then only the encode side is reported."""
+    W, H, wl, lossy, qs = cfg["W"], cfg["H"], cfg["wl"], cfg["lossy"], cfg["qs"]
+    exe = os.path.join(ROOT, "oracle", "_ref", "PICSONG_ref")
+    frames = min(cfg["frames"], 64)
+    tmp = scratch_dir(3 * frames * W * H, "pcs_refk_")
+    raw, enc, dec = os.path.join(tmp, "in.raw"), os.path.join(tmp, "o.pcs"), os.path.join(tmp, "o.raw")
+    write_raw(cfg, frames, raw)
+    lutdir = k_lut_dir(cfg["lut"])
+    best = None
+    for ns in (1, 8):
+        oe = subprocess.run([exe, "-cd", "0", "-wl", str(wl), "-cp", "2", "-type", str(lossy), "-qs", repr(qs), "-i", raw, "-o", enc, "-cbWidth", "64",
+                             "-cbHeight", "18", "-xSize", str(W), "-ySize", str(H), "-video", "1", "-frames", str(frames), "-LUTFolder", lutdir,
+                             "-numberOfStreams", str(ns), "-k", repr(args.k)], capture_output=True, text=True)
+        od = subprocess.run([exe, "-cd", "1", "-i", enc, "-o", dec, "-LUTFolder", lutdir, "-video", "1", "-numberOfStreams", str(ns)], capture_output=True, text=True)
+        me = re.search(r"without considering allocation periods is: ([0-9.eE+-]+)", oe.stdout)
+        md = re.search(r"without considering allocation periods[^:]*is: ([0-9.eE+-]+)", od.stdout)
+        r = {"streams": ns, "rc": [oe.returncode, od.returncode], "enc_s": float(me.group(1)) if me else None,
+             "dec_s": float(md.group(1)) if (md and od.returncode == 0) else None}
+        if r["enc_s"] and (best is None or r["enc_s"] < best["enc_s"]):
+            best = r
+    line = {**base, "k": args.k, "sample": f"{frames} frames through the reference executable, best of -numberOfStreams 1 / 8", "cli": best}
+    if best and best["enc_s"]:
+        mp = W * H * frames / 1e6
+        line["encode_mpix_s"] = mp / best["enc_s"]
+        if best["dec_s"]:
+            line["decode_mpix_s"] = mp / best["dec_s"]
+            line["value"] = mp / (best["enc_s"] + best["dec_s"])
+            line["e2e"] = {"value": line["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        else:
+            line["unavailable"] = "the reference decoder fails on its own -k stream for this geometry; encode side only"
+    else:
+        line["unavailable"] = "could not run the reference executable with -k"
+    print(json.dumps(line))
 
 
 def cpu_baseline(W, H, wl, lossy, qs, lutdir):
@@ -597,6 +647,8 @@ def run_reference(args):
     lutdir = f"{lroot}/{cfg['lut']}/"
     if cfg.get("rgb"):
         return run_reference_rgb(args, base, lroot)
+    if args.k > 0:
+        return run_reference_k(args, base, cfg)
     if not os.path.exists(harness):
         cb = cpu_baseline(W, H, wl, lossy, qs, lutdir)
         print(json.dumps({**base, "value": cb["value"], "cpu_baseline": cb,
@@ -706,6 +758,7 @@ def main():
     ap.add_argument("--cb-length", type=int, default=64, choices=[64, 32],
                     help="codeblock length: 64, or 32 = the reference's -DCBLOCK_LENGTH=32 build (BASELINE configs[2] sweep)")
     ap.add_argument("--wl", type=int, default=0, help="override the workload's wavelet levels")
+    ap.add_argument("--k", type=float, default=0.0, help="complexity-scalable mode (-k of the reference): > 0 uses the bulk-pass coder")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-continuity", action="store_true", help="skip the extra configs[1] measurement of the default run")
     args = ap.parse_args()
