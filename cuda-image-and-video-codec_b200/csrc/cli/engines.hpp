@@ -36,6 +36,7 @@ class Engine {
 
  protected:
   pcs_ctx* makeContext(int maxBatch, unsigned flags);
+  double _tLut = 0, _tCuda = 0, _tCreate = 0;  // start-up breakdown of makeContext (seconds)
   [[noreturn]] void die(const std::string& msg, int code = EXIT_FAILURE_CODE);
   static constexpr int EXIT_FAILURE_CODE = 1;
   int _codingPasses = 2, _waveletLevels = 5, _numberOfFrames = 0, _cbWidth = 64, _cbHeight = 18, _streams = 2;

@@ -71,3 +71,24 @@ def test_parameter_validation_and_no_cpu_fallback(lut_root):
     if not torch.cuda.is_available():
         rc, ctx = create()
         assert rc > 0 and not ctx.value, "without a CUDA device pcs_create must fail with the CUDA error"
+
+
+def test_torch_frame_generator_matches_numpy():
+    """bench.py generates the 600-frame video of BASELINE configs[3] with torch integer ops (on the GPU there); the formula is
+    integer-only, so it must reproduce picsong_b200.synth bit for bit -- also through bench.gen_frames' index runs and the
+    row bands of configs[4]."""
+    import os
+    import sys
+
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from picsong_b200 import synth
+    assert np.array_equal(synth.synth_video_torch(200, 150, 3, 7).numpy(), synth.synth_video(200, 150, 3, 7))
+    cfg = {"W": 192, "H": 130}
+    idx = [4, 5, 6, 20, 21, 9]
+    got = bench.gen_frames(cfg, idx, torch.device("cpu")).numpy()
+    assert np.array_equal(got, np.stack([synth.synth_frame(192, 130, f) for f in idx]))
+    bands = bench.gen_frames({"W": 256, "H": 64, "bands": True}, [0, 3], torch.device("cpu")).numpy()
+    assert np.array_equal(bands, np.stack([synth.synth_frame(256, 64, 0, 0, 64 * b) for b in (0, 3)]))
