@@ -92,25 +92,36 @@ struct Batch { int slot, f0, n; size_t words; };  // n == 0: end of stream; n < 
 // Page-locking memory costs ~0.3 ms per MB, more than coding the frames that go through it, so a buffer is allocated the
 // first time its slot is used (by the one thread that owns the slot at that moment): a short video never pays for slots
 // it does not reach, and the allocation of slot k+1 overlaps the GPU work on slot k.
+// Short jobs skip page-locking altogether: a job that moves less than ~1.5 GB is done sooner through pageable buffers (the
+// driver stages the copies at 10-20 GB/s) than the 0.3-0.7 s it takes to pin the ring.
 struct PinnedRing {
   std::vector<uint8_t*> in; std::vector<uint16_t*> out; std::vector<std::vector<int32_t>> lens;
   size_t inBytes, outBytes;
+  bool pin;
   std::atomic<long long> allocMicros{0};
-  PinnedRing(size_t inBytes_, size_t outWords, size_t nlens) : in(kRing, nullptr), out(kRing, nullptr), inBytes(inBytes_), outBytes(outWords * 2) {
+  PinnedRing(size_t inBytes_, size_t outWords, size_t nlens, bool pin_)
+      : in(kRing, nullptr), out(kRing, nullptr), inBytes(inBytes_), outBytes(outWords * 2), pin(pin_) {
     for (int i = 0; i < kRing; ++i) lens.emplace_back(nlens);
   }
   template <class P> P* get(std::vector<P*>& v, int i, size_t bytes) {
     if (!v[i]) {
       auto t0 = std::chrono::steady_clock::now();
-      v[i] = static_cast<P*>(pcs_host_alloc(bytes));
+      v[i] = static_cast<P*>(pin ? pcs_host_alloc(bytes) : std::aligned_alloc(4096, (bytes + 4095) / 4096 * 4096));
       allocMicros += (long long)(secondsSince(t0) * 1e6);
     }
     return v[i];
   }
   uint8_t* inBuf(int i) { return get(in, i, inBytes); }
   uint16_t* outBuf(int i) { return get(out, i, outBytes); }
-  ~PinnedRing() { for (auto p : in) pcs_host_free(p); for (auto p : out) pcs_host_free(p); }
+  ~PinnedRing() {
+    for (auto p : in) { if (pin) pcs_host_free(p); else std::free(p); }
+    for (auto p : out) { if (pin) pcs_host_free(p); else std::free(p); }
+  }
 };
+static bool worthPinning(size_t totalPixelBytes) {
+  if (const char* e = std::getenv("PICSONG_PIN")) return std::atoi(e) != 0;
+  return totalPixelBytes >= (size_t)1536 << 20;
+}
 
 }  // namespace
 
@@ -131,7 +142,7 @@ void CodingEngine::engineManager(int cType) {
   std::ofstream out(_outputFile, std::ios::binary | std::ios::trunc);
   if (!out) die("Error opening output file " + _outputFile);
   const size_t maxWords = (size_t)batch * pcs_frame_max_stream_words(ctx);
-  PinnedRing ring((size_t)batch * fpx, maxWords, (size_t)batch * planes);
+  PinnedRing ring((size_t)batch * fpx, maxWords, (size_t)batch * planes, worthPinning((size_t)frames * fpx));
   Channel<int> freeIn, freeOut;
   Channel<Batch> filled, coded;
   for (int i = 0; i < kRing; ++i) { freeIn.push(i); freeOut.push(i); }
@@ -182,7 +193,7 @@ void CodingEngine::engineManager(int cType) {
     std::cout << "The time spent with the app without considering allocation periods is: " << gpuSeconds << std::endl;
   }
   std::cout << "BPC acum time is: " << gpuSeconds << std::endl;  // whole GPU pipeline incl. PCIe (stages are fused)
-  std::cout << "Start-up (CUDA context, LUT parsing, device buffers): " << tContext << " s; page-locked host buffers: "
+  std::cout << "Start-up (CUDA context, LUT parsing, device buffers): " << tContext << " s; " << (ring.pin ? "page-locked" : "pageable (short job)") << " host buffers: "
             << ring.allocMicros.load() * 1e-6 << " s (overlapped with coding after the first batch)" << std::endl;
   std::cout << "Start-up detail: LUT parsing " << _tLut << " s, CUDA context creation " << _tCuda << " s, tables + device buffers " << _tCreate << " s" << std::endl;
   pcs_destroy(ctx);
@@ -231,7 +242,7 @@ void DecodingEngine::engineManager(int cType) {
   if (!video && planes == 1) out << "P5\n" << _img->width << " " << _img->height << "\n" << ((2 << (_img->bitDepth - 1)) - 1) << "\n";
   const size_t maxWords = (size_t)batch * pcs_frame_max_stream_words(ctx);
   // here the ring's "in" side holds pixels (output of the GPU) and its "out" side codestream words (input)
-  PinnedRing ring((size_t)batch * fpx, maxWords, 1);
+  PinnedRing ring((size_t)batch * fpx, maxWords, 1, worthPinning((size_t)frames * fpx));
   Channel<int> freeStream, freePx;
   Channel<Batch> filled, decoded;
   for (int i = 0; i < kRing; ++i) { freeStream.push(i); freePx.push(i); }
@@ -278,7 +289,7 @@ void DecodingEngine::engineManager(int cType) {
   if (video || planes == 3)
     std::cout << "The time spent with the app without considering allocation periods is: " << gpuSeconds << std::endl;
   std::cout << "BPC acum time is: " << gpuSeconds << std::endl;
-  std::cout << "Start-up (CUDA context, LUT parsing, device buffers): " << tContext << " s; page-locked host buffers: "
+  std::cout << "Start-up (CUDA context, LUT parsing, device buffers): " << tContext << " s; " << (ring.pin ? "page-locked" : "pageable (short job)") << " host buffers: "
             << ring.allocMicros.load() * 1e-6 << " s (overlapped with decoding after the first batch)" << std::endl;
   std::cout << "Start-up detail: LUT parsing " << _tLut << " s, CUDA context creation " << _tCuda << " s, tables + device buffers " << _tCreate << " s" << std::endl;
   pcs_destroy(ctx);

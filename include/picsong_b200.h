@@ -146,7 +146,9 @@ int32_t pcs_dwt_inverse(pcs_ctx* ctx, const int32_t* d_q, uint8_t* d_pixels, int
  * first half of BPCCuda<T>::Code (BPC/BPCEngine.ipp:24-37).
  * d_coeff: int32 or float [batch][A] (coeff_is_float selects); d_codewords: uint16
  * [batch][nCB][4096] (word 0 = MSB, word 1+j = codeword j; only the first d_sizes[cb] words of a
- * block are defined); d_sizes: int32 [batch][nCB] = 1 + codewords (4096 = expansion fallback). */
+ * block are defined); d_sizes: int32 [batch][nCB] = 1 + codewords (4096 = expansion fallback).
+ * Domain: |coefficient| < 2^23 (what 8..16-bit samples through the DWT can produce; Annex B.2 of SURVEY.md): the decoder
+ * treats MSB values 23..31 as "cannot occur" and writes zeros for such a block. */
 int32_t pcs_bpc_encode(pcs_ctx* ctx, const void* d_coeff, int32_t coeff_is_float, uint16_t* d_codewords,
                        int32_t* d_sizes, int32_t batch, void* stream);
 

@@ -24,7 +24,7 @@ REF = os.path.join(ROOT, "oracle", "_ref", "PICSONG_ref")
 def own_lines(out):
     keep = {}
     for key, pat in (("no_alloc_s", r"without considering allocation periods[^:]*: ([0-9.eE+-]+)"), ("app_s", r"The time spent with the app is: ([0-9.eE+-]+)"),
-                     ("startup", r"Start-up \(CUDA context, LUT parsing, device buffers\): ([0-9.eE+-]+) s; page-locked host buffers: ([0-9.eE+-]+)"), ("startup_detail", r"LUT parsing ([0-9.eE+-]+) s, CUDA context creation ([0-9.eE+-]+) s, tables \+ device buffers ([0-9.eE+-]+) s")):
+                     ("startup", r"Start-up \(CUDA context, LUT parsing, device buffers\): ([0-9.eE+-]+) s; [a-z() -]+ host buffers: ([0-9.eE+-]+)"), ("startup_detail", r"LUT parsing ([0-9.eE+-]+) s, CUDA context creation ([0-9.eE+-]+) s, tables \+ device buffers ([0-9.eE+-]+) s")):
         m = re.search(pat, out)
         if m:
             keep[key] = [float(g) for g in m.groups()] if len(m.groups()) > 1 else float(m.group(1))

@@ -92,3 +92,30 @@ def test_torch_frame_generator_matches_numpy():
     assert np.array_equal(got, np.stack([synth.synth_frame(192, 130, f) for f in idx]))
     bands = bench.gen_frames({"W": 256, "H": 64, "bands": True}, [0, 3], torch.device("cpu")).numpy()
     assert np.array_equal(bands, np.stack([synth.synth_frame(256, 64, 0, 0, 64 * b) for b in (0, 3)]))
+
+
+def test_create_refuses_tables_with_more_rows_than_the_decoder_stages():
+    """the decoder stages at most kMaxProbRows probability rows in shared memory while the encoder read
+    every row from global memory, so a custom LUT with more rows (nBp = 16 at wl = 10) would have decoded to garbage.
+    pcs_create now returns PCS_E_LUT_RANGE for such tables -- before touching CUDA, so this runs on the CPU box."""
+    import ctypes as C
+
+    import numpy as np
+    from picsong_b200 import _lib
+    lib = _lib.load()
+    p = _lib.PcsParams()
+    p.width = p.height = 2048
+    p.wavelet_levels, p.lossy, p.quant_size, p.coding_passes, p.k_factor = 10, 0, 1.0, 2, 0.0
+    p.cb_width, p.cb_height, p.frames = 64, 18, 0
+    p.bit_depth, p.bits_per_sample, p.endianess, p.is_signed, p.components, p.is_rgb = 8, 8, 0, 0, 1, 0
+    p.max_batch, p.flags = 1, 0
+    nBp, nSub, cR, cG, cS = 16, 3, 1, 4, 9
+    for i, v in enumerate((nBp, nSub, cR, cG, cS, 7, 3, 16)):
+        p.lut_header[i] = v
+    table = np.full((nSub * 10 + 1) * nBp * (cR + cS + cG), 64, dtype=np.int32)
+    p.lut = table.ctypes.data_as(C.POINTER(C.c_int32))
+    p.lut_len = int(table.size)
+    ctx = C.c_void_p()
+    assert lib.pcs_create(C.byref(p), C.byref(ctx)) == -3            # PCS_E_LUT_RANGE: (3*10+1)*16 + 32 = 528 rows > 497
+    p.bit_depth = 17
+    assert lib.pcs_create(C.byref(p), C.byref(ctx)) == -1            # PCS_E_ARG
