@@ -539,8 +539,6 @@ int dwt_inverse_fast(const int32_t*, long long, int, const void*, long long, int
 
 bool dwt_forward_l12_ok(const void*, const void*, const void*, int, int, int, int, int);
 int dwt_forward_l12(const uint8_t*, int, int, int, int, void*, long long, void*, long long, int, bool, float, bool, int, cudaStream_t, int offset);
-bool dwt_inverse_l21_ok(const int32_t*, const uint8_t*, const void*, int, int, int, int, int);
-int dwt_inverse_l21(const int32_t*, long long, const void*, long long, uint8_t*, int, int, int, int, int, bool, float, int, cudaStream_t, int offset);
 
 // PCS_DWT_FUSE = 0: per-level kernels of this file only; 1: streaming kernels of dwt_fast.cu, one level per launch;
 // 2 (default): levels 1+2 of u8 frames in one launch (dwt_fused.cu), the deeper levels through the streaming kernels
@@ -552,15 +550,6 @@ static int fuse_mode() {
     if (mode < 0 || mode > 2) mode = 2;
   }
   return mode;
-}
-// PCS_DWT_FUSE_INV = 0: inverse levels 2 and 1 as two streaming launches even in mode 2 (A/B switch of the fused inverse kernel)
-static bool inv_fuse_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("PCS_DWT_FUSE_INV");
-    on = e ? (atoi(e) != 0) : 1;
-  }
-  return on != 0;
 }
 
 // Host loop over levels (replaces DWTEngine::DWTForward, DWT/DWTGenerator.cu:1268-1342; no host
@@ -649,15 +638,6 @@ static int dwt_inverse_levels(const int32_t* d_q, uint8_t* d_px, void* d_scratch
                               bool rgb_px = false, int offset = 128) {
   const size_t A = (size_t)Wa * Ha, S = dwt_scratch_elems(Wa, Ha, wl);
   for (int l = lhigh; l >= llow; --l) {
-    // levels 2 and 1 in one launch (dwt_fused.cu): the LL1 plane stays in shared memory
-    if (l == 2 && llow == 1 && fuse_mode() == 2 && inv_fuse_enabled() && !tplane && !rgb_px && S % 4 == 0) {
-      const void* ll2 = wl == 2 ? nullptr : static_cast<const char*>(d_scratch) + ll_offset(Wa, Ha, 2) * 4;
-      if (ll_offset(Wa, Ha, 2) % 4 == 0 && dwt_inverse_l21_ok(d_q, d_px, ll2, W, H, Wa, Ha, wl)) {
-        const int rc = dwt_inverse_l21(d_q, (long long)A, ll2, (long long)S, d_px, W, H, Wa, Ha, wl, lossy, qs, frames, st, offset);
-        if (rc) return rc;
-        break;
-      }
-    }
     InvArgs a{};
     a.q = d_q; a.q_fstride = (long long)A; a.Wa = Wa;
     a.Wc = Wa >> (l - 1); a.Hc = Ha >> (l - 1);

@@ -20,8 +20,12 @@
 //     streaming stores; the LL1 row goes into a shared-memory ring of kLLSlots rows.
 //   * warps 4-5, "consumers": level 2 at FULL lane density.  A warp owns 256 LL1 columns (8 per lane) of the ring, so
 //     level 2 costs a quarter of level 1's instructions instead of the half an in-warp fusion pays (4 samples per
-//     lane).  Rows are handed over with mbarriers (producers arrive on ll_full[slot], consumers on ll_empty[slot]);
-//     there is no CTA-wide barrier in the loop.  HL2 / LH2 / HH2 go to the Mallat plane, LL2 to the scratch plane the
+//     lane).  Hand-over per ring row: "row stored" is a named barrier (producers bar.arrive, consumers bar.sync: the
+//     consumers wait about half of the time by design and a parked warp costs no issue slots); "row read" is an
+//     mbarrier (elected consumer lane arrives, producers try_wait, which normally succeeds at once).  A named barrier
+//     is a rendezvous of EVERY warp that bar.syncs on it: used for "row read" it locked the four producers into step
+//     at every row (12 % of the kernel's stall samples sat there; the mbarrier is worth 1.1-1.4 %, profiles/r2n_*).
+//     There is no CTA-wide barrier in the loop.  HL2 / LH2 / HH2 go to the Mallat plane, LL2 to the scratch plane the
 //     per-level kernels continue from (or, quantised, to the Mallat plane when wl == 2).
 //   * CTA pitch 912 = 2 x 456 LL1 columns: producers deliver 4 x 120 = 480 valid LL1 columns, the consumers' halo lanes
 //     take 8 on either side, and 912 keeps every TMA box start a multiple of 16 bytes (the unit rejects anything else).
@@ -89,8 +93,8 @@ __device__ __forceinline__ void tma_load_rows(void* dst, const CUtensorMap* tmap
       : "memory");
 }
 
-// Named barriers for the LL1 hand-over (ids 1 .. 2 * kLLSlots): a waiting warp is parked by the hardware and spends no
-// issue slots, unlike a polled mbarrier -- the consumers wait about half of the time by design.
+// Named barriers for the "row stored" side of the LL1 hand-over (ids 1 .. kLLSlots): a waiting warp is parked by the
+// hardware and spends no issue slots, unlike a polled mbarrier -- the consumers wait about half of the time by design.
 __device__ __forceinline__ void bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
@@ -132,6 +136,7 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
   __shared__ __align__(128) unsigned char s_in[kProd][kStages][4][256];
   __shared__ __align__(16) unsigned s_ll[kLLSlots][kLLRow];
   __shared__ __align__(8) unsigned long long s_full[kProd][kStages];
+  __shared__ __align__(8) unsigned long long s_empty[kLLSlots];  // "the consumers have read this ring row" (count: consumer warps)
 
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(kFullMask, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler: TMA operands stay in uniform registers
@@ -145,6 +150,7 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
   if (threadIdx.x == 0) {
     for (int p = 0; p < kProd; ++p)
       for (int d = 0; d < kStages; ++d) mbar_init(&s_full[p][d], 1);
+    for (int d = 0; d < kLLSlots; ++d) mbar_init(&s_empty[d], (unsigned)ncons);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -197,6 +203,7 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
       v1.init(r);
     }
     int ls = 0; bool lap0 = true;  // ring slot of the next LL1 row; first lap: the slots are free
+    unsigned epar = 0;             // parity of the s_empty phase the next lap waits for
     const int oc1 = c0 >> 1;
     VariantMask vm;
     // stores and hand-over of row pair pr (after the horizontal pass)
@@ -206,10 +213,10 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
         emit_pair<LOSSY, QS1, OT, T, 8>(lo, hi, out + (size_t)pr * a.pitch + oc1, out + (size_t)(pr + hh1) * a.pitch + oc1, hw1, a.q1, qs,
                                         false, nullptr);
       // ---- hand the LL1 row to the consumers ----
-      if (!lap0) bar_sync(1 + kLLSlots + ls, hand);  // the consumers have read what the slot held a lap ago
+      if (!lap0) mbar_wait(&s_empty[ls], epar);  // the consumers have read what the slot held a lap ago
       if (lane >= 1 && lane <= 30) sts4<T>(&s_ll[ls][120 * p + 4 * (lane - 1)], lo[0], lo[2], lo[4], lo[6]);
       bar_arrive(1 + ls, hand);
-      if (++ls == kLLSlots) { ls = 0; lap0 = false; }
+      if (++ls == kLLSlots) { ls = 0; if (!lap0) epar ^= 1u; lap0 = false; }
     };
     int slot = 0; unsigned par = 0;
 #pragma unroll 1
@@ -257,7 +264,8 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
     auto take = [&](T (&row)[8]) {
       bar_sync(1 + ls, hand);                  // every producer has stored its part of the row
       lds8(&s_ll[ls][ridx], row);
-      bar_arrive(1 + kLLSlots + ls, hand);     // (the loaded values are consumed before the slot can be overwritten: see below)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[ls]);  // release: the warp's loads above are ordered before it
       if (++ls == kLLSlots) ls = 0;
     };
     // horizontal pass, quantiser and stores of level-2 row pair p2
@@ -308,270 +316,6 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
   }
 }
 
-// =====================================================================================================================
-// inverse: levels 2 AND 1 in one CTA (the mirror image of the kernel above; the LL1 plane never reaches HBM)
-// =====================================================================================================================
-// Replaces the last two iterations of DWTEngine::DWTReverse (DWT/DWTGenerator.cu:1349-1424) + removeOffsetAndApplyMaxMin[Lossy]
-// (Engines/DecodingEngine.cu:706-729) + the u8 narrowing of IO/IOManager.ipp:332-335.
-//   * warps 4-5, "level-2 warps": synthesis of level 2 on 256 LL1 columns each (subband rows of the Mallat plane + the LL2
-//     plane of level 3 through one-step register prefetch), the two LL1 rows of a step go into the shared-memory ring;
-//   * warps 0-3, "level-1 warps": synthesis of level 1 on 256 pixel columns each.  HL1 / LH1 / HH1 rows arrive through a
-//     private ring of TMA tile loads (one 128-column x 2-row int32 box per subband and two-step stage), the LL1 row comes
-//     from the ring; u8 pixels leave with 8-byte streaming stores;
-//   * same hand-over protocol (named barriers), same 912-pixel CTA pitch as the forward kernel.
-constexpr int kStagesI = 3;  // two-step stages of the level-1 warps' subband ring (3 subbands x 2 rows x 128 ints each)
-constexpr int kLLRowI = 488; // 32-bit words per ring row of the inverse kernel (480 written; the halo lanes of the last warp read 8 more)
-
-struct FusedInvArgs {
-  const int32_t* q; long long q_fstride; int pitch;   // quantised Mallat plane
-  const void* ll2; long long ll2_fstride; int ll2_pitch;  // LL2 plane (scratch, type T) unless `first2`
-  int first2;                                         // wl == 2: LL2 comes from q, de-quantised
-  int Wc, Hc;                                         // frame size (adapted)
-  unsigned char* dst; long long dst_fstride; int dst_pitch; int H;  // u8 frames (rows >= H are padding and are not stored)
-  float r1[4], r2[4], rqs;                            // reciprocal quantiser steps of levels 1 / 2 and 1 / qs
-  int offset;                                         // level shift added back before the clamp
-  int nctax, nchunks, rp;                             // rp: level-1 row pairs per chunk
-};
-
-template <bool LOSSY, bool QS1>
-__global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_inverse_l21_kernel(const __grid_constant__ CUtensorMap tmapq2,
-                                                                                  const __grid_constant__ CUtensorMap tmapq1, const FusedInvArgs a) {
-  using T = typename VSel<LOSSY, 8>::T;
-  using VP = typename IVSel<LOSSY, 8>::type;
-  using T4 = typename std::conditional<LOSSY, float4, int4>::type;
-  __shared__ __align__(128) int s_sb[kProd][kStagesI][3][2][128];
-  __shared__ __align__(16) unsigned s_ll[kLLSlots][kLLRowI];
-  __shared__ __align__(8) unsigned long long s_full[kProd][kStagesI];
-
-  const int lane = threadIdx.x & 31;
-  const int warp = __shfl_sync(kFullMask, (int)(threadIdx.x >> 5), 0);
-  const int ctax = blockIdx.x % a.nctax, chunk = blockIdx.x / a.nctax, frame = blockIdx.y;
-  const int Wc = a.Wc, Hc = a.Hc, hw1 = Wc >> 1, hh1 = Hc >> 1, hw2 = Wc >> 2, hh2 = Hc >> 2;
-  const int X0 = ctax * kPitch;
-  const int B = (X0 >> 1) - 16;                       // LL1 column the ring rows start at
-  const int remPx = min(kPitch, Wc - X0);             // pixel columns this CTA owns
-  const int n1w = min(kProd, (remPx + 24 + 239) / 240);   // level-1 warps with owned columns (valid from X0 - 24 + 240 p)
-  const int needLL = min(120 * (n1w - 1) + 128, hw1 - B);  // ring columns the level-1 warps read inside the image
-  const int n2w = needLL > 240 ? 2 : 1;
-  const int hand = 32 * (n1w + n2w);
-
-  if (threadIdx.x == 0) {
-    for (int p = 0; p < kProd; ++p)
-      for (int d = 0; d < kStagesI; ++d) mbar_init(&s_full[p][d], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
-
-  const int n0 = chunk * a.rp, n1 = min(n0 + a.rp, hh1);
-  const int R0 = max(n0 - VP::kLead, 0);                      // LL1 rows [R0, Rlast] travel through the ring
-  const int Rlast = min(n1 + VP::kTail, hh1 - 1);
-  const f2 rqs2 = pk(a.rqs, a.rqs);
-
-  if (warp >= kProd) {
-    // =============================== level-2 warp: LL1 rows into the ring ===============================
-    const int c = warp - kProd;
-    if (c >= n2w) return;
-    const int o2 = B - 8 + 240 * c + 8 * lane;          // first of the lane's 8 LL1 (output) columns
-    const bool left = o2 == 0, right = o2 + 8 == hw1;
-    const int oc = min(max(o2, 0), hw1 - 8) >> 1;       // subband column of the lane's 4 low / 4 high samples
-    const int32_t* const q = a.q + (size_t)frame * a.q_fstride + oc;
-    const T* const lls = a.first2 ? nullptr : static_cast<const T*>(a.ll2) + (size_t)frame * a.ll2_fstride + oc;
-    struct Raw { int4 hl, lh, hh; T4 ll; };
-    auto load_pair = [&](int n) -> Raw {   // row pair n of level 2, whole-sample fold of the row index
-      int rl, rh;
-      if (n < 0) { rl = -n; rh = -n - 1; }
-      else if (n >= hh2) { rl = hh1 - 1 - n; rh = hh1 - 2 - n; }
-      else { rl = n; rh = n; }
-      const int32_t* row_lo = q + (size_t)rl * a.pitch;
-      const int32_t* row_hi = q + (size_t)(rh + hh2) * a.pitch;
-      Raw r;
-      r.hl = __ldg(reinterpret_cast<const int4*>(row_lo + hw2));
-      r.lh = __ldg(reinterpret_cast<const int4*>(row_hi));
-      r.hh = __ldg(reinterpret_cast<const int4*>(row_hi + hw2));
-      if (a.first2) {
-        const int4 t = __ldg(reinterpret_cast<const int4*>(row_lo));
-        if constexpr (LOSSY) {
-          const f2 h0 = pk(0.5f * a.r2[0], 0.5f * a.r2[0]);
-          float4 v;
-          upk(dequant2<QS1>(t.x, t.y, h0, rqs2), v.x, v.y);
-          upk(dequant2<QS1>(t.z, t.w, h0, rqs2), v.z, v.w);
-          r.ll = v;
-        } else {
-          r.ll = t;
-        }
-      } else {
-        r.ll = __ldg(reinterpret_cast<const T4*>(lls + (size_t)rl * a.ll2_pitch));
-      }
-      return r;
-    };
-    auto expand = [&](const Raw& r, T (&lo)[8], T (&hi)[8]) {
-      lo[0] = r.ll.x; lo[2] = r.ll.y; lo[4] = r.ll.z; lo[6] = r.ll.w;
-      if constexpr (LOSSY) {
-        const f2 h13 = pk(0.5f * a.r2[1], 0.5f * a.r2[3]), h22 = pk(0.5f * a.r2[2], 0.5f * a.r2[2]);
-        upk(dequant2<QS1>(r.hl.x, r.hh.x, h13, rqs2), lo[1], hi[1]);
-        upk(dequant2<QS1>(r.hl.y, r.hh.y, h13, rqs2), lo[3], hi[3]);
-        upk(dequant2<QS1>(r.hl.z, r.hh.z, h13, rqs2), lo[5], hi[5]);
-        upk(dequant2<QS1>(r.hl.w, r.hh.w, h13, rqs2), lo[7], hi[7]);
-        upk(dequant2<QS1>(r.lh.x, r.lh.y, h22, rqs2), hi[0], hi[2]);
-        upk(dequant2<QS1>(r.lh.z, r.lh.w, h22, rqs2), hi[4], hi[6]);
-      } else {
-        lo[1] = r.hl.x; lo[3] = r.hl.y; lo[5] = r.hl.z; lo[7] = r.hl.w;
-        hi[0] = r.lh.x; hi[2] = r.lh.y; hi[4] = r.lh.z; hi[6] = r.lh.w;
-        hi[1] = r.hh.x; hi[3] = r.hh.y; hi[5] = r.hh.z; hi[7] = r.hh.w;
-      }
-    };
-    int ls = 0; bool lap0 = true;
-    auto publish = [&](int y, const T (&v)[8]) {
-      if (y < R0 || y > Rlast) return;  // warp-uniform
-      if (!lap0) bar_sync(1 + kLLSlots + ls, hand);  // the level-1 warps have read what the slot held a lap ago
-      if (lane >= 1 && lane <= 30) {
-        sts4<T>(&s_ll[ls][240 * c + 8 * (lane - 1)], v[0], v[1], v[2], v[3]);
-        sts4<T>(&s_ll[ls][240 * c + 8 * (lane - 1) + 4], v[4], v[5], v[6], v[7]);
-      }
-      bar_arrive(1 + ls, hand);
-      if (++ls == kLLSlots) { ls = 0; lap0 = false; }
-    };
-    // level-2 step m releases LL1 rows odd_row(m) and even_row(m) = odd_row(m) + 1; the step that releases row R:
-    auto step_of_row = [](int R) { return ((R + 1) >> 1) + (LOSSY ? 1 : 0); };
-    const int mfirst = (R0 >> 1) - VP::kLead, mlast = step_of_row(Rlast);  // as a chunk of the per-level kernel starting at row pair R0 / 2
-    VP vp; vp.init();
-    Raw cur = load_pair(mfirst);
-#pragma unroll 1
-    for (int m = mfirst; m <= mlast; ++m) {
-      T lo[8], hi[8], re[8], ro[8];
-      expand(cur, lo, hi);
-      cur = load_pair(m + 1);  // prefetch (rows past the end fold to valid rows and are not used)
-      if constexpr (LOSSY) { hinv97_rows<8>(lo, hi, left, right); iv97_step_packed<8>(vp, lo, hi, re, ro); }
-      else { hinv53<8>(lo, left, right); hinv53<8>(hi, left, right); vp.step(lo, hi, re, ro); }
-      publish(VP::odd_row(m), ro);
-      publish(VP::even_row(m), re);
-    }
-  } else {
-    // =============================== level-1 warp: pixels ===============================
-    const int p = warp;
-    if (p >= n1w) return;
-    const int xw = X0 - 32 + 240 * p;
-    const int c0 = xw + 8 * lane;
-    const bool inimg = c0 >= 0 && c0 < Wc;
-    const bool wlane = lane >= 1 && lane <= 30 && inimg && c0 >= X0 && c0 < X0 + kPitch;
-    const bool left = c0 == 0, right = c0 + 8 == Wc;
-    const int ridx = 120 * p + 4 * lane;                 // the lane's 4 LL1 columns in a ring row
-    const int xs = xw >> 1;                              // subband column of the warp's first sample (a multiple of 4)
-    auto pair_rows = [&](int n, int& rl, int& rh) {      // row pair n: low row rl of (LL|HL), high row rh of (LH|HH)
-      if (n < 0) { rl = -n; rh = -n - 1; }
-      else if (n >= hh1) { rl = Hc - 1 - n; rh = Hc - 2 - n; }
-      else { rl = n; rh = n; }
-    };
-    const int ms = n0 - VP::kLead, mend = n1 + VP::kTail;
-    const int nstages = (mend - ms + 2) >> 1;
-    auto issue = [&](int j, int slot, unsigned dep) {    // subband rows of steps ms + 2j and ms + 2j + 1
-      if (lane == 0 && j < nstages) {
-        const int n = ms + 2 * j;
-        mbar_expect_tx(&s_full[p][slot], 3 * 2 * 512);
-        if (n >= 0 && n + 1 < hh1) {
-          tma_load_rows(&s_sb[p][slot][0][0][0], &tmapq2, hw1 + xs, n, frame, &s_full[p][slot], dep);
-          tma_load_rows(&s_sb[p][slot][1][0][0], &tmapq2, xs, n + hh1, frame, &s_full[p][slot], dep);
-          tma_load_rows(&s_sb[p][slot][2][0][0], &tmapq2, hw1 + xs, n + hh1, frame, &s_full[p][slot], dep);
-        } else {
-#pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            int rl, rh;
-            pair_rows(n + r, rl, rh);
-            tma_load_rows(&s_sb[p][slot][0][r][0], &tmapq1, hw1 + xs, rl, frame, &s_full[p][slot], dep);
-            tma_load_rows(&s_sb[p][slot][1][r][0], &tmapq1, xs, rh + hh1, frame, &s_full[p][slot], dep);
-            tma_load_rows(&s_sb[p][slot][2][r][0], &tmapq1, hw1 + xs, rh + hh1, frame, &s_full[p][slot], dep);
-          }
-        }
-      }
-    };
-#pragma unroll
-    for (int d = 0; d < kStagesI; ++d) issue(d, d, 0u);
-    unsigned char* const dst = a.dst + (size_t)frame * a.dst_fstride + c0;
-    auto store_row = [&](int y, const T (&v)[8]) {
-      if (y >= a.H) return;
-      unsigned b[8];
-      if constexpr (LOSSY) {  // clamp(rn((v + offset) + 0.01)), DecodingEngine.cu:714
-        const float foff = (float)a.offset;
-#pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-          float t0, t1;
-          upk(add2(add2(pk(v[j], v[j + 1]), pk(foff, foff)), pk(0.01f, 0.01f)), t0, t1);
-          b[j] = sat_u8(t0); b[j + 1] = sat_u8(t1);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) b[j] = (unsigned)min(max(v[j] + a.offset, 0), 255);  // :728
-      }
-      uint2 w;
-      w.x = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
-      w.y = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
-      __stcs(reinterpret_cast<uint2*>(dst + (size_t)y * a.dst_pitch), w);
-    };
-    // LL1 row of pair n.  Rows arrive in order R0, R0 + 1, ...; every row's barrier is met exactly once.  At the top of the
-    // image the mirror pairs -2, -1 read rows 2, 1 before row 0: rows 0..2 are awaited up front and read again later.
-    int taken = 0;          // rows R0 .. R0 + taken - 1 have been awaited
-    T4 lastll = {};         // row hh1 - 1, read again by the mirror pair hh1
-    auto ll_row = [&](int n) -> T4 {
-      int rl = n < 0 ? -n : (n >= hh1 ? Hc - 1 - n : n);
-      if (n >= hh1) return lastll;
-      while (R0 + taken <= rl) {  // warp-uniform
-        const int sl = taken % kLLSlots;
-        bar_sync(1 + sl, hand);
-        ++taken;
-      }
-      const int sl = (rl - R0) % kLLSlots;
-      return *reinterpret_cast<const T4*>(&s_ll[sl][ridx]);
-    };
-    auto release = [&](int n) {  // pair n (>= 0, in order) has read its row for the last time
-      if (n < R0 || n > Rlast) return;
-      // rows 1 .. kLead at the top of the image were also read by the mirror pairs, which came first: nothing else to wait for
-      bar_arrive(1 + kLLSlots + (n - R0) % kLLSlots, hand);
-    };
-    VP vp; vp.init();
-    int slot = 0; unsigned par = 0;
-    auto step = [&](int m, const int4 hl, const int4 lh, const int4 hh) {
-      T lo[8], hi[8], re[8], ro[8];
-      const T4 ll = ll_row(m);
-      if (m == hh1 - 1) lastll = ll;
-      lo[0] = ll.x; lo[2] = ll.y; lo[4] = ll.z; lo[6] = ll.w;
-      if constexpr (LOSSY) {
-        const f2 h13 = pk(0.5f * a.r1[1], 0.5f * a.r1[3]), h22 = pk(0.5f * a.r1[2], 0.5f * a.r1[2]);
-        upk(dequant2<QS1>(hl.x, hh.x, h13, rqs2), lo[1], hi[1]);
-        upk(dequant2<QS1>(hl.y, hh.y, h13, rqs2), lo[3], hi[3]);
-        upk(dequant2<QS1>(hl.z, hh.z, h13, rqs2), lo[5], hi[5]);
-        upk(dequant2<QS1>(hl.w, hh.w, h13, rqs2), lo[7], hi[7]);
-        upk(dequant2<QS1>(lh.x, lh.y, h22, rqs2), hi[0], hi[2]);
-        upk(dequant2<QS1>(lh.z, lh.w, h22, rqs2), hi[4], hi[6]);
-      } else {
-        lo[1] = hl.x; lo[3] = hl.y; lo[5] = hl.z; lo[7] = hl.w;
-        hi[0] = lh.x; hi[2] = lh.y; hi[4] = lh.z; hi[6] = lh.w;
-        hi[1] = hh.x; hi[3] = hh.y; hi[5] = hh.z; hi[7] = hh.w;
-      }
-      if (m >= 0 && m < hh1) release(m);  // the row's values are in registers
-      if constexpr (LOSSY) { hinv97_rows<8>(lo, hi, left, right); iv97_step_packed<8>(vp, lo, hi, re, ro); }
-      else { hinv53<8>(lo, left, right); hinv53<8>(hi, left, right); vp.step(lo, hi, re, ro); }
-      const int yo = VP::odd_row(m), ye = VP::even_row(m);
-      if (wlane) {
-        if (yo >= 2 * n0 && yo < 2 * n1) store_row(yo, ro);
-        if (ye >= 2 * n0 && ye < 2 * n1) store_row(ye, re);
-      }
-    };
-#pragma unroll 1
-    for (int j = 0; j < nstages; ++j) {
-      mbar_wait(&s_full[p][slot], par);
-      __syncwarp();
-      const int* const st = &s_sb[p][slot][0][0][4 * lane];
-      const int m = ms + 2 * j;
-      step(m, *reinterpret_cast<const int4*>(st), *reinterpret_cast<const int4*>(st + 256), *reinterpret_cast<const int4*>(st + 512));
-      const int4 hlB = *reinterpret_cast<const int4*>(st + 128), lhB = *reinterpret_cast<const int4*>(st + 384), hhB = *reinterpret_cast<const int4*>(st + 640);
-      issue(j + kStagesI, slot, (unsigned)(hlB.x ^ lhB.y ^ hhB.z));
-      if (++slot == kStagesI) { slot = 0; par ^= 1u; }
-      if (m + 1 <= mend) step(m + 1, hlB, lhB, hhB);
-    }
-  }
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_tiled() {
@@ -608,70 +352,6 @@ void launch_fused_k(const CUtensorMap& tmap4, const CUtensorMap& tmap1, FusedArg
   dwt_forward_l12_kernel<LOSSY, OT, QS1><<<grid, kThreads, 0, st>>>(tmap4, tmap1, a);
 }
 
-template <bool LOSSY, bool QS1>
-void launch_fused_inv_k(const CUtensorMap& t2, const CUtensorMap& t1, FusedInvArgs a, int frames, cudaStream_t st) {
-  static const long long slots = [] {
-    int dev = 0, sms = 148, per_sm = PCS_FUSED_MINB;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwt_inverse_l21_kernel<LOSSY, QS1>, kThreads, 0);
-    return (long long)sms * std::max(per_sm, 1);
-  }();
-  const int hh1 = a.Hc >> 1, warm = LOSSY ? 6 : 3;
-  static const int rp_env = [] { const char* e = std::getenv("PCS_FUSED_RP"); return e ? std::atoi(e) : 0; }();
-  int best = 4; long long best_cost = -1;
-  for (int rp = 4; rp <= 512; rp += 4) {
-    const long long ctas = (long long)a.nctax * ((hh1 + rp - 1) / rp) * frames;
-    const long long cost = ((ctas + slots - 1) / slots) * (rp + warm);
-    if (best_cost < 0 || cost <= best_cost) { best = rp; best_cost = cost; }
-  }
-  a.rp = rp_env > 0 ? std::max(4, rp_env & ~3) : best;
-  a.nchunks = (hh1 + a.rp - 1) / a.rp;
-  dim3 grid(a.nctax * a.nchunks, frames);
-  dwt_inverse_l21_kernel<LOSSY, QS1><<<grid, kThreads, 0, st>>>(t2, t1, a);
-}
-
-}  // namespace
-
-// Can levels 2+1 of the inverse transform of this geometry go through the fused kernel?  (u8 frames without horizontal crop)
-bool dwt_inverse_l21_ok(const int32_t* d_q, const uint8_t* d_px, const void* ll2, int W, int H, int Wa, int Ha, int wl) {
-  if (wl < 2 || W != Wa || H > Ha || Wa % 64 || Ha % 64 || Wa < 64 || Ha < 64) return false;
-  if ((reinterpret_cast<uintptr_t>(d_q) & 15) || (reinterpret_cast<uintptr_t>(d_px) & 7)) return false;
-  if (ll2 && (reinterpret_cast<uintptr_t>(ll2) & 15)) return false;
-  if (((long long)W * H) % 8) return false;
-  return encode_tiled() != nullptr;
-}
-
-// Levels 2 and 1 of the inverse transform of `frames` frames in one launch.  ll2: scratch plane holding LL2 (output of level 3;
-// ignored when wl == 2, where LL2 is de-quantised from d_q).
-int dwt_inverse_l21(const int32_t* d_q, long long q_fstride, const void* ll2, long long ll2_fstride, uint8_t* d_px, int W, int H, int Wa, int Ha,
-                    int wl, bool lossy, float qs, int frames, cudaStream_t st, int offset) {
-  alignas(64) CUtensorMap t2, t1;
-  const cuuint64_t gdim[3] = {(cuuint64_t)Wa, (cuuint64_t)Ha, (cuuint64_t)frames};
-  const cuuint64_t gstride[2] = {(cuuint64_t)Wa * 4, (cuuint64_t)q_fstride * 4};
-  const cuuint32_t box2[3] = {128, 2, 1}, box1[3] = {128, 1, 1}, estr[3] = {1, 1, 1};
-  for (int k = 0; k < 2; ++k) {
-    const CUresult r = encode_tiled()(k ? &t1 : &t2, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, const_cast<int32_t*>(d_q), gdim, gstride, k ? box1 : box2,
-                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
-  }
-  FusedInvArgs a{};
-  a.q = d_q; a.q_fstride = q_fstride; a.pitch = Wa;
-  a.ll2 = ll2; a.ll2_fstride = ll2_fstride; a.ll2_pitch = Wa >> 2; a.first2 = wl == 2;
-  a.Wc = Wa; a.Hc = Ha; a.dst = d_px; a.dst_fstride = (long long)W * H; a.dst_pitch = W; a.H = H;
-  for (int i = 0; i < 4; ++i) { a.r1[i] = 1.0f / kQ[0][i]; a.r2[i] = 1.0f / kQ[1][i]; }
-  a.rqs = 1.0f / qs; a.offset = offset;
-  a.nctax = (Wa + kPitch - 1) / kPitch;
-  const bool qs1 = a.rqs == 1.0f;
-  if (!lossy) launch_fused_inv_k<false, true>(t2, t1, a, frames, st);
-  else if (qs1) launch_fused_inv_k<true, true>(t2, t1, a, frames, st);
-  else launch_fused_inv_k<true, false>(t2, t1, a, frames, st);
-  ++g_launches;
-  return (int)cudaGetLastError();
-}
-
-namespace {
 }  // namespace
 
 // Can levels 1+2 of this geometry go through the fused kernel?  (u8 frames without horizontal padding, wl >= 2)
