@@ -132,6 +132,11 @@ __device__ __forceinline__ unsigned byte_of(unsigned x, int k) { return __byte_p
 struct EncState { unsigned lower, size, slot, count, lt; };
 // One call site of the interval coder for the whole warp.  `abw` / `anbw`: words whose bit `bitm` says
 // "this lane codes a 1 here" / "codes a 0 here" (neither: the lane is idle at this call site).
+// A completed codeword (size == 0) is not stored when it completes but when its lane starts the next one (or by the flush
+// at the end of the block, which stores every lane's current word): the store then sits with the slot hand-out inside the
+// part of the step that is skipped, with a warp-uniform branch, at the call sites where no lane starts a codeword.  The
+// lane's first "completed word" is the initial state (lower = 0): its slot is WORDS - 2, which no codeword of a block that
+// is not expanded can own (slots < count <= WORDS - 2; an expanded block is rewritten raw).
 // Hand-scheduled as predicated PTX: nvcc's lowering of the equivalent C++ (kept below) costs ~50 % more
 // instructions on the ALU pipe, which is what bounds this kernel.
 #ifndef PCS_ENC_PTX
@@ -143,7 +148,7 @@ __device__ __forceinline__ void enc_step(unsigned abw, unsigned anbw, unsigned b
 #if PCS_ENC_PTX
   asm volatile(
       "{\n\t"
-      ".reg .pred pab, panb, pact, pneed, pst;\n\t"
+      ".reg .pred pab, panb, pact, pneed, pz;\n\t"
       ".reg .b32 t, m, x, pre, pm, r, q, sl;\n\t"
       ".reg .b64 ad;\n\t"
       "and.b32 t, %4, %6;\n\t"
@@ -153,6 +158,11 @@ __device__ __forceinline__ void enc_step(unsigned abw, unsigned anbw, unsigned b
       "or.pred pact, pab, panb;\n\t"
       "setp.eq.and.u32 pneed, %1, 0, pact;\n\t"       // lanes that start a codeword at this call site,
       "vote.sync.ballot.b32 m, pneed, 0xffffffff;\n\t"  // served in lane order (BPCEngine.cu:376-384)
+      "setp.eq.u32 pz, m, 0;\n\t"
+      "@pz bra.uni LAB_ENC_NONEED;\n\t"                // warp-uniform: nobody starts a codeword here (about 2 sites in 3)
+      "min.u32 sl, %2, %11;\n\t"
+      "mad.wide.u32 ad, sl, 2, %10;\n\t"
+      "@pneed st.global.u16 [ad], %0;\n\t"             // the codeword the lane has just completed (deferred store)
       "and.b32 x, m, %7;\n\t"
       "popc.b32 pre, x;\n\t"
       "popc.b32 pm, m;\n\t"
@@ -160,16 +170,13 @@ __device__ __forceinline__ void enc_step(unsigned abw, unsigned anbw, unsigned b
       "add.u32 %3, %3, pm;\n\t"
       "@pneed mov.u32 %1, 0xFFFF;\n\t"
       "@pneed mov.u32 %0, 0;\n\t"
+      "LAB_ENC_NONEED:\n\t"
       "mul.lo.u32 r, %1, %8;\n\t"
       "shr.u32 q, r, %9;\n\t"
       "add.u32 r, q, 1;\n\t"
       "@pab sub.u32 %1, %1, r;\n\t"
       "@pab add.u32 %0, %0, r;\n\t"
       "@panb mov.u32 %1, q;\n\t"
-      "setp.eq.and.u32 pst, %1, 0, pact;\n\t"
-      "min.u32 sl, %2, %11;\n\t"
-      "mad.wide.u32 ad, sl, 2, %10;\n\t"
-      "@pst st.global.u16 [ad], %0;\n\t"
       "}"
       : "+r"(c.lower), "+r"(c.size), "+r"(c.slot), "+r"(c.count)
       : "r"(abw), "r"(anbw), "r"(bitm), "r"(c.lt), "r"(p), "r"(prec), "l"(out1), "n"(WORDS - 2)
@@ -179,13 +186,15 @@ __device__ __forceinline__ void enc_step(unsigned abw, unsigned anbw, unsigned b
   const bool act = ab || anb;
   const bool need = act && (c.size == 0);
   const unsigned m = __ballot_sync(kFull, need);
-  const unsigned pre = __popc(m & c.lt);
-  if (need) { c.slot = c.count + pre; c.size = 0xFFFFu; c.lower = 0u; }
-  c.count += __popc(m);
+  if (m != 0) {
+    if (need) out1[min(c.slot, (unsigned)(WORDS - 2))] = (unsigned short)c.lower;
+    const unsigned pre = __popc(m & c.lt);
+    if (need) { c.slot = c.count + pre; c.size = 0xFFFFu; c.lower = 0u; }
+    c.count += __popc(m);
+  }
   const unsigned q = (c.size * p) >> prec;
   if (ab) { c.size = c.size - q - 1u; c.lower = c.lower + q + 1u; }
   if (anb) c.size = q;
-  if (act && c.size == 0) out1[min(c.slot, (unsigned)(WORDS - 2))] = (unsigned short)c.lower;
 #endif
 }
 
@@ -249,7 +258,7 @@ __global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* 
   unsigned short* const out1 = out + 1;
   const unsigned prec = (unsigned)p.prec;
 
-  EncState ac; ac.lower = 0; ac.size = 0; ac.slot = 0; ac.count = 0; ac.lt = (1u << lane) - 1u;
+  EncState ac; ac.lower = 0; ac.size = 0; ac.slot = kWords - 2;  /* dump slot for the deferred store of the initial state, see enc_step */ ac.count = 0; ac.lt = (1u << lane) - 1u;
   u64 s0 = 0, s1 = 0;  // significant BEFORE the current plane
   for (int bp = MSB; bp >= 0; --bp, --row) {
     u64 B0, B1;
@@ -413,15 +422,29 @@ struct DecState { unsigned lower, size, slot, count, code, lt; };
 // One call site of the interval decoder for the whole warp (BPCEngine.cu:405-442); returns the decoded
 // bit (0 for idle lanes).  `actw` bit `bitm`: this lane decodes a symbol here.  Predicated PTX, see enc_step.
 // PREC = 7 (every shipped LUT): the shift is an immediate; PREC = 0: taken from `prec` at run time.
+// PCS_DEC_SKIP_REFILL (default 1): no lane starts a codeword at about two call sites out of three; the ten instructions
+// that hand out stream slots and fetch the words are then jumped over with a warp-uniform branch (the ballot is the
+// same in every lane).
+#ifndef PCS_DEC_SKIP_REFILL
+#define PCS_DEC_SKIP_REFILL 1
+#endif
+#if PCS_DEC_SKIP_REFILL
+#define PCS_DEC_SKIP_OPEN "setp.eq.u32 pz, m, 0;\n\t@pz bra.uni LAB_NOREFILL;\n\t"
+#define PCS_DEC_SKIP_CLOSE "LAB_NOREFILL:\n\t"
+#else
+#define PCS_DEC_SKIP_OPEN
+#define PCS_DEC_SKIP_CLOSE
+#endif
 #define PCS_DEC_STEP_ASM(SHR)                                   \
       "{\n\t"                                                   \
-      ".reg .pred pact, pneed, pb, pnb;\n\t"                     \
+      ".reg .pred pact, pneed, pb, pnb, pz;\n\t"                 \
       ".reg .b32 t, m, x, pre, pm, r, q, sl, lim;\n\t"           \
       ".reg .b64 ad;\n\t"                                        \
       "and.b32 t, %6, %7;\n\t"                                   \
       "setp.ne.u32 pact, t, 0;\n\t"                              \
       "setp.eq.and.u32 pneed, %1, 0, pact;\n\t"                  \
       "vote.sync.ballot.b32 m, pneed, 0xffffffff;\n\t"           \
+      PCS_DEC_SKIP_OPEN                                          \
       "and.b32 x, m, %8;\n\t"                                    \
       "popc.b32 pre, x;\n\t"                                     \
       "popc.b32 pm, m;\n\t"                                      \
@@ -432,6 +455,7 @@ struct DecState { unsigned lower, size, slot, count, code, lt; };
       "@pneed ld.global.nc.u16 %4, [ad];\n\t"                    \
       "@pneed mov.u32 %1, 0xFFFF;\n\t"                           \
       "@pneed mov.u32 %0, 0;\n\t"                                \
+      PCS_DEC_SKIP_CLOSE                                         \
       "mul.lo.u32 r, %1, %9;\n\t"                                \
       SHR                                                        \
       "add.u32 t, q, 1;\n\t"                                     \

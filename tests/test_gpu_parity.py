@@ -377,7 +377,7 @@ for (W, H, wl, lossy, qs, B) in [(512, 384, 3, 0, 1.0, 3), (1024, 512, 4, 1, 1.0
         out.append(hashlib.sha256(c.cpu().numpy().tobytes()).hexdigest())
     s, lens = cd.encode_frames(px.cpu().numpy(), 0)
     out.append(hashlib.sha256(np.asarray(s).tobytes()).hexdigest())
-    back = cd.decode_frames(s, lens)   # inverse transform: levels 2+1 in one launch unless PCS_DWT_FUSE=1
+    back = cd.decode_frames(s, lens)
     if not lossy:
         assert np.array_equal(back, px.cpu().numpy())
     out.append(hashlib.sha256(np.asarray(back).tobytes()).hexdigest())
@@ -386,9 +386,10 @@ print("HASHES " + " ".join(out))
 
 
 def test_fused_levels_match_per_level_launches(lut_root):
-    """Levels 1+2 in one launch, forward and inverse (dwt_fused.cu: LL1 handed between level-1 and level-2 warps through
-    shared memory, TMA row loads; the default) against one launch per level (PCS_DWT_FUSE=1): same coefficients and same
-    decoded pixels bit for bit, also with short chunks (PCS_FUSED_RP) so that chunk seams and the LL1 ring wrap many times.  The switches are read once per
+    """Levels 1+2 of the forward transform in one launch (dwt_fused.cu: LL1 handed from producer to consumer warps through
+    shared memory, TMA row loads; the default) against one launch per level (PCS_DWT_FUSE=1): same coefficients, same
+    streams and same decoded pixels bit for bit, also with short chunks (PCS_FUSED_RP) so that chunk seams and the LL1 ring
+    wrap many times.  The switches are read once per
     process, hence the subprocesses."""
     import os
     import subprocess
