@@ -149,7 +149,7 @@ __device__ __forceinline__ void enc_step(unsigned abw, unsigned anbw, unsigned b
   asm volatile(
       "{\n\t"
       ".reg .pred pab, panb, pact, pneed, pz;\n\t"
-      ".reg .b32 t, m, x, pre, pm, r, q, sl;\n\t"
+      ".reg .b32 t, m, x, pre, pm, r, sl;\n\t"
       ".reg .b64 ad;\n\t"
       "and.b32 t, %4, %6;\n\t"
       "setp.ne.u32 pab, t, 0;\n\t"
@@ -157,9 +157,9 @@ __device__ __forceinline__ void enc_step(unsigned abw, unsigned anbw, unsigned b
       "setp.ne.u32 panb, t, 0;\n\t"
       "or.pred pact, pab, panb;\n\t"
       "setp.eq.and.u32 pneed, %1, 0, pact;\n\t"       // lanes that start a codeword at this call site,
+      "vote.sync.any.pred pz, pneed, 0xffffffff;\n\t"
+      "@!pz bra.uni LAB_ENC_NONEED;\n\t"               // warp-uniform: nobody starts a codeword here (about every other site)
       "vote.sync.ballot.b32 m, pneed, 0xffffffff;\n\t"  // served in lane order (BPCEngine.cu:376-384)
-      "setp.eq.u32 pz, m, 0;\n\t"
-      "@pz bra.uni LAB_ENC_NONEED;\n\t"                // warp-uniform: nobody starts a codeword here (about 2 sites in 3)
       "min.u32 sl, %2, %11;\n\t"
       "mad.wide.u32 ad, sl, 2, %10;\n\t"
       "@pneed st.global.u16 [ad], %0;\n\t"             // the codeword the lane has just completed (deferred store)
@@ -171,15 +171,14 @@ __device__ __forceinline__ void enc_step(unsigned abw, unsigned anbw, unsigned b
       "@pneed mov.u32 %1, 0xFFFF;\n\t"
       "@pneed mov.u32 %0, 0;\n\t"
       "LAB_ENC_NONEED:\n\t"
-      "mul.lo.u32 r, %1, %8;\n\t"
-      "shr.u32 q, r, %9;\n\t"
-      "add.u32 r, q, 1;\n\t"
+      "mad.lo.u32 r, %1, %8, %12;\n\t"                 // size * p + 2^prec ...
+      "shr.u32 r, r, %9;\n\t"                          // ... >> prec = q + 1
       "@pab sub.u32 %1, %1, r;\n\t"
       "@pab add.u32 %0, %0, r;\n\t"
-      "@panb mov.u32 %1, q;\n\t"
+      "@panb add.u32 %1, r, -1;\n\t"
       "}"
       : "+r"(c.lower), "+r"(c.size), "+r"(c.slot), "+r"(c.count)
-      : "r"(abw), "r"(anbw), "r"(bitm), "r"(c.lt), "r"(p), "r"(prec), "l"(out1), "n"(WORDS - 2)
+      : "r"(abw), "r"(anbw), "r"(bitm), "r"(c.lt), "r"(p), "r"(prec), "l"(out1), "n"(WORDS - 2), "r"(1u << prec)
       : "memory");
 #else
   const bool ab = (abw & bitm) != 0, anb = (anbw & bitm) != 0;
@@ -203,11 +202,11 @@ __device__ __forceinline__ void enc_step(unsigned abw, unsigned anbw, unsigned b
 #endif
 constexpr int kSppUnroll = PCS_SPP_UNROLL;
 
-// CTAs per SM the encoder is register-bounded for.  4 (128 registers): no spills at all -- smsp__inst_executed_op_local_ld/st
-// = 0.  5 (96 registers) spills 92 bytes: 9.2 M local loads + 4.0 M local stores in 3.13 G warp instructions per
-// 32 4K frames (0.4 %), and measures the same within noise (3.81 vs 3.83 ms; profiles/r2h_bpc_metrics.md).
+// CTAs per SM the encoder is register-bounded for.  Round 2 measured 4 (128 registers, no spills) and 5 (96 registers, 92 bytes
+// of spill) the same within noise (3.81 vs 3.83 ms per 32 4K frames, profiles/r2h_bpc_metrics.md); with the shorter coder step of
+// enc_step the extra warps pay: 3.29 ms at 4, 3.12 ms at 5 (profiles/r2s_bpc_variants.json; spill traffic is in r2t_bpc_metrics.md).
 #ifndef PCS_ENC_MINB
-#define PCS_ENC_MINB 4
+#define PCS_ENC_MINB 5
 #endif
 template <typename T, int ROWS>  // ROWS: codeblock length, 64 or 32 (the reference's CBLOCK_LENGTH, BPC/BPCEngine.cuh:33-36)
 __global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* __restrict__ coeff, unsigned short* __restrict__ cw,
@@ -429,21 +428,21 @@ struct DecState { unsigned lower, size, slot, count, code, lt; };
 #define PCS_DEC_SKIP_REFILL 1
 #endif
 #if PCS_DEC_SKIP_REFILL
-#define PCS_DEC_SKIP_OPEN "setp.eq.u32 pz, m, 0;\n\t@pz bra.uni LAB_NOREFILL;\n\t"
+#define PCS_DEC_SKIP_OPEN "vote.sync.any.pred pz, pneed, 0xffffffff;\n\t@!pz bra.uni LAB_NOREFILL;\n\tvote.sync.ballot.b32 m, pneed, 0xffffffff;\n\t"
 #define PCS_DEC_SKIP_CLOSE "LAB_NOREFILL:\n\t"
 #else
-#define PCS_DEC_SKIP_OPEN
+#define PCS_DEC_SKIP_OPEN "vote.sync.ballot.b32 m, pneed, 0xffffffff;\n\t"
 #define PCS_DEC_SKIP_CLOSE
 #endif
-#define PCS_DEC_STEP_ASM(SHR)                                   \
+// MULSHR: r = size * p + 2^prec; t = r >> prec  (= q + 1: the "+ 1" of the interval split rides on the multiply-add)
+#define PCS_DEC_STEP_ASM(MULSHR)                                \
       "{\n\t"                                                   \
       ".reg .pred pact, pneed, pb, pnb, pz;\n\t"                 \
-      ".reg .b32 t, m, x, pre, pm, r, q, sl, lim;\n\t"           \
+      ".reg .b32 t, m, x, pre, pm, r, sl, lim;\n\t"              \
       ".reg .b64 ad;\n\t"                                        \
       "and.b32 t, %6, %7;\n\t"                                   \
       "setp.ne.u32 pact, t, 0;\n\t"                              \
       "setp.eq.and.u32 pneed, %1, 0, pact;\n\t"                  \
-      "vote.sync.ballot.b32 m, pneed, 0xffffffff;\n\t"           \
       PCS_DEC_SKIP_OPEN                                          \
       "and.b32 x, m, %8;\n\t"                                    \
       "popc.b32 pre, x;\n\t"                                     \
@@ -456,14 +455,12 @@ struct DecState { unsigned lower, size, slot, count, code, lt; };
       "@pneed mov.u32 %1, 0xFFFF;\n\t"                           \
       "@pneed mov.u32 %0, 0;\n\t"                                \
       PCS_DEC_SKIP_CLOSE                                         \
-      "mul.lo.u32 r, %1, %9;\n\t"                                \
-      SHR                                                        \
-      "add.u32 t, q, 1;\n\t"                                     \
+      MULSHR                                                     \
       "add.u32 lim, %0, t;\n\t"                                  \
       "setp.ge.and.u32 pb|pnb, %4, lim, pact;\n\t"               \
       "@pb sub.u32 %1, %1, t;\n\t"                               \
       "@pb mov.u32 %0, lim;\n\t"                                 \
-      "@pnb mov.u32 %1, q;\n\t"                                  \
+      "@pnb add.u32 %1, t, -1;\n\t"                              \
       "selp.u32 %5, 1, 0, pb;\n\t"                               \
       "}"
 template <int PREC, int WORDS>
@@ -471,13 +468,13 @@ __device__ __forceinline__ unsigned dec_step(unsigned actw, unsigned bitm, unsig
                                              const unsigned short* in1, unsigned prec) {
   unsigned b;
   if constexpr (PREC == 7) {
-    asm volatile(PCS_DEC_STEP_ASM("shr.u32 q, r, 7;\n\t")
+    asm volatile(PCS_DEC_STEP_ASM("mad.lo.u32 r, %1, %9, 128;\n\tshr.u32 t, r, 7;\n\t")
                  : "+r"(c.lower), "+r"(c.size), "+r"(c.slot), "+r"(c.count), "+r"(c.code), "=r"(b)
                  : "r"(actw), "r"(bitm), "r"(c.lt), "r"(p), "r"(prec), "l"(in1), "n"(WORDS - 2)
                  : "memory");
     return b;
   }
-  asm volatile(PCS_DEC_STEP_ASM("shr.u32 q, r, %10;\n\t")
+  asm volatile(PCS_DEC_STEP_ASM("shl.b32 t, 1, %10;\n\tmad.lo.u32 r, %1, %9, t;\n\tshr.u32 t, r, %10;\n\t")
                : "+r"(c.lower), "+r"(c.size), "+r"(c.slot), "+r"(c.count), "+r"(c.code), "=r"(b)
                : "r"(actw), "r"(bitm), "r"(c.lt), "r"(p), "r"(prec), "l"(in1), "n"(WORDS - 2)
                : "memory");
@@ -489,6 +486,12 @@ __device__ __forceinline__ unsigned dec_step(unsigned actw, unsigned bitm, unsig
 // instructions, 0.03 %): 4 CTAs per SM is spill-free but 1.8 % slower (6.08 vs 5.98 ms per 32 4K frames).
 #ifndef PCS_DEC_MINB
 #define PCS_DEC_MINB 5
+#endif
+// The nibble-transposed context words of a 32-row half are pinned where they are computed (PCS_DEC_PIN = 2); the compiler
+// otherwise re-derives single words of the transposition network inside the row loop (about ten instructions per use).
+// cfg4, 32 frames: 5.14 ms unpinned, 5.04 sign-context words only (1), 4.92 all sixteen (2); profiles/r2s_bpc_variants.json.
+#ifndef PCS_DEC_PIN
+#define PCS_DEC_PIN 2
 #endif
 __device__ __forceinline__ unsigned lds_u8(unsigned addr) {
   unsigned v;
@@ -519,7 +522,9 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
   // from the CTA's shared window at every use (4 uniform-datapath instructions per sign call site)
   unsigned sgn0 = (unsigned)__cvta_generic_to_shared(s_sign);
   asm volatile("mov.u32 %0, %0;" : "+r"(sgn0));
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  // Everything the control flow of this kernel depends on is the same in all lanes of a warp; the broadcasts below tell
+  // the compiler so (it otherwise guards every vote / redux of the coder with a divergence check: 30 BRA.DIV + UMOV pairs).
+  const int lane = threadIdx.x & 31, wib = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
   const int w = blockIdx.x * (blockDim.x >> 5) + wib;
   if (w >= p.total_cb) return;
   const int frame = (w / p.ncb) * p.pstep + p.pfirst, cb = w % p.ncb;
@@ -528,8 +533,8 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
   int* dst = q + (size_t)frame * p.A + (size_t)(by * ROWS) * p.Wa + bx * kCB + 2 * lane;
   const size_t blk = (size_t)frame * p.ncb + cb;
   const unsigned short* in = cw + blk * kWords;
-  const int size = sizes[blk];
-  const int MSB = in[0];
+  const int size = __shfl_sync(kFull, sizes[blk], 0);
+  const int MSB = __shfl_sync(kFull, (int)in[0], 0);
   unsigned (*pl)[32] = s_pl[wib];
 
   if (size == kWords) {  // raw block (BPCEngine.cu:2197-2200,1914-1922,94-111)
@@ -591,6 +596,12 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
         unsigned c1[4];
         nibble_net(n0); nibble_net(n1); nibble_net(c0);
         nibble_net2((unsigned)(Ds1 >> sh), (unsigned)(Dn1 >> sh), c1);
+#if PCS_DEC_PIN >= 1
+        asm volatile("" : "+r"(c0[0]), "+r"(c0[1]), "+r"(c0[2]), "+r"(c0[3]), "+r"(c1[0]), "+r"(c1[1]), "+r"(c1[2]), "+r"(c1[3]));
+#endif
+#if PCS_DEC_PIN >= 2
+        asm volatile("" : "+r"(n0[0]), "+r"(n0[1]), "+r"(n0[2]), "+r"(n0[3]), "+r"(n1[0]), "+r"(n1[1]), "+r"(n1[2]), "+r"(n1[3]));
+#endif
 #pragma unroll 1
         for (int g = 0; g < 8; ++g) {  // rows 4g .. 4g+3
           const int r0 = 4 * g;
