@@ -33,21 +33,25 @@ namespace {
 typedef unsigned long long u64;
 constexpr unsigned kFull = 0xffffffffu;
 
-__device__ __forceinline__ void add3(u64 a, u64 b, u64 c, u64& s, u64& cy) {
+template <typename W> __device__ __forceinline__ void add3(W a, W b, W c, W& s, W& cy) {
   s = a ^ b ^ c;
   cy = (a & b) | (c & (a ^ b));
 }
-// bit-sliced population count of 8 one-bit row masks -> 4 bit planes (value 0..8 per row)
-__device__ __forceinline__ void count8(u64 m0, u64 m1, u64 m2, u64 m3, u64 m4, u64 m5, u64 m6, u64 m7, u64 k[4]) {
-  u64 s1, c1, s2, c2, b0, c4, s5, c5;
+// bit-sliced population count of 8 one-bit row masks -> 4 bit planes (value 0..8 per row); W = u64 (64 rows) or unsigned (32)
+template <typename W> __device__ __forceinline__ void count8(W m0, W m1, W m2, W m3, W m4, W m5, W m6, W m7, W (&k)[4]) {
+  W s1, c1, s2, c2, b0, c4, s5, c5;
   add3(m0, m1, m2, s1, c1);
   add3(m3, m4, m5, s2, c2);
-  const u64 s3 = m6 ^ m7, c3 = m6 & m7;
+  const W s3 = m6 ^ m7, c3 = m6 & m7;
   add3(s1, s2, s3, b0, c4);
   add3(c1, c2, c3, s5, c5);
-  const u64 c6 = s5 & c4;
+  const W c6 = s5 & c4;
   k[0] = b0; k[1] = s5 ^ c4; k[2] = c5 ^ c6; k[3] = c5 & c6;
 }
+// rows [sh, sh + 32) of a 64-row mask; of the mask moved one row down (row i holds x[i-1]) / one row up (x[i+1])
+__device__ __forceinline__ unsigned rows32(u64 x, int sh) { return (unsigned)(x >> sh); }
+__device__ __forceinline__ unsigned rows32_prev(u64 x, int sh) { return (unsigned)((x << 1) >> sh); }
+__device__ __forceinline__ unsigned rows32_next(u64 x, int sh) { return (unsigned)((x >> 1) >> sh); }
 
 __device__ __forceinline__ u64 shfl_up64(u64 v, int lane) {
   unsigned lo = __shfl_up_sync(kFull, (unsigned)v, 1), hi = __shfl_up_sync(kFull, (unsigned)(v >> 32), 1);
@@ -564,17 +568,6 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
     const unsigned char* const prob = s_prob + 16 * ((row >= 0 && row < zero_row) ? row : zero_row);
     const unsigned pref = prob[9];
     const u64 Lb = shfl_up64(s1, lane), Lg = shfl_up64(g1, lane), Rb = shfl_down64(s0, lane);
-    // static part of the contexts: state BEFORE this pass of all eight neighbours
-    u64 K0[4], K1[4];
-    count8(Lb << 1, s0 << 1, s1 << 1, Lb, s1, Lb >> 1, s0 >> 1, s1 >> 1, K0);
-    count8(s0 << 1, s1 << 1, Rb << 1, s0, Rb, s0 >> 1, s1 >> 1, Rb >> 1, K1);
-    // static sign-context inputs.  Column 0: its horizontal pair (left lane's column 1, own column 1) is not
-    // visited before it -> the sign of their sum, presented as a fake "left" neighbour; the sample below is
-    // never visited before.
-    const u64 Lp = Lb & ~Lg, Ln = Lb & Lg, Rp = s1 & ~g1, Rn = s1 & g1;
-    const u64 Hp0 = (Lp & ~Rn) | (Rp & ~Ln), Hn0 = (Ln & ~Rp) | (Rn & ~Lp);
-    const u64 Hs0 = Hp0 | Hn0;                                   // |h| != 0
-    const u64 Ds0 = s0 >> 1, Dn0 = (s0 & g0) >> 1, Ds1 = s1 >> 1, Dn1 = (s1 & g1) >> 1;
 
     u64 B0 = 0, B1 = 0;  // decoded 1-bits of this plane
     u64 N0 = 0, N1 = 0;  // newly significant in this pass
@@ -584,18 +577,30 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
 #pragma unroll 1
     for (int h = 0; h < kHalves; ++h) {
       const int sh = 32 * h;
-      const unsigned S0 = (unsigned)(s0 >> sh), S1 = (unsigned)(s1 >> sh), G0 = (unsigned)(g0 >> sh), G1 = (unsigned)(g1 >> sh);
+      const unsigned S0 = rows32(s0, sh), S1 = rows32(s1, sh), G0 = rows32(g0, sh), G1 = rows32(g1, sh);
       const unsigned A0 = ~S0, A1 = ~S1;
       const unsigned anyact = __reduce_or_sync(kFull, A0 | A1);
       // this half's decoded bits (= new flags) and new signs; rows are shifted in from the top, so row i ends at bit i
       unsigned nb0 = 0, nb1 = 0, ng0 = 0, ng1 = 0;
       if (anyact != 0) {
-        unsigned n0[4] = {(unsigned)(K0[0] >> sh), (unsigned)(K0[1] >> sh), (unsigned)(K0[2] >> sh), (unsigned)(K0[3] >> sh)};
-        unsigned n1[4] = {(unsigned)(K1[0] >> sh), (unsigned)(K1[1] >> sh), (unsigned)(K1[2] >> sh), (unsigned)(K1[3] >> sh)};
-        unsigned c0[4] = {(unsigned)(Hs0 >> sh), (unsigned)(Hn0 >> sh), (unsigned)(Ds0 >> sh), (unsigned)(Dn0 >> sh)};
+        // Static part of the contexts of these 32 rows: state BEFORE this pass of all eight neighbours.  Built per half from
+        // the 64-row state words, on 32-bit slices, so that only those words stay live across the row loop.
+        const unsigned Lbs = rows32(Lb, sh), Rbs = rows32(Rb, sh);
+        unsigned n0[4], n1[4];
+        count8(rows32_prev(Lb, sh), rows32_prev(s0, sh), rows32_prev(s1, sh), Lbs, S1, rows32_next(Lb, sh), rows32_next(s0, sh),
+               rows32_next(s1, sh), n0);
+        count8(rows32_prev(s0, sh), rows32_prev(s1, sh), rows32_prev(Rb, sh), S0, Rbs, rows32_next(s0, sh), rows32_next(s1, sh),
+               rows32_next(Rb, sh), n1);
+        // static sign-context inputs.  Column 0: its horizontal pair (left lane's column 1, own column 1) is not
+        // visited before it -> the sign of their sum, presented as a fake "left" neighbour; the sample below is
+        // never visited before.
+        const unsigned Lgs = rows32(Lg, sh);
+        const unsigned Lp = Lbs & ~Lgs, Ln = Lbs & Lgs, Rp = S1 & ~G1, Rn = S1 & G1;
+        const unsigned Hp0 = (Lp & ~Rn) | (Rp & ~Ln), Hn0 = (Ln & ~Rp) | (Rn & ~Lp);
+        unsigned c0[4] = {Hp0 | Hn0 /* |h| != 0 */, Hn0, rows32_next(s0, sh), rows32_next(s0 & g0, sh)};
         unsigned c1[4];
         nibble_net(n0); nibble_net(n1); nibble_net(c0);
-        nibble_net2((unsigned)(Ds1 >> sh), (unsigned)(Dn1 >> sh), c1);
+        nibble_net2(rows32_next(s1, sh), rows32_next(s1 & g1, sh), c1);
 #if PCS_DEC_PIN >= 1
         asm volatile("" : "+r"(c0[0]), "+r"(c0[1]), "+r"(c0[2]), "+r"(c0[3]), "+r"(c1[0]), "+r"(c1[1]), "+r"(c1[2]), "+r"(c1[3]));
 #endif
@@ -613,7 +618,10 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
             nb0 >>= 4; nb1 >>= 4; ng0 >>= 4; ng1 >>= 4;
             continue;
           }
-          const unsigned a40 = A0 >> r0, a41 = A1 >> r0, s40 = S0 >> r0, s41 = S1 >> r0, g40 = G0 >> r0, g41 = G1 >> r0;
+          unsigned a40 = A0 >> r0, a41 = A1 >> r0, s40 = S0 >> r0, s41 = S1 >> r0, g40 = G0 >> r0, g41 = G1 >> r0;
+#if PCS_DEC_PIN >= 3
+          asm volatile("" : "+r"(a40), "+r"(a41), "+r"(s40), "+r"(s41), "+r"(g40), "+r"(g41));  // one shift per group, not per use
+#endif
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) {
             const unsigned bitm = 1u << qq;
