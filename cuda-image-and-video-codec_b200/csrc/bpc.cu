@@ -24,6 +24,8 @@
 //   * codeword slot reservation is an explicit __ballot_sync over "lanes of this call whose interval
 //     is exhausted" instead of __activemask() inside divergent code;
 //   * codewords are written as uint16 (the reference writes int32 and narrows later).
+#include <algorithm>
+
 #include "pcs_common.cuh"
 
 namespace pcs {
@@ -206,11 +208,11 @@ __device__ __forceinline__ void enc_step(unsigned abw, unsigned anbw, unsigned b
 #endif
 constexpr int kSppUnroll = PCS_SPP_UNROLL;
 
-// CTAs per SM the encoder is register-bounded for.  Round 2 measured 4 (128 registers, no spills) and 5 (96 registers, 92 bytes
-// of spill) the same within noise (3.81 vs 3.83 ms per 32 4K frames, profiles/r2h_bpc_metrics.md); with the shorter coder step of
-// enc_step the extra warps pay: 3.29 ms at 4, 3.12 ms at 5 (profiles/r2s_bpc_variants.json; spill traffic is in r2t_bpc_metrics.md).
+// CTAs per SM the encoder is register-bounded for (32 KB of shared memory per CTA allow 6).  The coder step is short and
+// latency-bound, so resident warps pay: 3.48 ms per 32 4K frames at 4 CTAs (128 registers), 3.15 at 5 (96), 2.98 at 6 (80
+// registers, 56 bytes of spill; profiles/r2w_bpc_occupancy.json, spill traffic in profiles/r2x_bpc_metrics.md).
 #ifndef PCS_ENC_MINB
-#define PCS_ENC_MINB 5
+#define PCS_ENC_MINB 6
 #endif
 template <typename T, int ROWS>  // ROWS: codeblock length, 64 or 32 (the reference's CBLOCK_LENGTH, BPC/BPCEngine.cuh:33-36)
 __global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* __restrict__ coeff, unsigned short* __restrict__ cw,
@@ -281,51 +283,56 @@ __global__ void __launch_bounds__(128, PCS_ENC_MINB) bpc_encode_kernel(const T* 
     const u64 a0 = s0 | B0, a1 = s1 | B1;  // significant AFTER this plane's SPP visit
     const u64 Lb = shfl_up64(s1, lane), La = shfl_up64(a1, lane);
     const u64 Rb = shfl_down64(s0, lane), Ra = shfl_down64(a0, lane);
-    // significance contexts of all 64 rows (BPCEngine.cu:222-230 with the visit-order rule of :770-843):
-    // rows above and same-row samples visited earlier use the "after" state, everything else "before".
-    u64 K0[4], K1[4];
-    count8(La << 1, a0 << 1, a1 << 1, Lb, s1, Lb >> 1, s0 >> 1, s1 >> 1, K0);
-    count8(a0 << 1, a1 << 1, Ra << 1, a0, Ra, s0 >> 1, s1 >> 1, Rb >> 1, K1);
-    // sign contexts (BPCEngine.cu:252-308) bit-sliced: pos/neg contribution of L,R (h) and U,D (v)
-    u64 SY0, I00, I01, SY1, I10, I11;
-    {
-      const u64 Lp = Lb & ~Lg, Ln = Lb & Lg, Rp = s1 & ~g1, Rn = s1 & g1;
-      const u64 Us = a0 << 1, Ug = g0 << 1, Ds = s0 >> 1, Dg = g0 >> 1;
-      const u64 Up = Us & ~Ug, Un = Us & Ug, Dp = Ds & ~Dg, Dn = Ds & Dg;
-      const u64 hp = (Lp & ~Rn) | (Rp & ~Ln), hn = (Ln & ~Rp) | (Rn & ~Lp);
-      const u64 vp = (Up & ~Dn) | (Dp & ~Un), vn = (Un & ~Dp) | (Dn & ~Up);
-      const u64 both = (hp & vp) | (hn & vn);
-      SY0 = g0 ^ (hn | (~hp & vn));
-      I00 = (~(hp | hn) & (vp | vn)) | both;
-      I01 = ((hp | hn) & ~(vp | vn)) | both;
-    }
-    {
-      const u64 Lp = a0 & ~g0, Ln = a0 & g0, Rp = Ra & ~Rg, Rn = Ra & Rg;
-      const u64 Us = a1 << 1, Ug = g1 << 1, Ds = s1 >> 1, Dg = g1 >> 1;
-      const u64 Up = Us & ~Ug, Un = Us & Ug, Dp = Ds & ~Dg, Dn = Ds & Dg;
-      const u64 hp = (Lp & ~Rn) | (Rp & ~Ln), hn = (Ln & ~Rp) | (Rn & ~Lp);
-      const u64 vp = (Up & ~Dn) | (Dp & ~Un), vn = (Un & ~Dp) | (Dn & ~Up);
-      const u64 both = (hp & vp) | (hn & vn);
-      SY1 = g1 ^ (hn | (~hp & vn));
-      I10 = (~(hp | hn) & (vp | vn)) | both;
-      I11 = ((hp | hn) & ~(vp | vn)) | both;
-    }
-
     // ---- significance propagation pass: rows in order, column 0 then column 1 (BPCEngine.cu:770-843) ----
+    // The context words of a 32-row half are built inside the loop, on 32-bit slices of the 64-row state words, so that only
+    // those state words stay live across the coding loop (the 64-row versions cost 28 more registers for the same work).
 #pragma unroll 1
     for (int h = 0; h < kHalves; ++h) {
       const int sh = 32 * h;
-      const unsigned A0 = ~(unsigned)(s0 >> sh), A1 = ~(unsigned)(s1 >> sh);
+      const unsigned S0 = rows32(s0, sh), S1 = rows32(s1, sh);
+      const unsigned A0 = ~S0, A1 = ~S1;
       const unsigned anyact = __reduce_or_sync(kFull, A0 | A1);  // rows of this half in which some lane codes a symbol
       if (anyact == 0) continue;
-      const unsigned b0 = (unsigned)(B0 >> sh), b1 = (unsigned)(B1 >> sh), y0 = (unsigned)(SY0 >> sh), y1 = (unsigned)(SY1 >> sh);
-      unsigned n0[4] = {(unsigned)(K0[0] >> sh), (unsigned)(K0[1] >> sh), (unsigned)(K0[2] >> sh), (unsigned)(K0[3] >> sh)};
-      unsigned n1[4] = {(unsigned)(K1[0] >> sh), (unsigned)(K1[1] >> sh), (unsigned)(K1[2] >> sh), (unsigned)(K1[3] >> sh)};
+      const unsigned b0 = rows32(B0, sh), b1 = rows32(B1, sh), G0 = rows32(g0, sh), G1 = rows32(g1, sh);
+      const unsigned a0s = S0 | b0, Lbs = rows32(Lb, sh), Ras = rows32(Ra, sh);
+      // significance contexts (BPCEngine.cu:222-230 with the visit-order rule of :770-843):
+      // rows above and same-row samples visited earlier use the "after" state, everything else "before".
+      unsigned n0[4], n1[4];
+      count8(rows32_prev(La, sh), rows32_prev(a0, sh), rows32_prev(a1, sh), Lbs, S1, rows32_next(Lb, sh), rows32_next(s0, sh),
+             rows32_next(s1, sh), n0);
+      count8(rows32_prev(a0, sh), rows32_prev(a1, sh), rows32_prev(Ra, sh), a0s, Ras, rows32_next(s0, sh), rows32_next(s1, sh),
+             rows32_next(Rb, sh), n1);
+      // sign contexts (BPCEngine.cu:252-308) bit-sliced: pos/neg contribution of L,R (h) and U,D (v)
+      unsigned y0, I00, I01, y1, I10, I11;
+      {
+        const unsigned Lgs = rows32(Lg, sh);
+        const unsigned Lp = Lbs & ~Lgs, Ln = Lbs & Lgs, Rp = S1 & ~G1, Rn = S1 & G1;
+        const unsigned Us = rows32_prev(a0, sh), Ug = rows32_prev(g0, sh), Ds = rows32_next(s0, sh), Dg = rows32_next(g0, sh);
+        const unsigned Up = Us & ~Ug, Un = Us & Ug, Dp = Ds & ~Dg, Dn = Ds & Dg;
+        const unsigned hp = (Lp & ~Rn) | (Rp & ~Ln), hn = (Ln & ~Rp) | (Rn & ~Lp);
+        const unsigned vp = (Up & ~Dn) | (Dp & ~Un), vn = (Un & ~Dp) | (Dn & ~Up);
+        const unsigned both = (hp & vp) | (hn & vn);
+        y0 = G0 ^ (hn | (~hp & vn));
+        I00 = (~(hp | hn) & (vp | vn)) | both;
+        I01 = ((hp | hn) & ~(vp | vn)) | both;
+      }
+      {
+        const unsigned Rgs = rows32(Rg, sh);
+        const unsigned Lp = a0s & ~G0, Ln = a0s & G0, Rp = Ras & ~Rgs, Rn = Ras & Rgs;
+        const unsigned Us = rows32_prev(a1, sh), Ug = rows32_prev(g1, sh), Ds = rows32_next(s1, sh), Dg = rows32_next(g1, sh);
+        const unsigned Up = Us & ~Ug, Un = Us & Ug, Dp = Ds & ~Dg, Dn = Ds & Dg;
+        const unsigned hp = (Lp & ~Rn) | (Rp & ~Ln), hn = (Ln & ~Rp) | (Rn & ~Lp);
+        const unsigned vp = (Up & ~Dn) | (Dp & ~Un), vn = (Un & ~Dp) | (Dn & ~Up);
+        const unsigned both = (hp & vp) | (hn & vn);
+        y1 = G1 ^ (hn | (~hp & vn));
+        I10 = (~(hp | hn) & (vp | vn)) | both;
+        I11 = ((hp | hn) & ~(vp | vn)) | both;
+      }
       const bool has8 = (n0[3] | n1[3]) != 0;  // some row of this lane has all 8 neighbours significant
       nibble_net(n0); nibble_net(n1);
       unsigned i0[4], i1[4];
-      nibble_net2((unsigned)(I00 >> sh), (unsigned)(I01 >> sh), i0);
-      nibble_net2((unsigned)(I10 >> sh), (unsigned)(I11 >> sh), i1);
+      nibble_net2(I00, I01, i0);
+      nibble_net2(I10, I11, i1);
 #pragma unroll 1
       for (int jj = 0; jj < 2; ++jj) {
         // probabilities of rows 16*jj + 4*t + q: byte t of P?[q] (significance) and S?[q] (sign)
@@ -513,7 +520,7 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
   unsigned char* const s_sign0 = s_sign;
   unsigned char* const s_sign1 = s_sign + 64;
   // probability bytes per table row: [0..8] significance contexts, [9] refinement, [12..15] sign contexts
-  __shared__ uint4 s_tab[kMaxProbRows + 1];
+  extern __shared__ uint4 s_tab[];  // min(nrows, kMaxProbRows) + 1 rows (the launch sizes it): a 4K / wl = 5 table is 4 KB, not 8
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     s_sign1[i] = (unsigned char)sign_entry1((unsigned)i);
     if (i < 64) s_sign0[i] = (unsigned char)sign_entry0((unsigned)i);
@@ -1053,12 +1060,13 @@ int bpc_encode(const void* d_coeff, bool is_float, uint16_t* d_cw, int32_t* d_si
 
 int bpc_decode(const uint16_t* d_cw, const int32_t* d_sizes, int32_t* d_q, const BpcArgs& a, cudaStream_t st) {
   const int blocks = (a.total_cb + 3) / 4;
+  const size_t tab_bytes = ((size_t)std::min(a.nrows, kMaxProbRows) + 1) * sizeof(uint4);  // + the all-zero row
   if (a.cb_rows == 32) {
-    if (a.prec == 7) bpc_decode_kernel<7, 32><<<blocks, 128, 0, st>>>(d_cw, d_sizes, d_q, a);
-    else bpc_decode_kernel<0, 32><<<blocks, 128, 0, st>>>(d_cw, d_sizes, d_q, a);
+    if (a.prec == 7) bpc_decode_kernel<7, 32><<<blocks, 128, tab_bytes, st>>>(d_cw, d_sizes, d_q, a);
+    else bpc_decode_kernel<0, 32><<<blocks, 128, tab_bytes, st>>>(d_cw, d_sizes, d_q, a);
   } else {
-    if (a.prec == 7) bpc_decode_kernel<7, 64><<<blocks, 128, 0, st>>>(d_cw, d_sizes, d_q, a);
-    else bpc_decode_kernel<0, 64><<<blocks, 128, 0, st>>>(d_cw, d_sizes, d_q, a);
+    if (a.prec == 7) bpc_decode_kernel<7, 64><<<blocks, 128, tab_bytes, st>>>(d_cw, d_sizes, d_q, a);
+    else bpc_decode_kernel<0, 64><<<blocks, 128, tab_bytes, st>>>(d_cw, d_sizes, d_q, a);
   }
   ++g_launches;
   return (int)cudaGetLastError();
