@@ -570,6 +570,7 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
   const unsigned short* const in1 = in + 1;
   const unsigned prec = (unsigned)p.prec;
   DecState ac; ac.lower = 0; ac.size = 0; ac.slot = 0; ac.count = 0; ac.code = 0; ac.lt = (1u << lane) - 1u;
+  const unsigned not31 = lane == 31 ? 0u : ~0u, not0 = lane == 0 ? 0u : ~0u;  // masks for the shuffled neighbour words
   u64 s0 = 0, s1 = 0, g0 = 0, g1 = 0;  // significant before this plane; sign (1 = negative) of significant samples
   for (int bp = MSB; bp >= 0; --bp, --row) {
     const unsigned char* const prob = s_prob + 16 * ((row >= 0 && row < zero_row) ? row : zero_row);
@@ -646,7 +647,7 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
             const unsigned cur0 = (((s40 >> qq) & 1u) | cn0) | (neg0 << 1);  // significant | negative << 1
             // right neighbour's (i, column 0): state and new flag
             unsigned rv = __shfl_down_sync(kFull, cur0 | (cn0 << 2), 1);
-            if (lane == 31) rv = 0;
+            rv &= not31;  // no right neighbour outside the codeblock
             const unsigned cnr = rv >> 2;
             // ---- column 1 ----
             ctx = (n1[qq] >> r0) + pns + pnr + cn0 + cnr;
@@ -660,7 +661,7 @@ __global__ void __launch_bounds__(128, PCS_DEC_MINB) bpc_decode_kernel(const uns
             nb1 = __funnelshift_r(nb1, cn1, 1); ng1 = __funnelshift_r(ng1, cn1 & neg1, 1);
             const unsigned cur1 = (((s41 >> qq) & 1u) | cn1) | (neg1 << 1);
             unsigned lv = __shfl_up_sync(kFull, cn1, 1);
-            if (lane == 0) lv = 0;
+            lv &= not0;
             pns = cn0 + cn1; pnl = lv; pnr = cnr;
             u0 = cur0 << 4; u1 = cur1 << 6;
           }
