@@ -529,8 +529,8 @@ static size_t ll_offset(int Wa, int Ha, int l) {
   return n;
 }
 
-bool dwt_forward_fast_ok(const void*, const void*, const void*, bool, int, long long, int, int, int, int);
-int dwt_forward_fast(const void*, bool, long long, int, int, int, int, void*, long long, int, void*, long long, int, int, int, int, bool, float,
+bool dwt_forward_fast_ok(const void*, const void*, const void*, bool, int, long long, int, int, int);
+int dwt_forward_fast(const void*, bool, long long, int, int, int, int, void*, long long, int, void*, long long, int, int, int, bool, float,
                      bool, int, cudaStream_t, bool rgb, long long comp_stride, int offset);
 
 bool dwt_inverse_fast_ok(const void*, const void*, const void*, bool, int, long long, int, long long, int, int);
@@ -578,14 +578,13 @@ static int dwt_forward_levels(const uint8_t* d_px, void* d_coeff, void* d_scratc
     const void* src = u8 ? static_cast<const void*>(d_px) : l == 1 ? tplane : static_cast<const char*>(d_scratch) + ll_offset(Wa, Ha, l - 1) * 4;
     const long long sfs = u8 ? (long long)W * H * (rgb_px ? 3 : 1) : l == 1 ? (long long)A : (long long)S;
     const int sp = u8 ? W : Wc;
-    const int lv = 1;
     void* ll = (l == wl) ? nullptr : static_cast<char*>(d_scratch) + ll_offset(Wa, Ha, l) * 4;
-    if (!dwt_forward_fast_ok(src, d_coeff, ll, u8, sp, sfs, H, Wc, Hc, lv)) break;
+    if (!dwt_forward_fast_ok(src, d_coeff, ll, u8, sp, sfs, H, Wc, Hc)) break;
     if (S % 4) break;
-    int rc = dwt_forward_fast(src, u8, sfs, sp, H, Wc, Hc, d_coeff, (long long)A, Wa, ll, (long long)S, Wa >> (l + lv - 1), l, lv, wl, lossy,
+    int rc = dwt_forward_fast(src, u8, sfs, sp, H, Wc, Hc, d_coeff, (long long)A, Wa, ll, (long long)S, Wa >> l, l, wl, lossy,
                               qs, out_int, frames, st, u8 && rgb_px, (long long)W * H, offset);
     if (rc) return rc;
-    first = l + lv;
+    first = l + 1;
   }
   for (int l = first; l <= llast; ++l) {
     FwdArgs a{};
@@ -707,7 +706,7 @@ bool dwt_forward_rgb_ok(const uint8_t* d_px, const void* d_coeff, const void* d_
   const size_t S = dwt_scratch_elems(Wa, Ha, wl);
   const void* ll = wl == 1 ? nullptr : static_cast<const char*>(d_scratch) + ll_offset(Wa, Ha, 1) * 4;
   return fuse_mode() > 0 && S % 4 == 0 && ((long long)W * H) % 8 == 0 &&
-         dwt_forward_fast_ok(d_px, d_coeff, ll, true, W, (long long)W * H * 3, H, Wa, Ha, 1);
+         dwt_forward_fast_ok(d_px, d_coeff, ll, true, W, (long long)W * H * 3, H, Wa, Ha);
 }
 int dwt_forward_rgb(const uint8_t* d_px, void* d_coeff, void* d_scratch, int W, int H, int Wa, int Ha, int wl, bool lossy, float qs,
                     bool out_int, int planes, cudaStream_t st) {

@@ -14,8 +14,8 @@
 // lifting of a finished row pair needs four shuffles; image borders are explicit mirror rules in the lifting steps, so
 // halo lanes outside the image never influence a result.  Bandwidth-critical inputs (u8 pixels forward, subband rows
 // of the finest inverse level) are staged through a per-warp cp.async ring; 9/7 arithmetic is issued as packed
-// f32x2 instructions.  Also in this file, both off by default and kept as measured experiments: levels
-// 1+2 fused in one warp (LEVELS = 2) and all levels as one dependency-ordered persistent work queue.
+// f32x2 instructions.  (Levels 1+2 of the forward transform of u8 frames normally go through dwt_fused.cu; the in-warp fusion of
+// two levels and the persistent work queue this file once carried were measured, lost, and are gone: DESIGN.md 4.1.)
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -35,8 +35,8 @@ struct FastFwdArgs {
   void* out; long long out_fstride; int pitch;              // Mallat plane and its row pitch (the adapted frame width)
   void* ll; long long ll_fstride; int ll_pitch;             // LL destination of the LAST level of this launch (scratch), unless `last`
   int last;                                                 // that level is the last level: LL goes to `out`, quantised
-  float q1[4], q2[4], qs;                                   // quantiser steps of the first / second level of this launch: LL, HL, LH, HH
-  int nW1, ls1, nW2, ls2;                                   // row-variant tiling of the reference, per level (9/7 only)
+  float q1[4], qs;                                          // quantiser steps of this level: LL, HL, LH, HH
+  int nW1, ls1;                                             // row-variant tiling of the reference (9/7 only)
   int nstrips, nchunks, rp;                                 // rp: row pairs per chunk (multiple of 4)
   long long comp_stride;                                    // RGB input: bytes between the R, G and B planes of a frame
   int offset;                                               // u8 input: level shift 2^(bps-1), 0 for signed samples
@@ -61,10 +61,8 @@ __device__ __forceinline__ void rgb_component(int comp, const float (&r)[8], con
     upk(fma2(pk(b[j], b[j + 1]), M2, fma2(pk(r[j], r[j + 1]), M0, mul2(pk(g[j], g[j + 1]), M1))), v[j], v[j + 1]);
 }
 
-// One work item = one 256-column strip x one chunk of row pairs of one frame, one level (LEVELS = 1; LL -> scratch or,
-// if last, -> out) or two fused levels (LEVELS = 2, u8 input only).  SRC_U8: the input is the u8 frame (level 1), else
-// the 32-bit LL plane of the level above.  COH: that plane was written by other SMs during this very launch (queue
-// kernel below), so it is read through L2 (ld.global.cg) instead of the non-coherent path.
+// One work item = one 256-column strip x one chunk of row pairs of one frame, one level (LL -> scratch or, if last, -> out).
+// SRC_U8: the input is the u8 frame (level 1), else the 32-bit LL plane of the level above.
 #ifndef PCS_FWD_PF2
 #define PCS_FWD_PF2 1
 #endif
@@ -82,18 +80,17 @@ typedef unsigned char FwdRing[kFwdDepth][2][32][8];
 #endif
 // RGB (u8 input, one level): `frame` is a component PLANE 3f + c of planar RGB frames; the three colour planes of
 // frame f are staged side by side (ringp[0..2]) and the colour transform runs in the load.
-template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS, bool QS1, bool COH, bool RGB = false>
+template <bool LOSSY, typename OT, bool SRC_U8, bool QS1, bool RGB = false>
 __device__ __forceinline__ void fwd_item(const FastFwdArgs& a, const int strip, const int chunk, const int frame, FwdRing* const ringp) {
-  static_assert(!RGB || (SRC_U8 && LEVELS == 1), "the fused colour transform reads u8 pixels and feeds one level");
+  static_assert(!RGB || SRC_U8, "the fused colour transform reads u8 pixels");
   using T = typename VSel<LOSSY, 8>::T;
   using VP1 = typename VSel<LOSSY, 8>::type;
-  using VP2 = typename VSel<LOSSY, 4>::type;
   using RowT = typename std::conditional<SRC_U8, uint2, Row8<T>>::type;
   constexpr bool kPf2 = kPf2On && LOSSY;
   const int lane = threadIdx.x & 31;
-  constexpr int kHalo = LEVELS;                        // halo lanes per side
+  constexpr int kHalo = 1;                             // halo lanes per side
   constexpr int kEff = (32 - 2 * kHalo) * 8;           // effective columns per strip
-  const int Wc = a.Wc, Hc = a.Hc, hw1 = Wc >> 1, hh1 = Hc >> 1, hw2 = Wc >> 2, hh2 = Hc >> 2;
+  const int Wc = a.Wc, Hc = a.Hc, hw1 = Wc >> 1, hh1 = Hc >> 1;
   const int c0 = strip * kEff - 8 * kHalo + 8 * lane;  // first of the lane's 8 columns
   const bool inimg = c0 >= 0 && c0 < Wc;
   const bool wlane = lane >= kHalo && lane < 32 - kHalo && inimg;
@@ -107,13 +104,9 @@ __device__ __forceinline__ void fwd_item(const FastFwdArgs& a, const int strip, 
   T* const llbase = a.last ? nullptr : static_cast<T*>(a.ll) + (size_t)frame * a.ll_fstride;
   const float qs = a.qs;
 
-  // first-level row pairs [n0, n1) and second-level row pairs [m2_0, m2_1) are written by this chunk
+  // row pairs [n0, n1) are written by this chunk
   const int n0 = chunk * a.rp, n1 = min(n0 + a.rp, hh1);
-  const int m2_0 = n0 >> 1, m2_1 = n1 >> 1;
-  const int M0 = max(m2_0 - VP2::kWarm, 0);  // first second-level step; it starts from LL row 2*M0
-  // first / last first-level pair whose output is needed (by that level itself and by the second one)
-  const int P0 = LEVELS == 2 ? min(n0, 2 * M0) : n0;
-  const int Plast = LEVELS == 2 ? min(max(n1 - 1, 2 * (m2_1 - 1 + VP2::kDelay) + 2), hh1 - 1) : n1 - 1;
+  const int P0 = n0, Plast = n1 - 1;  // first / last pair whose output is needed
 
   // Row staging.  u8 input (level 1, the bandwidth-critical launch): every lane cp.async-copies its own 8
   // bytes of the rows of the next kDepth steps into a per-warp shared-memory ring and reads them back
@@ -154,15 +147,12 @@ __device__ __forceinline__ void fwd_item(const FastFwdArgs& a, const int strip, 
     } else {
       RowT r;
       const auto* p4 = reinterpret_cast<const decltype(r.a)*>(srcT + (size_t)row_index(y) * a.src_pitch);
-      if constexpr (COH) { r.a = __ldcg(p4); r.b = __ldcg(p4 + 1); }
-      else { r.a = __ldg(p4); r.b = __ldg(p4 + 1); }
+      r.a = __ldg(p4); r.b = __ldg(p4 + 1);
       return r;
     }
   };
 
   VP1 v1;
-  VP2 v2;
-  T ll_odd[4] = {};  // buffered odd LL row for the second level
   const int ms = P0 - VP1::kWarm;          // first step: pair P0 is the first valid one
   const int mend = Plast + VP1::kDelay;    // last step
   RowT pa, pb, pc, pd;  // 32-bit input: rows of step m and (PCS_FWD_PF2) of step m + 1, loaded ahead
@@ -219,44 +209,7 @@ __device__ __forceinline__ void fwd_item(const FastFwdArgs& a, const int strip, 
     if (wlane && pr >= n0 && pr < n1) {
       const int oc1 = c0 >> 1;
       emit_pair<LOSSY, QS1, OT, T, 8>(lo, hi, out + (size_t)pr * a.pitch + oc1, out + (size_t)(pr + hh1) * a.pitch + oc1, hw1, a.q1, qs,
-                                 LEVELS == 1 && a.last, (LEVELS == 1 && !a.last) ? llbase + (size_t)pr * a.ll_pitch + oc1 : nullptr);
-    }
-    if constexpr (LEVELS == 2) {
-      // ---- second level in the same warp: LL row R arrives, 4 samples per lane (LL columns c0/2 .. c0/2+3) ----
-      const int R = pr;
-      if (R < 2 * M0) continue;
-      T row[4] = {lo[0], lo[2], lo[4], lo[6]};
-      if (R == 2 * M0) { v2.init(row); continue; }
-      const bool lastrow = R == hh1 - 1;  // bottom of the image: LL row hh1 does not exist
-      if (R & 1) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) ll_odd[j] = row[j];
-        if (!lastrow) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) row[j] = v2.xe[j];  // x[n] := x[n-2]
-      }
-      // normally one step (M = R/2 - 1); at the bottom row the last step and, for 9/7, the flush step
-      const int Mfirst = lastrow ? (R - 1) >> 1 : (R >> 1) - 1;
-      const int Mlast = lastrow ? Mfirst + VP2::kDelay : Mfirst;
-      for (int M = Mfirst; M <= Mlast; ++M) {
-        T lo2[4], hi2[4];
-        if constexpr (LOSSY) v2.step(ll_odd, row, M == 0, M == 1, M == hh2, lo2, hi2);
-        else v2.step(ll_odd, row, M == 0, lo2, hi2);
-        const int p2 = M - VP2::kDelay;
-        if (p2 < m2_0 || p2 >= m2_1) continue;
-        if constexpr (LOSSY) {
-          // the same lanes hold the second level's borders
-          if (pair_variant(p2, a.nW2, a.ls2)) { hfwd97<4, true>(lo2, kIK, left, right); hfwd97<4, true>(hi2, kK, left, right); }
-          else { hfwd97<4, false>(lo2, kIK, left, right); hfwd97<4, false>(hi2, kK, left, right); }
-        } else {
-          hfwd53<4>(lo2, left, right);
-          hfwd53<4>(hi2, left, right);
-        }
-        if (!wlane) continue;
-        const int oc2 = c0 >> 2;
-        emit_pair<LOSSY, QS1, OT, T, 4>(lo2, hi2, out + (size_t)p2 * a.pitch + oc2, out + (size_t)(p2 + hh2) * a.pitch + oc2, hw2, a.q2, qs,
-                                   a.last != 0, a.last ? nullptr : llbase + (size_t)p2 * a.ll_pitch + oc2);
-      }
+                                 a.last != 0, !a.last ? llbase + (size_t)pr * a.ll_pitch + oc1 : nullptr);
     }
   }
 }
@@ -264,30 +217,30 @@ __device__ __forceinline__ void fwd_item(const FastFwdArgs& a, const int strip, 
 #ifndef PCS_FWD_MINB_U8
 #define PCS_FWD_MINB_U8 4
 #endif
-template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS, bool QS1, bool RGB = false>
-__global__ void __launch_bounds__(128, LEVELS == 2 ? 3 : SRC_U8 ? PCS_FWD_MINB_U8 : PCS_FWD_MINB) dwt_forward_fused(const FastFwdArgs a) {
+template <bool LOSSY, typename OT, bool SRC_U8, bool QS1, bool RGB = false>
+__global__ void __launch_bounds__(128, SRC_U8 ? PCS_FWD_MINB_U8 : PCS_FWD_MINB) dwt_forward_fused(const FastFwdArgs a) {
   __shared__ __align__(16) FwdRing s_ring[SRC_U8 ? 4 : 1][RGB ? 3 : 1];
   const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (item >= a.nstrips * a.nchunks) return;
-  fwd_item<LOSSY, OT, SRC_U8, LEVELS, QS1, false, RGB>(a, item % a.nstrips, item / a.nstrips, blockIdx.y,
+  fwd_item<LOSSY, OT, SRC_U8, QS1, RGB>(a, item % a.nstrips, item / a.nstrips, blockIdx.y,
                                                        &s_ring[SRC_U8 ? (threadIdx.x >> 5) : 0][0]);
 }
 
 
 // The chunk length is chosen per kernel variant, for the number of CTAs that variant really keeps resident.
-template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS, bool QS1, bool RGB = false>
+template <bool LOSSY, typename OT, bool SRC_U8, bool QS1, bool RGB = false>
 void launch_k(FastFwdArgs a, int frames, cudaStream_t st) {
-  static const long long slots = resident_ctas(dwt_forward_fused<LOSSY, OT, SRC_U8, LEVELS, QS1, RGB>);
+  static const long long slots = resident_ctas(dwt_forward_fused<LOSSY, OT, SRC_U8, QS1, RGB>);
   const int hh1 = a.Hc >> 1;
-  a.rp = choose_rp(a.nstrips, hh1, frames, LEVELS == 2 ? 12 : 3, 4, slots);
+  a.rp = choose_rp(a.nstrips, hh1, frames, 3, 4, slots);
   a.nchunks = (hh1 + a.rp - 1) / a.rp;
   dim3 grid((a.nstrips * a.nchunks + 3) / 4, frames);
-  dwt_forward_fused<LOSSY, OT, SRC_U8, LEVELS, QS1, RGB><<<grid, 128, 0, st>>>(a);
+  dwt_forward_fused<LOSSY, OT, SRC_U8, QS1, RGB><<<grid, 128, 0, st>>>(a);
 }
-template <bool LOSSY, typename OT, bool SRC_U8, int LEVELS, bool RGB = false>
+template <bool LOSSY, typename OT, bool SRC_U8, bool RGB = false>
 void launch(const FastFwdArgs& a, int frames, cudaStream_t st) {
-  if (a.qs == 1.0f) launch_k<LOSSY, OT, SRC_U8, LEVELS, true, RGB>(a, frames, st);
-  else launch_k<LOSSY, OT, SRC_U8, LEVELS, false, RGB>(a, frames, st);
+  if (a.qs == 1.0f) launch_k<LOSSY, OT, SRC_U8, true, RGB>(a, frames, st);
+  else launch_k<LOSSY, OT, SRC_U8, false, RGB>(a, frames, st);
 }
 
 
@@ -559,9 +512,8 @@ void launch_inv(const FastInvArgs& a, int frames, bool qs1, cudaStream_t st) {
 
 // Can the streaming kernel take level `level` (1-based) of this geometry?  src = its input.
 bool dwt_forward_fast_ok(const void* src, const void* d_coeff, const void* ll, bool src_u8, int src_pitch, long long src_fstride, int H,
-                         int Wc, int Hc, int levels) {
+                         int Wc, int Hc) {
   if (Wc % 8 || Hc % 2 || Wc < 64 || Hc < 16) return false;
-  if (levels == 2 && (Wc % 32 || Hc % 16 || Hc < 64)) return false;
   if (reinterpret_cast<uintptr_t>(d_coeff) & 15) return false;
   if (ll && (reinterpret_cast<uintptr_t>(ll) & 15)) return false;
   if (src_u8) {
@@ -572,42 +524,36 @@ bool dwt_forward_fast_ok(const void* src, const void* d_coeff, const void* ll, b
   return true;
 }
 
-// `levels` (1 or 2) levels of the forward transform, starting at 1-based level `level`, in one launch.
+// Level `level` (1-based) of the forward transform in one launch.
 int dwt_forward_fast(const void* src, bool src_u8, long long src_fstride, int src_pitch, int H, int Wc, int Hc, void* d_coeff,
-                     long long out_fstride, int pitch, void* d_ll, long long ll_fstride, int ll_pitch, int level, int levels, int wl,
+                     long long out_fstride, int pitch, void* d_ll, long long ll_fstride, int ll_pitch, int level, int wl,
                      bool lossy, float qs, bool out_int, int frames, cudaStream_t st, bool rgb, long long comp_stride, int offset) {
   // rgb: src = planar u8 RGB frames (src_fstride per FRAME, comp_stride between colour planes), `frames` counts
-  // component planes (3 per frame) and the colour transform is fused into the load (one level only)
+  // component planes (3 per frame) and the colour transform is fused into the load
   FastFwdArgs a{};
   a.comp_stride = comp_stride; a.offset = offset;
   a.src = src; a.src_fstride = src_fstride; a.src_pitch = src_pitch; a.H = src_u8 ? H : Hc; a.Wc = Wc; a.Hc = Hc;
   a.out = d_coeff; a.out_fstride = out_fstride; a.pitch = pitch;
   a.ll = d_ll; a.ll_fstride = ll_fstride; a.ll_pitch = ll_pitch;
-  a.last = (level + levels - 1 == wl);
-  for (int i = 0; i < 4; ++i) { a.q1[i] = kQ[level - 1][i]; a.q2[i] = kQ[level < 10 ? level : 9][i]; }
+  a.last = (level == wl);
+  for (int i = 0; i < 4; ++i) a.q1[i] = kQ[level - 1][i];
   a.qs = qs;
   variant_params(Hc, &a.nW1, &a.ls1);
-  variant_params(Hc >> 1, &a.nW2, &a.ls2);
-  const int eff = (32 - 2 * levels) * 8;
-  a.nstrips = (Wc + eff - 1) / eff;
+  a.nstrips = (Wc + 239) / 240;  // 30 working lanes x 8 columns per strip
   if (src_u8) {
-    if (levels == 2) {
-      if (!lossy) launch<false, int, true, 2>(a, frames, st);
-      else if (out_int) launch<true, int, true, 2>(a, frames, st);
-      else launch<true, float, true, 2>(a, frames, st);
-    } else if (rgb) {
-      if (!lossy) launch<false, int, true, 1, true>(a, frames, st);
-      else if (out_int) launch<true, int, true, 1, true>(a, frames, st);
-      else launch<true, float, true, 1, true>(a, frames, st);
+    if (rgb) {
+      if (!lossy) launch<false, int, true, true>(a, frames, st);
+      else if (out_int) launch<true, int, true, true>(a, frames, st);
+      else launch<true, float, true, true>(a, frames, st);
     } else {
-      if (!lossy) launch<false, int, true, 1>(a, frames, st);
-      else if (out_int) launch<true, int, true, 1>(a, frames, st);
-      else launch<true, float, true, 1>(a, frames, st);
+      if (!lossy) launch<false, int, true>(a, frames, st);
+      else if (out_int) launch<true, int, true>(a, frames, st);
+      else launch<true, float, true>(a, frames, st);
     }
   } else {
-    if (!lossy) launch<false, int, false, 1>(a, frames, st);
-    else if (out_int) launch<true, int, false, 1>(a, frames, st);
-    else launch<true, float, false, 1>(a, frames, st);
+    if (!lossy) launch<false, int, false>(a, frames, st);
+    else if (out_int) launch<true, int, false>(a, frames, st);
+    else launch<true, float, false>(a, frames, st);
   }
   ++g_launches;
   return (int)cudaGetLastError();
