@@ -48,7 +48,7 @@ WORKLOADS = {
                  desc="configs[1]: 4096x4096 8-bit grey, lossy 9/7 qs=1.0, wl=5, 64x64 codeblocks"),
     "cfg3": dict(W=7680, H=4320, wl=6, lossy=0, qs=1.0, lut="n1_lossless", frames=2, batch=2, scaling="weak",
                  desc="configs[2]: 7680x4320 8-bit grey, lossless 5/3, wl=6, 64x64 codeblocks"),
-    "cfg4": dict(W=3840, H=2160, wl=5, lossy=1, qs=1.0, lut="video_lossy", frames=600, batch=32, scaling="strong",
+    "cfg4": dict(W=3840, H=2160, wl=5, lossy=1, qs=1.0, lut="video_lossy", frames=600, batch=96, scaling="strong",
                  desc="configs[3]: 3840x2160 8-bit grey video, 600 frames, lossy 9/7 qs=1, wl=5, frame-sharded"),
     "cfg5": dict(W=32768, H=4096, wl=5, lossy=0, qs=1.0, lut="n1_lossless", frames=8, batch=2, scaling="strong", bands=True,
                  desc="configs[4]: 32768x32768 8-bit grey still as 8 row bands of 32768x4096, lossless 5/3, wl=5, band-sharded"),
