@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(kThreads, PCS_FUSED_MINB) dwt_forward_l12_kern
   const int Plast = min(2 * (m2_1 - 1 + VP::kDelay) + 2, hh1 - 1);  // last one (level 2 reads one or three rows past n1)
   const int hand = 32 * (nprod + ncons);  // threads that meet at a hand-over barrier
   const float qs = a.qs;
-  OT* const out = static_cast<OT*>(a.out) + (size_t)frame * a.out_fstride;
+  OT* out = static_cast<OT*>(a.out) + (size_t)frame * a.out_fstride;
+  asm volatile("" : "+l"(out));  // keep the frame's base pointer in registers: the compiler otherwise rebuilds it from the parameters at every store
 
   if (warp < kProd) {
     // =============================== producer: level 1 on 256 pixel columns ===============================
